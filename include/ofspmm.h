@@ -1,0 +1,176 @@
+/*
+ * ofspmm.h — C ABI of the B200-native SpMM operator library (libofspmm_b200.so).
+ *
+ * This is the drop-in boundary for the OneFlow user op `spmm_csr` (+ `spmm_csr_grad_b`,
+ * `sddmm_csr`): the body of `user_op::OpKernel::Compute(KernelComputeContext*)`
+ * (reference: oneflow/core/framework/op_kernel.h:305-308) pulls raw pointers, shapes, attrs and
+ * the `cudaStream_t` out of `ctx` and calls the functions below (glue sources:
+ * of-spmm_b200/oneflow_glue/, binding walk-through: INTEGRATION.md).
+ *
+ * Conventions — each mirrors a rule of the reference's kernel contract:
+ *   - plain pointers and sizes only; every data pointer is a DEVICE pointer unless the name ends
+ *     in `_host`; no torch / OneFlow types;
+ *   - nothing here allocates or frees device memory and nothing synchronises the stream or the
+ *     device: temporary storage is a caller-owned workspace sized by the matching
+ *     `*_workspace_bytes()` query, which plays the role of `SetInferTmpSizeFn`
+ *     (oneflow/core/framework/user_op_kernel_registry.h:60,90;
+ *      oneflow/user/kernels/unsorted_segment_sum_kernel.cpp:191-202);
+ *   - work is enqueued on the given stream and the call returns (async contract of
+ *     oneflow/core/framework/op_kernel.h:311); all calls are CUDA-graph capturable
+ *     (user_op::CudaGraphSupport, oneflow/core/kernel/cuda_graph_support.h:28-42);
+ *   - no global mutable state, no cudaSetDevice: the library is re-entrant and runs on whatever
+ *     device is current on the calling thread (oneflow/core/vm/virtual_machine.cpp:69-77);
+ *   - errors are int status codes; no C++ exception crosses the boundary.  The glue turns a
+ *     non-zero status into CHECK / LOG(FATAL) like OF_CUDA_CHECK does
+ *     (oneflow/core/device/cuda_util.h:54-57);
+ *   - outputs are fully overwritten (the framework does not zero them,
+ *     oneflow/core/vm/op_call_instruction_policy.cpp:78-85);
+ *   - column indices outside [0, cols) are skipped, as the reference's segment-sum skips
+ *     out-of-range ids (oneflow/user/kernels/unsorted_segment_sum_kernel_util.cpp:35-39).
+ *
+ * dtype codes reuse OneFlow's DataType numbering (oneflow/core/common/data_type.proto:4-17) so
+ * the glue passes `tensor->data_type()` through unchanged.
+ */
+#ifndef OFSPMM_H_
+#define OFSPMM_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define OFSPMM_API
+#else
+#define OFSPMM_API __attribute__((visibility("default")))
+#endif
+
+/* Same object as cudaStream_t (CUstream_st*); spelled out so C callers need no CUDA headers. */
+typedef struct CUstream_st* ofspmm_stream_t;
+
+/* oneflow::DataType values (data_type.proto:4-17). */
+enum {
+  OFSPMM_DTYPE_FLOAT = 2,     /* kFloat    */
+  OFSPMM_DTYPE_INT32 = 5,     /* kInt32    */
+  OFSPMM_DTYPE_INT64 = 6,     /* kInt64    */
+  OFSPMM_DTYPE_BFLOAT16 = 11  /* kBFloat16 */
+};
+
+enum {
+  OFSPMM_OK = 0,
+  OFSPMM_ERR_INVALID_ARG = 1,       /* null pointer, negative size, inconsistent shape        */
+  OFSPMM_ERR_UNSUPPORTED_DTYPE = 2, /* dtype combination without a kernel                      */
+  OFSPMM_ERR_WORKSPACE = 3,         /* workspace null / misaligned / smaller than the query    */
+  OFSPMM_ERR_CUDA = 4,              /* a CUDA runtime call or launch failed (cudaGetLastError) */
+  OFSPMM_ERR_TOO_LARGE = 5,         /* rows or nnz >= 2^31 (row offsets are kept in 32 bits)   */
+  OFSPMM_ERR_NO_DEVICE = 6          /* no sm_100 device current on this thread                 */
+};
+
+/* A (rows × cols) in CSR.  crow has rows+1 entries, col / val have nnz entries.
+ * idx_dtype ∈ {INT32, INT64} applies to both crow and col (INDEX_DATA_TYPE_SEQ,
+ * oneflow/core/common/data_type_seq.h:50-52).  val_dtype ∈ {FLOAT, BFLOAT16}; BFLOAT16 values are
+ * only accepted together with a BFLOAT16 dense operand.  `val` may be NULL for ofspmm_sddmm. */
+typedef struct ofspmm_csr {
+  int64_t rows;
+  int64_t cols;
+  int64_t nnz;
+  const void* crow;
+  const void* col;
+  const void* val;
+  int32_t idx_dtype;
+  int32_t val_dtype;
+} ofspmm_csr;
+
+/* ---- SpMM forward: C[rows × n] = A · B[cols × n]  (replaces the `spmm_csr` kernel body; data
+ * movement analogue in the reference: GatherForwardGpu + UnsortedSegmentRowSumGpu,
+ * oneflow/user/kernels/gather_kernel_util.cu:28-41,
+ * oneflow/user/kernels/unsorted_segment_sum_kernel_util.cu:96-117).
+ * B and C are row-major, contiguous, of `dense_dtype` ∈ {FLOAT, BFLOAT16}; accumulation is fp32,
+ * bf16 outputs are rounded once.  Deterministic: the summation order depends only on
+ * (crow, n, dtype), never on scheduling. */
+OFSPMM_API size_t ofspmm_fwd_workspace_bytes(int64_t rows, int64_t cols, int64_t nnz, int64_t n,
+                                             int dense_dtype);
+OFSPMM_API int ofspmm_fwd(const ofspmm_csr* A, const void* B, void* C, int64_t n, int dense_dtype,
+                          void* workspace, size_t workspace_bytes, ofspmm_stream_t stream);
+
+/* ---- Backward wrt the dense operand: dB[cols × n] = A^T · dY[rows × n]  (replaces
+ * `spmm_csr_grad_b`; reference analogue = memset + atomic scatter-add,
+ * oneflow/user/kernels/unsorted_segment_sum_kernel.cpp:91-117,
+ * oneflow/user/kernels/embedding_kernel_util.cu:50-64).
+ * Two routes:
+ *   (1) `At` != NULL: a CSR of A^T built once by ofspmm_csr_transpose and kept in the op's
+ *       OpKernelState; runs the forward kernel on it — deterministic, no atomics;
+ *   (2) `At` == NULL: vector-atomic scatter (red.global.add.v4.f32) into an fp32 accumulator
+ *       (dB itself for FLOAT, the workspace for BFLOAT16) — order-nondeterministic like the
+ *       reference's cuda::atomic::Add path. */
+OFSPMM_API size_t ofspmm_bwd_b_workspace_bytes(int64_t rows, int64_t cols, int64_t nnz, int64_t n,
+                                               int dense_dtype, int have_transpose);
+OFSPMM_API int ofspmm_bwd_b(const ofspmm_csr* A, const ofspmm_csr* At, const void* dY, void* dB,
+                            int64_t n, int dense_dtype, void* workspace, size_t workspace_bytes,
+                            ofspmm_stream_t stream);
+
+/* ---- SDDMM value gradient: dval[p] = <dY[i,:], B[col[p],:]> for every stored entry p of row i
+ * (replaces `sddmm_csr`; no reference analogue).  dval has `val_dtype` of A
+ * (FLOAT, or BFLOAT16 with a BFLOAT16 dense operand); A->val is not read. */
+OFSPMM_API size_t ofspmm_sddmm_workspace_bytes(int64_t rows, int64_t cols, int64_t nnz, int64_t n,
+                                               int dense_dtype);
+OFSPMM_API int ofspmm_sddmm(const ofspmm_csr* A, const void* dY, const void* B, void* dval,
+                            int64_t n, int dense_dtype, void* workspace, size_t workspace_bytes,
+                            ofspmm_stream_t stream);
+
+/* ---- Merge-path / nnz-balanced partitioner.  Splits the merged list of
+ * (row-end, non-zero) items into `parts` equal spans; writes parts+1 split points
+ * (out_row[k], out_nz[k]) with out_row[k] + out_nz[k] = min(k·ceil((rows+nnz)/parts), rows+nnz).
+ * Device version (outputs are device int64 arrays) and its host twin (all pointers host) must
+ * agree bit-for-bit; contrast the reference's equal-count BalancedSplitter
+ * (oneflow/core/common/balanced_splitter.cpp:20-39). */
+OFSPMM_API int ofspmm_partition(const void* crow, int idx_dtype, int64_t rows, int64_t nnz,
+                                int64_t parts, int64_t* out_row, int64_t* out_nz,
+                                ofspmm_stream_t stream);
+OFSPMM_API int ofspmm_partition_host(const void* crow_host, int idx_dtype, int64_t rows,
+                                     int64_t nnz, int64_t parts, int64_t* out_row_host,
+                                     int64_t* out_nz_host);
+
+/* ---- Row-length histogram in log2 buckets: hist[0] = empty rows, hist[b] = rows with
+ * 2^(b-1) <= len < 2^b (b = 1..31).  32 device int64 counters, overwritten.  Feeds the kernel
+ * variant choice. */
+OFSPMM_API int ofspmm_row_hist(const void* crow, int idx_dtype, int64_t rows, int64_t* hist32,
+                               ofspmm_stream_t stream);
+
+/* ---- Device CSR → CSR-of-A^T (stable: entries of one column keep ascending row order), the
+ * one-off the op's OpKernelState runs for route (1) of ofspmm_bwd_b.  Output arrays are caller
+ * owned: t_crow[cols+1], t_col[nnz] of A->idx_dtype, t_val[nnz] of A->val_dtype (may be NULL
+ * together with A->val), t_perm[nnz] int32/int64 like idx (may be NULL) = source position of each
+ * transposed entry. */
+OFSPMM_API size_t ofspmm_csr_transpose_workspace_bytes(int64_t rows, int64_t cols, int64_t nnz,
+                                                       int idx_dtype);
+OFSPMM_API int ofspmm_csr_transpose(const ofspmm_csr* A, void* t_crow, void* t_col, void* t_val,
+                                    void* t_perm, void* workspace, size_t workspace_bytes,
+                                    ofspmm_stream_t stream);
+
+/* ---- Host-buffer convenience entry (what a CPU-tensor caller / the e2e benchmark uses): copies
+ * the CSR arrays and B from HOST memory (pinned recommended) to device staging carved from
+ * `workspace`, runs ofspmm_fwd, copies C back to `C_host`, all on `stream`; the caller
+ * synchronises the stream.  Workspace = ofspmm_fwd_host_workspace_bytes(...). */
+OFSPMM_API size_t ofspmm_fwd_host_workspace_bytes(int64_t rows, int64_t cols, int64_t nnz,
+                                                  int64_t n, int dense_dtype, int idx_dtype,
+                                                  int val_dtype);
+OFSPMM_API int ofspmm_fwd_host(const ofspmm_csr* A_host, const void* B_host, void* C_host,
+                               int64_t n, int dense_dtype, void* workspace, size_t workspace_bytes,
+                               ofspmm_stream_t stream);
+
+/* ---- Introspection. */
+OFSPMM_API const char* ofspmm_strerror(int status);
+OFSPMM_API int ofspmm_version(void);
+/* Number of kernels the library has launched on this process so far (monotonic, relaxed atomic);
+ * the benchmark reports the delta over its timed region as `gpu_launches`. */
+OFSPMM_API uint64_t ofspmm_launch_count(void);
+/* Name of the kernel variant ofspmm_fwd would pick for this shape (static string). */
+OFSPMM_API const char* ofspmm_fwd_variant(int64_t rows, int64_t nnz, int64_t n, int dense_dtype);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OFSPMM_H_ */

@@ -1,0 +1,104 @@
+"""ctypes binding of libofspmm_b200.so (include/ofspmm.h).
+
+The product path has no CPU fallback: if the CUDA library is missing this module raises
+``OfspmmLibraryError`` at load time, and every status code other than OFSPMM_OK raises
+``OfspmmError`` — the Python mirror of the glue's CHECK / LOG(FATAL) on a non-zero status
+(reference convention: oneflow/core/device/cuda_util.h:54-57).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libofspmm_b200.so")
+
+DTYPE_FLOAT, DTYPE_INT32, DTYPE_INT64, DTYPE_BFLOAT16 = 2, 5, 6, 11
+
+EXPORTS = (
+    "ofspmm_fwd_workspace_bytes", "ofspmm_fwd", "ofspmm_bwd_b_workspace_bytes", "ofspmm_bwd_b",
+    "ofspmm_sddmm_workspace_bytes", "ofspmm_sddmm", "ofspmm_partition", "ofspmm_partition_host",
+    "ofspmm_row_hist", "ofspmm_csr_transpose_workspace_bytes", "ofspmm_csr_transpose",
+    "ofspmm_fwd_host_workspace_bytes", "ofspmm_fwd_host", "ofspmm_strerror", "ofspmm_version",
+    "ofspmm_launch_count", "ofspmm_fwd_variant",
+)
+
+
+class OfspmmLibraryError(ImportError):
+    pass
+
+
+class OfspmmError(RuntimeError):
+    def __init__(self, status: int, where: str):
+        self.status = status
+        msg = lib().ofspmm_strerror(status).decode()
+        super().__init__(f"{where}: ofspmm status {status} ({msg})")
+
+
+class CsrStruct(ctypes.Structure):
+    """struct ofspmm_csr (include/ofspmm.h)."""
+    _fields_ = [("rows", ctypes.c_int64), ("cols", ctypes.c_int64), ("nnz", ctypes.c_int64),
+                ("crow", ctypes.c_void_p), ("col", ctypes.c_void_p), ("val", ctypes.c_void_p),
+                ("idx_dtype", ctypes.c_int32), ("val_dtype", ctypes.c_int32)]
+
+
+_LIB = None
+
+
+def lib() -> ctypes.CDLL:
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(LIB_PATH):
+        raise OfspmmLibraryError(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(or `make -C of-spmm_b200/csrc`).  There is no CPU fallback on this path.")
+    try:
+        L = ctypes.CDLL(LIB_PATH)
+    except OSError as e:  # pragma: no cover
+        raise OfspmmLibraryError(f"cannot load {LIB_PATH}: {e}") from e
+    i64, i32, vp, sz = ctypes.c_int64, ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t
+    csr_p = ctypes.POINTER(CsrStruct)
+    L.ofspmm_fwd_workspace_bytes.argtypes = [i64, i64, i64, i64, i32]
+    L.ofspmm_fwd_workspace_bytes.restype = sz
+    L.ofspmm_fwd.argtypes = [csr_p, vp, vp, i64, i32, vp, sz, vp]
+    L.ofspmm_fwd.restype = i32
+    L.ofspmm_bwd_b_workspace_bytes.argtypes = [i64, i64, i64, i64, i32, i32]
+    L.ofspmm_bwd_b_workspace_bytes.restype = sz
+    L.ofspmm_bwd_b.argtypes = [csr_p, csr_p, vp, vp, i64, i32, vp, sz, vp]
+    L.ofspmm_bwd_b.restype = i32
+    L.ofspmm_sddmm_workspace_bytes.argtypes = [i64, i64, i64, i64, i32]
+    L.ofspmm_sddmm_workspace_bytes.restype = sz
+    L.ofspmm_sddmm.argtypes = [csr_p, vp, vp, vp, i64, i32, vp, sz, vp]
+    L.ofspmm_sddmm.restype = i32
+    L.ofspmm_partition.argtypes = [vp, i32, i64, i64, i64, vp, vp, vp]
+    L.ofspmm_partition.restype = i32
+    L.ofspmm_partition_host.argtypes = [vp, i32, i64, i64, i64, vp, vp]
+    L.ofspmm_partition_host.restype = i32
+    L.ofspmm_row_hist.argtypes = [vp, i32, i64, vp, vp]
+    L.ofspmm_row_hist.restype = i32
+    L.ofspmm_csr_transpose_workspace_bytes.argtypes = [i64, i64, i64, i32]
+    L.ofspmm_csr_transpose_workspace_bytes.restype = sz
+    L.ofspmm_csr_transpose.argtypes = [csr_p, vp, vp, vp, vp, vp, sz, vp]
+    L.ofspmm_csr_transpose.restype = i32
+    L.ofspmm_fwd_host_workspace_bytes.argtypes = [i64, i64, i64, i64, i32, i32, i32]
+    L.ofspmm_fwd_host_workspace_bytes.restype = sz
+    L.ofspmm_fwd_host.argtypes = [csr_p, vp, vp, i64, i32, vp, sz, vp]
+    L.ofspmm_fwd_host.restype = i32
+    L.ofspmm_strerror.argtypes = [i32]
+    L.ofspmm_strerror.restype = ctypes.c_char_p
+    L.ofspmm_version.restype = i32
+    L.ofspmm_launch_count.restype = ctypes.c_uint64
+    L.ofspmm_fwd_variant.argtypes = [i64, i64, i64, i32]
+    L.ofspmm_fwd_variant.restype = ctypes.c_char_p
+    _LIB = L
+    return L
+
+
+def check(status: int, where: str) -> None:
+    if status != 0:
+        raise OfspmmError(status, where)
+
+
+def launch_count() -> int:
+    return int(lib().ofspmm_launch_count())

@@ -1,0 +1,121 @@
+// fwd.cu — variant selection and launch of the merge-path SpMM kernels (spmm_kernels.cuh).
+#include "internal.h"
+#include "spmm_kernels.cuh"
+
+namespace ofspmm {
+
+namespace {
+
+template <typename DT, typename ValT, typename IdxT, int VEC, int LPR, int CH>
+int launch_one(const FwdParams& p, int panels, cudaStream_t stream) {
+  constexpr int ITEMS = kTaskItems;
+  constexpr int WARPS = kWarpsPerCta;
+  auto kern = spmm_merge_kernel<DT, ValT, IdxT, VEC, LPR, CH, ITEMS, WARPS>;
+  const size_t smem = sizeof(TaskStage<IdxT, ValT, ITEMS>) * WARPS + sizeof(uint64_t) * WARPS;
+  OFSPMM_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  DevInfo dev;
+  if (int rc = get_dev_info(&dev)) return rc;
+  int occ = 0;
+  OFSPMM_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, WARPS * 32, smem));
+  if (occ < 1) return OFSPMM_ERR_CUDA;
+  // persistent grid: a whole number of CTAs per SM (148 SMs on B200), never more than the tasks
+  const int64_t ctas_needed = (static_cast<int64_t>(p.P) + WARPS - 1) / WARPS;
+  int64_t per_panel = static_cast<int64_t>(dev.sms) * occ / panels;
+  if (per_panel < dev.sms) per_panel = dev.sms;
+  const int gx = static_cast<int>(ctas_needed < per_panel ? ctas_needed : per_panel);
+  kern<<<dim3(gx, panels), WARPS * 32, smem, stream>>>(p);
+  count_launch();
+  OFSPMM_CUDA_OK(cudaGetLastError());
+  // stitch rows that span several tasks
+  auto fix = spmm_fixup_kernel<DT, IdxT, VEC, WARPS>;
+  fix<<<static_cast<unsigned>(ctas_needed), WARPS * 32, 0, stream>>>(p);
+  count_launch();
+  OFSPMM_CUDA_OK(cudaGetLastError());
+  return OFSPMM_OK;
+}
+
+template <typename DT, typename ValT, typename IdxT>
+int launch_typed(const FwdParams& p, bool aligned, cudaStream_t stream) {
+  constexpr int VECW = 16 / sizeof(DT);
+  const int n = p.n;
+  if (aligned && n % VECW == 0) {
+    const int nvec = n / VECW;
+    if (nvec <= 8) return launch_one<DT, ValT, IdxT, VECW, 8, 1>(p, 1, stream);
+    if (nvec <= 16) return launch_one<DT, ValT, IdxT, VECW, 16, 1>(p, 1, stream);
+    if (nvec <= 32) return launch_one<DT, ValT, IdxT, VECW, 32, 1>(p, 1, stream);
+    if (nvec <= 64) return launch_one<DT, ValT, IdxT, VECW, 32, 2>(p, 1, stream);
+    return launch_one<DT, ValT, IdxT, VECW, 32, 4>(p, (nvec + 127) / 128, stream);
+  }
+  if (n <= 32) return launch_one<DT, ValT, IdxT, 1, 32, 1>(p, 1, stream);
+  if (n <= 64) return launch_one<DT, ValT, IdxT, 1, 32, 2>(p, 1, stream);
+  if (n <= 128) return launch_one<DT, ValT, IdxT, 1, 32, 4>(p, 1, stream);
+  return launch_one<DT, ValT, IdxT, 1, 32, 8>(p, (n + 255) / 256, stream);
+}
+
+template <typename IdxT>
+int launch_idx(const FwdParams& p, int dense_dtype, int val_dtype, bool aligned, cudaStream_t stream) {
+  if (dense_dtype == OFSPMM_DTYPE_FLOAT && val_dtype == OFSPMM_DTYPE_FLOAT)
+    return launch_typed<float, float, IdxT>(p, aligned, stream);
+  if (dense_dtype == OFSPMM_DTYPE_BFLOAT16 && val_dtype == OFSPMM_DTYPE_FLOAT)
+    return launch_typed<__nv_bfloat16, float, IdxT>(p, aligned, stream);
+  if (dense_dtype == OFSPMM_DTYPE_BFLOAT16 && val_dtype == OFSPMM_DTYPE_BFLOAT16)
+    return launch_typed<__nv_bfloat16, __nv_bfloat16, IdxT>(p, aligned, stream);
+  return OFSPMM_ERR_UNSUPPORTED_DTYPE;
+}
+
+}  // namespace
+
+int launch_task_partition(const void* crow, int idx_dtype, int64_t rows, int64_t nnz, int64_t P,
+                          void* part, cudaStream_t stream) {
+  const int threads = 256;
+  const unsigned blocks = static_cast<unsigned>((P + 1 + threads - 1) / threads);
+  if (idx_dtype == OFSPMM_DTYPE_INT32) {
+    task_partition_kernel<int32_t><<<blocks, threads, 0, stream>>>(
+        static_cast<const int32_t*>(crow), static_cast<int>(rows), static_cast<int>(nnz), kTaskItems,
+        static_cast<int>(P), static_cast<int2*>(part));
+  } else {
+    task_partition_kernel<int64_t><<<blocks, threads, 0, stream>>>(
+        static_cast<const int64_t*>(crow), static_cast<int>(rows), static_cast<int>(nnz), kTaskItems,
+        static_cast<int>(P), static_cast<int2*>(part));
+  }
+  count_launch();
+  OFSPMM_CUDA_OK(cudaGetLastError());
+  return OFSPMM_OK;
+}
+
+int launch_fwd(const ofspmm_csr* A, const void* B, void* C, int64_t n, int dense_dtype,
+               const void* part, float* carry, float* head, int64_t P, cudaStream_t stream) {
+  FwdParams p;
+  p.crow = A->crow;
+  p.col = A->col;
+  p.val = A->val;
+  p.B = B;
+  p.C = C;
+  p.part = static_cast<const int2*>(part);
+  p.carry = carry;
+  p.head = head;
+  p.cols = A->cols;
+  p.rows = static_cast<int>(A->rows);
+  p.nnz = static_cast<int>(A->nnz);
+  p.n = static_cast<int>(n);
+  p.P = static_cast<int>(P);
+  const bool aligned = ((reinterpret_cast<uintptr_t>(B) | reinterpret_cast<uintptr_t>(C)) & 15) == 0;
+  if (A->idx_dtype == OFSPMM_DTYPE_INT32) return launch_idx<int32_t>(p, dense_dtype, A->val_dtype, aligned, stream);
+  if (A->idx_dtype == OFSPMM_DTYPE_INT64) return launch_idx<int64_t>(p, dense_dtype, A->val_dtype, aligned, stream);
+  return OFSPMM_ERR_UNSUPPORTED_DTYPE;
+}
+
+const char* fwd_variant_name(int64_t n, int dense_dtype, bool aligned) {
+  const int vecw = dense_dtype == OFSPMM_DTYPE_BFLOAT16 ? 8 : 4;
+  if (aligned && n % vecw == 0) {
+    const int64_t nvec = n / vecw;
+    if (nvec <= 8) return "merge_path/vector-per-row(8 lanes x 16B, 4 nnz per step)";
+    if (nvec <= 16) return "merge_path/vector-per-row(16 lanes x 16B, 2 nnz per step)";
+    if (nvec <= 32) return "merge_path/warp-per-row(32 lanes x 16B)";
+    if (nvec <= 64) return "merge_path/warp-per-row(32 lanes x 2 x 16B)";
+    return "merge_path/warp-per-row(32 lanes x 4 x 16B, column panels)";
+  }
+  return "merge_path/warp-per-row(scalar lanes, unaligned n)";
+}
+
+}  // namespace ofspmm

@@ -1,0 +1,125 @@
+"""CPU tests of the host side: the C-ABI library loads and exports every symbol include/ofspmm.h
+declares, size queries and argument validation work without a GPU, the host partitioner is
+bit-exact with the oracle, and the op mirror raises the reference-style inference errors."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import ofspmm_b200 as ofs
+from oracle import oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_lib = __import__("importlib").import_module("of-spmm_b200._lib")
+
+
+def _declared_symbols():
+    src = open(os.path.join(ROOT, "include", "ofspmm.h")).read()
+    return sorted(set(re.findall(r"OFSPMM_API[^;]*?\b(ofspmm_\w+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    names = _declared_symbols()
+    assert len(names) >= 17
+    L = ctypes.CDLL(ofs.LIB_PATH)
+    for n in names:
+        assert hasattr(L, n), f"{n} declared in include/ofspmm.h but not exported"
+    assert set(names) == set(_lib.EXPORTS)
+
+
+def test_library_has_sm100a_code_only():
+    import subprocess
+    out = subprocess.run(["cuobjdump", "-lelf", ofs.LIB_PATH], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_\d+a?", out))
+    assert archs == {"sm_100a"}, archs
+
+
+def test_version_strerror_and_queries():
+    L = _lib.lib()
+    assert L.ofspmm_version() == 100
+    assert L.ofspmm_strerror(0) == b"ok"
+    assert b"workspace" in L.ofspmm_strerror(3)
+    # workspace grows with the task count and the dense width; bf16 adds the fp32 head buffer
+    w32 = L.ofspmm_fwd_workspace_bytes(1000, 1000, 100000, 128, 2)
+    wbf = L.ofspmm_fwd_workspace_bytes(1000, 1000, 100000, 128, 11)
+    assert 0 < w32 < wbf
+    tasks = -(-(1000 + 100000) // 256)
+    assert w32 >= (tasks + 1) * 8 + tasks * 128 * 4
+    assert L.ofspmm_sddmm_workspace_bytes(1000, 1000, 100000, 128, 2) >= (tasks + 1) * 8
+    assert b"warp-per-row" in L.ofspmm_fwd_variant(1, 1, 128, 2)
+    assert b"vector-per-row" in L.ofspmm_fwd_variant(1, 1, 64, 2)
+
+
+def test_argument_validation_without_gpu():
+    L = _lib.lib()
+    crow = np.zeros(3, np.int32)
+    A = _lib.CsrStruct(2, 2, 0, crow.ctypes.data, None, None, 5, 2)
+    assert L.ofspmm_fwd(None, None, None, 4, 2, None, 0, None) == 1            # null csr
+    A.rows = -1
+    assert L.ofspmm_fwd(ctypes.byref(A), None, None, 4, 2, None, 0, None) == 1  # negative size
+    A.rows, A.idx_dtype = 2, 9
+    assert L.ofspmm_fwd(ctypes.byref(A), None, None, 4, 2, None, 0, None) == 2  # kFloat16 index
+    A.idx_dtype, A.val_dtype = 5, 11
+    assert L.ofspmm_fwd(ctypes.byref(A), None, None, 4, 2, None, 0, None) == 2  # bf16 val + fp32 dense
+    A.val_dtype, A.nnz = 2, 2 ** 31
+    assert L.ofspmm_fwd(ctypes.byref(A), None, None, 4, 2, None, 0, None) == 5  # too large
+    assert L.ofspmm_partition_host(None, 5, 1, 1, 1, None, None) == 1
+
+
+@pytest.mark.parametrize("idx", [np.int32, np.int64])
+@pytest.mark.parametrize("parts", [1, 2, 5, 8, 333])
+def test_partition_host_bit_exact_vs_oracle(idx, parts):
+    A = ofs.graphs.rmat_csr(11, 8, seed=4)
+    crow = A.crow.numpy().astype(idx)
+    r0, z0 = O.merge_path_partition(crow, parts)
+    r1, z1 = ofs.merge_path_partition_host(torch.from_numpy(crow), A.nnz, parts)
+    assert np.array_equal(r0, r1.numpy()) and np.array_equal(z0, z1.numpy())
+    assert np.array_equal(O.row_blocks(crow, parts), ofs.row_blocks(torch.from_numpy(crow), A.nnz, parts).numpy())
+
+
+def test_infer_errors_mirror_reference_checks():
+    crow = torch.tensor([0, 1, 2], dtype=torch.int32)
+    col = torch.tensor([0, 1], dtype=torch.int32)
+    val = torch.ones(2)
+    b = torch.ones(2, 4)
+    ops = __import__("importlib").import_module("of-spmm_b200.ops")
+    assert ops.infer_spmm_csr(crow, col, val, b, 2, 2) == ((2, 4), torch.float32)
+    with pytest.raises(ofs.OpInferError, match="a_rows\\+1"):
+        ops.infer_spmm_csr(crow, col, val, b, 3, 2)
+    with pytest.raises(ofs.OpInferError, match="a_cols"):
+        ops.infer_spmm_csr(crow, col, val, b, 2, 5)
+    with pytest.raises(ofs.OpInferError, match="index dtype"):
+        ops.infer_spmm_csr(crow.float(), col, val, b, 2, 2)
+    with pytest.raises(ofs.OpInferError, match="no registered kernel"):
+        ops.infer_spmm_csr(crow, col, val, b.double(), 2, 2)
+    with pytest.raises(ofs.OpInferError, match="bfloat16 a_val"):
+        ops.infer_spmm_csr(crow, col, val.bfloat16(), b, 2, 2)
+    # exactly one kernel is registered and it is the CUDA one: CPU tensors do not fall back
+    with pytest.raises(ofs.OpInferError, match="no kernel registered for device type cpu"):
+        ofs.spmm_csr(crow, col, val, b, 2, 2)
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    monkeypatch.setattr(_lib, "_LIB", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libofspmm_b200.so")
+    with pytest.raises(ofs.OfspmmLibraryError, match="no CPU fallback"):
+        _lib.lib()
+
+
+def test_generators_are_seeded_and_well_formed():
+    for A in (ofs.graphs.uniform_csr(512, 512, 0.02, seed=1), ofs.graphs.reddit_like(256, seed=2),
+              ofs.graphs.products_like(512, seed=3), ofs.graphs.rmat_csr(10, 16, seed=4)):
+        crow, col = A.crow.long(), A.col.long()
+        assert crow[0] == 0 and crow[-1] == A.nnz and (crow[1:] >= crow[:-1]).all()
+        rows = torch.repeat_interleave(torch.arange(A.rows), A.row_lengths())
+        key = rows * A.cols + col
+        assert (key[1:] > key[:-1]).all()                # sorted + unique within rows
+        assert col.min() >= 0 and col.max() < A.cols
+    a = ofs.graphs.reddit_like(256, seed=2)
+    b = ofs.graphs.reddit_like(256, seed=2)
+    assert torch.equal(a.col, b.col) and torch.equal(a.val, b.val)
+    full = ofs.graphs.expected_alg_bytes(232965, 232965, 114615892, 128, 4)
+    assert abs(full["m2"] / 1e9 - 59.72) < 0.01 and abs(full["m1"] / 1e9 - 1.156) < 0.001
