@@ -94,6 +94,14 @@ OFSPMM_API size_t ofspmm_fwd_workspace_bytes(int64_t rows, int64_t cols, int64_t
                                              int dense_dtype);
 OFSPMM_API int ofspmm_fwd(const ofspmm_csr* A, const void* B, void* C, int64_t n, int dense_dtype,
                           void* workspace, size_t workspace_bytes, ofspmm_stream_t stream);
+/* Same with explicit row strides (in elements, >= n): B is cols × n inside a row-major buffer of
+ * leading dimension ldb, C likewise with ldc — a column slice of a wider matrix, as
+ * `user_op::Tensor::stride()` describes it (oneflow/core/framework/user_op_tensor.h:31-72).  Used
+ * by the multi-GPU path to compute / write one column panel of the dense operands at a time
+ * while the next panel's all-gather is in flight.  Workspace = ofspmm_fwd_workspace_bytes(n). */
+OFSPMM_API int ofspmm_fwd_strided(const ofspmm_csr* A, const void* B, int64_t ldb, void* C,
+                                  int64_t ldc, int64_t n, int dense_dtype, void* workspace,
+                                  size_t workspace_bytes, ofspmm_stream_t stream);
 
 /* ---- Backward wrt the dense operand: dB[cols × n] = A^T · dY[rows × n]  (replaces
  * `spmm_csr_grad_b`; reference analogue = memset + atomic scatter-add,

@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libofspmm_b200.so")
 DTYPE_FLOAT, DTYPE_INT32, DTYPE_INT64, DTYPE_BFLOAT16 = 2, 5, 6, 11
 
 EXPORTS = (
-    "ofspmm_fwd_workspace_bytes", "ofspmm_fwd", "ofspmm_bwd_b_workspace_bytes", "ofspmm_bwd_b",
+    "ofspmm_fwd_workspace_bytes", "ofspmm_fwd", "ofspmm_fwd_strided", "ofspmm_bwd_b_workspace_bytes", "ofspmm_bwd_b",
     "ofspmm_sddmm_workspace_bytes", "ofspmm_sddmm", "ofspmm_partition", "ofspmm_partition_host",
     "ofspmm_row_hist", "ofspmm_csr_transpose_workspace_bytes", "ofspmm_csr_transpose",
     "ofspmm_fwd_host_workspace_bytes", "ofspmm_fwd_host", "ofspmm_strerror", "ofspmm_version",
@@ -63,6 +63,8 @@ def lib() -> ctypes.CDLL:
     L.ofspmm_fwd_workspace_bytes.restype = sz
     L.ofspmm_fwd.argtypes = [csr_p, vp, vp, i64, i32, vp, sz, vp]
     L.ofspmm_fwd.restype = i32
+    L.ofspmm_fwd_strided.argtypes = [csr_p, vp, i64, vp, i64, i64, i32, vp, sz, vp]
+    L.ofspmm_fwd_strided.restype = i32
     L.ofspmm_bwd_b_workspace_bytes.argtypes = [i64, i64, i64, i64, i32, i32]
     L.ofspmm_bwd_b_workspace_bytes.restype = sz
     L.ofspmm_bwd_b.argtypes = [csr_p, csr_p, vp, vp, i64, i32, vp, sz, vp]

@@ -66,12 +66,14 @@ int check_ws(const void* ws, size_t have, size_t need) {
 }
 
 // C = A·B through the merge-path kernels; shared by ofspmm_fwd and route (1) of ofspmm_bwd_b.
-int run_fwd(const ofspmm_csr* A, const void* B, void* C, int64_t n, int dense_dtype, void* ws,
-            size_t ws_bytes, cudaStream_t stream) {
+int run_fwd(const ofspmm_csr* A, const void* B, int64_t ldb, void* C, int64_t ldc, int64_t n,
+            int dense_dtype, void* ws, size_t ws_bytes, cudaStream_t stream) {
   if (A->rows == 0 || n == 0) return OFSPMM_OK;
-  const size_t out_bytes = static_cast<size_t>(A->rows) * static_cast<size_t>(n) * dense_size(dense_dtype);
+  if (ldb < n || ldc < n || ldb >= (int64_t{1} << 30)) return OFSPMM_ERR_INVALID_ARG;
   if (A->nnz == 0 || A->cols == 0) {
-    OFSPMM_CUDA_OK(cudaMemsetAsync(C, 0, out_bytes, stream));
+    OFSPMM_CUDA_OK(cudaMemset2DAsync(C, static_cast<size_t>(ldc) * dense_size(dense_dtype), 0,
+                                     static_cast<size_t>(n) * dense_size(dense_dtype),
+                                     static_cast<size_t>(A->rows), stream));
     return OFSPMM_OK;
   }
   const FwdWorkspace L = fwd_workspace_layout(A->rows, A->nnz, n, dense_dtype);
@@ -79,7 +81,7 @@ int run_fwd(const ofspmm_csr* A, const void* B, void* C, int64_t n, int dense_dt
   unsigned char* w = static_cast<unsigned char*>(ws);
   const int64_t P = num_tasks(A->rows, A->nnz);
   if (int rc = launch_task_partition(A->crow, A->idx_dtype, A->rows, A->nnz, P, w + L.part_off, stream)) return rc;
-  return launch_fwd(A, B, C, n, dense_dtype, w + L.part_off, reinterpret_cast<float*>(w + L.carry_off),
+  return launch_fwd(A, B, ldb, C, ldc, n, dense_dtype, w + L.part_off, reinterpret_cast<float*>(w + L.carry_off),
                     reinterpret_cast<float*>(w + L.head_off), P, stream);
 }
 
@@ -102,7 +104,16 @@ int ofspmm_fwd(const ofspmm_csr* A, const void* B, void* C, int64_t n, int dense
   if (int rc = check_dtypes(A, dense_dtype)) return rc;
   if (n < 0 || n >= (int64_t{1} << 31)) return OFSPMM_ERR_INVALID_ARG;
   if (A->rows > 0 && n > 0 && (C == nullptr || (A->nnz > 0 && A->cols > 0 && B == nullptr))) return OFSPMM_ERR_INVALID_ARG;
-  return run_fwd(A, B, C, n, dense_dtype, workspace, workspace_bytes, reinterpret_cast<cudaStream_t>(stream));
+  return run_fwd(A, B, n, C, n, n, dense_dtype, workspace, workspace_bytes, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int ofspmm_fwd_strided(const ofspmm_csr* A, const void* B, int64_t ldb, void* C, int64_t ldc, int64_t n,
+                       int dense_dtype, void* workspace, size_t workspace_bytes, ofspmm_stream_t stream) {
+  if (int rc = check_csr(A, true)) return rc;
+  if (int rc = check_dtypes(A, dense_dtype)) return rc;
+  if (n < 0 || n >= (int64_t{1} << 31)) return OFSPMM_ERR_INVALID_ARG;
+  if (A->rows > 0 && n > 0 && (C == nullptr || (A->nnz > 0 && A->cols > 0 && B == nullptr))) return OFSPMM_ERR_INVALID_ARG;
+  return run_fwd(A, B, ldb, C, ldc, n, dense_dtype, workspace, workspace_bytes, reinterpret_cast<cudaStream_t>(stream));
 }
 
 size_t ofspmm_bwd_b_workspace_bytes(int64_t rows, int64_t cols, int64_t nnz, int64_t n, int dense_dtype,
@@ -126,7 +137,7 @@ int ofspmm_bwd_b(const ofspmm_csr* A, const ofspmm_csr* At, const void* dY, void
     if (int rc = check_csr(At, true)) return rc;
     if (At->rows != A->cols || At->cols != A->rows || At->nnz != A->nnz) return OFSPMM_ERR_INVALID_ARG;
     if (int rc = check_dtypes(At, dense_dtype)) return rc;
-    return run_fwd(At, dY, dB, n, dense_dtype, workspace, workspace_bytes, stream);
+    return run_fwd(At, dY, n, dB, n, n, dense_dtype, workspace, workspace_bytes, stream);
   }
   // route (2): vector-atomic scatter into an fp32 accumulator
   const size_t out_elems = static_cast<size_t>(A->cols) * static_cast<size_t>(n);
@@ -265,7 +276,7 @@ int ofspmm_fwd_host(const ofspmm_csr* Ah, const void* B_host, void* C_host, int6
   Ad.crow = d_crow;
   Ad.col = d_col;
   Ad.val = d_val;
-  if (int rc = run_fwd(&Ad, d_B, d_C, n, dense_dtype, w + off, workspace_bytes - off, stream)) return rc;
+  if (int rc = run_fwd(&Ad, d_B, n, d_C, n, n, dense_dtype, w + off, workspace_bytes - off, stream)) return rc;
   OFSPMM_CUDA_OK(cudaMemcpyAsync(C_host, d_C, static_cast<size_t>(Ah->rows) * n * ds, cudaMemcpyDeviceToHost, stream));
   return OFSPMM_OK;
 }

@@ -86,6 +86,14 @@ template <> __device__ __forceinline__ __nv_bfloat16 from_float<__nv_bfloat16>(f
 template <typename DT, int VEC> struct RowVec;
 
 template <> struct RowVec<float, 4> {
+  using Raw = uint4;
+  __device__ __forceinline__ static Raw load_raw(const float* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+  __device__ __forceinline__ static void fma(float (&acc)[4], float v, const Raw& r) {
+    acc[0] = fmaf(v, __uint_as_float(r.x), acc[0]);
+    acc[1] = fmaf(v, __uint_as_float(r.y), acc[1]);
+    acc[2] = fmaf(v, __uint_as_float(r.z), acc[2]);
+    acc[3] = fmaf(v, __uint_as_float(r.w), acc[3]);
+  }
   __device__ __forceinline__ static void load(const float* p, float (&out)[4]) {
     const float4 v = __ldg(reinterpret_cast<const float4*>(p));
     out[0] = v.x; out[1] = v.y; out[2] = v.z; out[3] = v.w;
@@ -96,11 +104,24 @@ template <> struct RowVec<float, 4> {
 };
 
 template <> struct RowVec<float, 1> {
+  using Raw = float;
+  __device__ __forceinline__ static Raw load_raw(const float* p) { return __ldg(p); }
+  __device__ __forceinline__ static void fma(float (&acc)[1], float v, const Raw& r) { acc[0] = fmaf(v, r, acc[0]); }
   __device__ __forceinline__ static void load(const float* p, float (&out)[1]) { out[0] = __ldg(p); }
   __device__ __forceinline__ static void store_stream(float* p, const float (&v)[1]) { __stcs(p, v[0]); }
 };
 
 template <> struct RowVec<__nv_bfloat16, 8> {
+  using Raw = uint4;
+  __device__ __forceinline__ static Raw load_raw(const __nv_bfloat16* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+  __device__ __forceinline__ static void fma(float (&acc)[8], float v, const Raw& r) {
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {  // bf16 -> fp32 is a 16-bit shift / mask
+      acc[2 * i] = fmaf(v, __uint_as_float(w[i] << 16), acc[2 * i]);
+      acc[2 * i + 1] = fmaf(v, __uint_as_float(w[i] & 0xffff0000u), acc[2 * i + 1]);
+    }
+  }
   __device__ __forceinline__ static void load(const __nv_bfloat16* p, float (&out)[8]) {
     const uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
     const uint32_t w[4] = {v.x, v.y, v.z, v.w};
@@ -122,6 +143,11 @@ template <> struct RowVec<__nv_bfloat16, 8> {
 };
 
 template <> struct RowVec<__nv_bfloat16, 1> {
+  using Raw = unsigned short;
+  __device__ __forceinline__ static Raw load_raw(const __nv_bfloat16* p) { return __ldg(reinterpret_cast<const unsigned short*>(p)); }
+  __device__ __forceinline__ static void fma(float (&acc)[1], float v, const Raw& r) {
+    acc[0] = fmaf(v, __uint_as_float(static_cast<uint32_t>(r) << 16), acc[0]);
+  }
   __device__ __forceinline__ static void load(const __nv_bfloat16* p, float (&out)[1]) {
     out[0] = __uint_as_float(static_cast<uint32_t>(__ldg(reinterpret_cast<const unsigned short*>(p))) << 16);
   }

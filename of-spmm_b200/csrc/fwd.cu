@@ -6,11 +6,12 @@ namespace ofspmm {
 
 namespace {
 
-template <typename DT, typename ValT, typename IdxT, int VEC, int LPR, int CH>
-int launch_one(const FwdParams& p, int panels, cudaStream_t stream) {
+template <typename DT, typename ValT, typename IdxT, int VEC, int LPR, int CH, bool kFull>
+int launch_full(FwdParams p, int panels, cudaStream_t stream) {
+  p.panels = panels;
   constexpr int ITEMS = kTaskItems;
   constexpr int WARPS = kWarpsPerCta;
-  auto kern = spmm_merge_kernel<DT, ValT, IdxT, VEC, LPR, CH, ITEMS, WARPS>;
+  auto kern = spmm_merge_kernel<DT, ValT, IdxT, VEC, LPR, CH, kFull, ITEMS, WARPS>;
   const size_t smem = sizeof(TaskStage<IdxT, ValT, ITEMS>) * WARPS + sizeof(uint64_t) * WARPS;
   OFSPMM_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   DevInfo dev;
@@ -20,10 +21,10 @@ int launch_one(const FwdParams& p, int panels, cudaStream_t stream) {
   if (occ < 1) return OFSPMM_ERR_CUDA;
   // persistent grid: a whole number of CTAs per SM (148 SMs on B200), never more than the tasks
   const int64_t ctas_needed = (static_cast<int64_t>(p.P) + WARPS - 1) / WARPS;
-  int64_t per_panel = static_cast<int64_t>(dev.sms) * occ / panels;
-  if (per_panel < dev.sms) per_panel = dev.sms;
-  const int gx = static_cast<int>(ctas_needed < per_panel ? ctas_needed : per_panel);
-  kern<<<dim3(gx, panels), WARPS * 32, smem, stream>>>(p);
+  const int64_t ctas_all = (static_cast<int64_t>(p.P) * panels + WARPS - 1) / WARPS;
+  const int64_t resident = static_cast<int64_t>(dev.sms) * occ;
+  const int gx = static_cast<int>(ctas_all < resident ? ctas_all : resident);
+  kern<<<gx, WARPS * 32, smem, stream>>>(p);
   count_launch();
   OFSPMM_CUDA_OK(cudaGetLastError());
   // stitch rows that span several tasks
@@ -34,14 +35,25 @@ int launch_one(const FwdParams& p, int panels, cudaStream_t stream) {
   return OFSPMM_OK;
 }
 
+// kFull (no masked lanes, immediate chunk offsets) when n is a whole number of register tiles.
+template <typename DT, typename ValT, typename IdxT, int VEC, int LPR, int CH>
+int launch_one(const FwdParams& p, int panels, cudaStream_t stream) {
+  if (p.n % (LPR * VEC * CH) == 0) return launch_full<DT, ValT, IdxT, VEC, LPR, CH, true>(p, panels, stream);
+  return launch_full<DT, ValT, IdxT, VEC, LPR, CH, false>(p, panels, stream);
+}
+
 template <typename DT, typename ValT, typename IdxT>
 int launch_typed(const FwdParams& p, bool aligned, cudaStream_t stream) {
   constexpr int VECW = 16 / sizeof(DT);
   const int n = p.n;
-  if (aligned && n % VECW == 0) {
+  if (aligned && n % VECW == 0 && p.ldb % VECW == 0 && p.ldc % VECW == 0) {
     const int nvec = n / VECW;
     if (nvec <= 8) return launch_one<DT, ValT, IdxT, VECW, 8, 1>(p, 1, stream);
     if (nvec <= 16) return launch_one<DT, ValT, IdxT, VECW, 16, 1>(p, 1, stream);
+#ifdef OFSPMM_FORCE_PANEL16
+    // tuning experiment: half-width column panels (B panel = half the bytes in L2)
+    if (nvec % 16 == 0) return launch_one<DT, ValT, IdxT, VECW, 16, 1>(p, nvec / 16, stream);
+#endif
     if (nvec <= 32) return launch_one<DT, ValT, IdxT, VECW, 32, 1>(p, 1, stream);
     if (nvec <= 64) return launch_one<DT, ValT, IdxT, VECW, 32, 2>(p, 1, stream);
     return launch_one<DT, ValT, IdxT, VECW, 32, 4>(p, (nvec + 127) / 128, stream);
@@ -83,9 +95,12 @@ int launch_task_partition(const void* crow, int idx_dtype, int64_t rows, int64_t
   return OFSPMM_OK;
 }
 
-int launch_fwd(const ofspmm_csr* A, const void* B, void* C, int64_t n, int dense_dtype,
-               const void* part, float* carry, float* head, int64_t P, cudaStream_t stream) {
+int launch_fwd(const ofspmm_csr* A, const void* B, int64_t ldb, void* C, int64_t ldc, int64_t n,
+               int dense_dtype, const void* part, float* carry, float* head, int64_t P,
+               cudaStream_t stream) {
   FwdParams p;
+  p.ldb = ldb;
+  p.ldc = ldc;
   p.crow = A->crow;
   p.col = A->col;
   p.val = A->val;

@@ -10,8 +10,14 @@
 
 namespace ofspmm {
 
-constexpr int kTaskItems = 256;  // merge items (row-ends + non-zeros) per warp task
-constexpr int kWarpsPerCta = 8;
+#ifndef OFSPMM_ITEMS
+#define OFSPMM_ITEMS 256
+#endif
+#ifndef OFSPMM_WARPS
+#define OFSPMM_WARPS 8
+#endif
+constexpr int kTaskItems = OFSPMM_ITEMS;  // merge items (row-ends + non-zeros) per warp task
+constexpr int kWarpsPerCta = OFSPMM_WARPS;
 
 extern std::atomic<uint64_t> g_launches;
 inline void count_launch(uint64_t k = 1) { g_launches.fetch_add(k, std::memory_order_relaxed); }
@@ -37,8 +43,9 @@ FwdWorkspace fwd_workspace_layout(int64_t rows, int64_t nnz, int64_t n, int dens
 // Each returns an OFSPMM_* status; all launches go to `stream`.
 int launch_task_partition(const void* crow, int idx_dtype, int64_t rows, int64_t nnz, int64_t P,
                           void* part, cudaStream_t stream);
-int launch_fwd(const ofspmm_csr* A, const void* B, void* C, int64_t n, int dense_dtype,
-               const void* part, float* carry, float* head, int64_t P, cudaStream_t stream);
+int launch_fwd(const ofspmm_csr* A, const void* B, int64_t ldb, void* C, int64_t ldc, int64_t n,
+               int dense_dtype, const void* part, float* carry, float* head, int64_t P,
+               cudaStream_t stream);
 int launch_sddmm(const ofspmm_csr* A, const void* dY, const void* B, void* dval, int64_t n,
                  int dense_dtype, const void* part, int64_t P, cudaStream_t stream);
 int launch_bwd_atomic(const ofspmm_csr* A, const void* dY, float* acc, void* dB_cast_out,

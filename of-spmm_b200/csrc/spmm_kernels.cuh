@@ -11,10 +11,14 @@
 //
 // Data movement per task: the task's col / val / crow slices are staged into shared memory with
 // three 1-D TMA bulk copies (cp.async.bulk + mbarrier complete_tx, L2 evict-first since the CSR
-// stream is read exactly once); every non-zero then costs one LDS broadcast of (col, val) and one
-// coalesced 16-byte-per-lane gather of the dense row (float4 or 8 x bf16), fp32 FMA accumulate.
-// LPR lanes cover one dense row (vector-per-row when LPR < 32: 32/LPR non-zeros in flight per
-// warp instruction, combined with __shfl_xor at the row end; warp-per-row when LPR == 32).
+// stream is read exactly once).  A short per-task pass neutralises out-of-range column indices
+// in the staged copy, so the hot loop is check-free: per 4 non-zeros it issues one 16-byte LDS
+// broadcast of 4 column indices, one of 4 values, four IMAD.WIDE addresses and four coalesced
+// 16-byte-per-lane gathers of dense rows (float4 or 8 x bf16) feeding fp32 FMAs.
+// LPR lanes cover one dense row (vector-per-row when LPR < 32: 32/LPR groups of non-zeros in
+// flight per warp instruction, combined with __shfl_xor at the row end; warp-per-row when
+// LPR == 32).  Dense widths beyond one register tile are processed as column panels, panel-major
+// in time, so the B panel that is being gathered stays L2-resident.
 //
 // Output: rows that start and end inside a task are streamed to C once (st.global.cs).  The
 // trailing partial row of a task goes to carry[k] (fp32); a row that ends in task k but started
@@ -22,6 +26,13 @@
 // carries in ascending task order — no atomics, bitwise reproducible.
 #pragma once
 #include "common.cuh"
+
+#ifndef OFSPMM_B_LOAD
+#define OFSPMM_B_LOAD 0  // 0: ld.global.nc   1: + L1::no_allocate   2: + L2 evict_last policy
+#endif
+#ifndef OFSPMM_MIN_CTAS
+#define OFSPMM_MIN_CTAS 5
+#endif
 
 namespace ofspmm {
 
@@ -39,6 +50,9 @@ struct FwdParams {
   int nnz;
   int n;             // dense width
   int P;             // number of tasks
+  int panels;        // column panels of LPR*VEC*CH columns each
+  long long ldb;     // row stride of B in elements (>= n)
+  long long ldc;     // row stride of C in elements (>= n)
 };
 
 template <typename IdxT, typename ValT, int ITEMS>
@@ -72,12 +86,121 @@ __device__ __forceinline__ void seg_copy_edges(T* dst, const T* src, int count, 
   }
 }
 
-template <typename DT, typename ValT, typename IdxT, int VEC, int LPR, int CH, int ITEMS, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32) spmm_merge_kernel(const FwdParams p) {
-  constexpr int G = 32 / LPR;                       // non-zeros processed per warp step
-  constexpr int U = (CH * VEC >= 16) ? 2 : 4;       // unroll: independent gathers in flight
+// One task's CSR slices in shared memory.
+template <typename IdxT, typename ValT>
+struct StagedTask {
+  const IdxT* scol;  // scol[e] = col[ns + e]
+  const ValT* sval;  // sval[e] = val[ns + e]   (unused when values are not staged)
+  const IdxT* srow;  // srow[i] = crow[rs + i]
+  int pre_c, pre_v;  // slot of element 0 inside st.col / st.val (address alignment phase)
+};
+
+// Stages crow[rs..re], col[ns..ne) and (optionally) val[ns..ne) of a task: TMA bulk copies for
+// the 16-byte aligned bodies, lanes for the ragged edges, then waits for the bytes to land and
+// neutralises out-of-range column indices (col := 0, val := 0) in the staged copy.
+template <bool kWithVal, typename IdxT, typename ValT, int ITEMS>
+__device__ __forceinline__ StagedTask<IdxT, ValT> stage_task(
+    TaskStage<IdxT, ValT, ITEMS>& st, uint64_t* bar, uint32_t& phase, const IdxT* __restrict__ crow,
+    const IdxT* __restrict__ col, const ValT* __restrict__ val, int rs, int ns, int cnt_row,
+    int cnt_nz, long long cols, int lane, uint64_t pol_stream) {
+  int pre_c, head_c, body_c, pre_v = 0, head_v = 0, body_v = 0, pre_r, head_r, body_r;
+  seg_plan(col + ns, cnt_nz, pre_c, head_c, body_c);
+  if constexpr (kWithVal) seg_plan(val + ns, cnt_nz, pre_v, head_v, body_v);
+  seg_plan(crow + rs, cnt_row, pre_r, head_r, body_r);
+  const uint32_t tx = static_cast<uint32_t>(body_c * sizeof(IdxT) + body_v * sizeof(ValT) +
+                                            body_r * sizeof(IdxT));
+  __syncwarp();  // every lane is done reading the previous task's stage
+  if (lane == 0 && tx != 0) {
+    mbar_arrive_expect_tx(bar, tx);
+    if (body_c) tma_bulk_g2s(st.col + pre_c + head_c, col + ns + head_c, body_c * sizeof(IdxT), bar, pol_stream);
+    if (kWithVal && body_v) tma_bulk_g2s(st.val + pre_v + head_v, val + ns + head_v, body_v * sizeof(ValT), bar, pol_stream);
+    if (body_r) tma_bulk_g2s(st.crow + pre_r + head_r, crow + rs + head_r, body_r * sizeof(IdxT), bar, pol_stream);
+  }
+  seg_copy_edges(st.col, col + ns, cnt_nz, pre_c, head_c, body_c, lane);
+  if constexpr (kWithVal) seg_copy_edges(st.val, val + ns, cnt_nz, pre_v, head_v, body_v, lane);
+  seg_copy_edges(st.crow, crow + rs, cnt_row, pre_r, head_r, body_r, lane);
+  if (tx != 0) {
+    mbar_wait(bar, phase);
+    phase ^= 1;
+  }
+  __syncwarp();
+  // sanitise: indices outside [0, cols) contribute nothing (reference: segment-sum skips them)
+  for (int e = lane; e < cnt_nz; e += 32) {
+    const IdxT c = st.col[pre_c + e];
+    if (static_cast<unsigned long long>(c) >= static_cast<unsigned long long>(cols)) {
+      st.col[pre_c + e] = 0;
+      if constexpr (kWithVal) st.val[pre_v + e] = from_float<ValT>(0.f);
+    }
+  }
+  __syncwarp();
+  StagedTask<IdxT, ValT> t;
+  t.scol = st.col + pre_c;
+  t.sval = st.val + pre_v;
+  t.srow = st.crow + pre_r;
+  t.pre_c = pre_c;
+  t.pre_v = pre_v;
+  return t;
+}
+
+// Dense-row gather (16 bytes per lane when vectorised) with the configured cache policy; the raw
+// bits stay in registers until the FMAs consume them (bf16 is widened at use, not at load).
+template <typename DT, int VEC>
+__device__ __forceinline__ typename RowVec<DT, VEC>::Raw load_b(const char* p, uint64_t pol) {
+#if OFSPMM_B_LOAD == 0
+  (void)pol;
+  return RowVec<DT, VEC>::load_raw(reinterpret_cast<const DT*>(p));
+#else
+  if constexpr (VEC * sizeof(DT) == 16) {
+    uint4 w;
+#if OFSPMM_B_LOAD == 1
+    (void)pol;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(w.x), "=r"(w.y), "=r"(w.z), "=r"(w.w) : "l"(p));
+#else
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=r"(w.x), "=r"(w.y), "=r"(w.z), "=r"(w.w) : "l"(p), "l"(pol));
+#endif
+    return w;
+  } else {
+    (void)pol;
+    return RowVec<DT, VEC>::load_raw(reinterpret_cast<const DT*>(p));
+  }
+#endif
+}
+
+// Byte offset of dense row c (already validated, non-negative): one IMAD.WIDE.U32 for int32 ids.
+template <typename IdxT>
+__device__ __forceinline__ unsigned long long row_offset(IdxT c, uint32_t row_bytes) {
+  if constexpr (sizeof(IdxT) == 4) {
+    return static_cast<unsigned long long>(static_cast<uint32_t>(c)) * row_bytes;
+  } else {
+    return static_cast<unsigned long long>(c) * row_bytes;
+  }
+}
+
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint2 lds64(uint32_t addr) {
+  uint2 v;
+  asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+  return v;
+}
+
+// kFull: n is a whole number of LPR*VEC*CH-column tiles, so no lane is ever masked and the chunk
+// offsets are immediates.  Otherwise masked chunks are pointed at column 0 (a valid address:
+// their loads are harmless duplicates) and only the stores are predicated.
+template <typename DT, typename ValT, typename IdxT, int VEC, int LPR, int CH, bool kFull, int ITEMS, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, CH == 1 ? OFSPMM_MIN_CTAS : (CH == 2 ? 3 : 2))
+spmm_merge_kernel(const FwdParams p) {
+  constexpr int G = 32 / LPR;  // groups of lanes working on different non-zeros
   constexpr bool kF32Out = sizeof(DT) == 4;
+  constexpr bool kVecIdx = sizeof(IdxT) == 4;  // 16-byte LDS path needs 4-byte indices
+  constexpr uint32_t kChunkBytes = LPR * VEC * sizeof(DT);
   using Stage = TaskStage<IdxT, ValT, ITEMS>;
+  using RV = RowVec<DT, VEC>;
 
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Stage* stages = reinterpret_cast<Stage*>(smem_raw);
@@ -85,116 +208,136 @@ __global__ void __launch_bounds__(WARPS * 32) spmm_merge_kernel(const FwdParams 
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int grp = lane / LPR;  // which of the G concurrent non-zeros
+  const int grp = lane / LPR;  // which group of concurrent non-zeros
   const int lig = lane % LPR;  // lane in group -> column chunk
   Stage& st = stages[warp];
   uint64_t* bar = &bars[warp];
+  const uint32_t col_sa = smem_u32(st.col);
+  const uint32_t val_sa = smem_u32(st.val);
 
   if (lane == 0) mbar_init(bar, 1);
   fence_mbar_init();
   __syncwarp();
 
   const uint64_t pol_stream = l2_policy_evict_first();
+#if OFSPMM_B_LOAD == 2
+  const uint64_t pol_b = l2_policy_evict_last();
+#else
+  const uint64_t pol_b = 0;
+#endif
   const IdxT* __restrict__ crow = static_cast<const IdxT*>(p.crow);
   const IdxT* __restrict__ col = static_cast<const IdxT*>(p.col);
   const ValT* __restrict__ val = static_cast<const ValT*>(p.val);
   const int n = p.n;
+  const uint32_t row_bytes = static_cast<uint32_t>(p.ldb) * sizeof(DT);
 
-  // this lane's columns: panel base + chunk ch * LPR*VEC + lig*VEC
-  const int col0 = blockIdx.y * (LPR * VEC * CH) + lig * VEC;
-  unsigned chmask = 0;
-#pragma unroll
-  for (int ch = 0; ch < CH; ++ch)
-    if (col0 + ch * LPR * VEC < n) chmask |= 1u << ch;
-  const DT* __restrict__ Bl = static_cast<const DT*>(p.B) + col0;
-  DT* __restrict__ Cl = static_cast<DT*>(p.C) + col0;
-  float* __restrict__ carry = p.carry + col0;
-  float* __restrict__ headbuf = p.head + col0;
-
+  const long long total_tasks = static_cast<long long>(p.P) * p.panels;
   const int total_warps = gridDim.x * WARPS;
   uint32_t phase = 0;
 
-  for (int k = blockIdx.x * WARPS + warp; k < p.P; k += total_warps) {
+  for (long long t = blockIdx.x * WARPS + warp; t < total_tasks; t += total_warps) {
+    // panel-major: all tasks of column panel 0, then panel 1, ... (keeps the B panel in L2)
+    const int panel = static_cast<int>(t / p.P);
+    const int k = static_cast<int>(t - static_cast<long long>(panel) * p.P);
+    const int col0 = panel * (LPR * VEC * CH) + lig * VEC;
+    unsigned chmask = 0;
+    uint32_t choff[CH];  // byte offset of chunk ch from the lane base (0-column for masked chunks)
+#pragma unroll
+    for (int ch = 0; ch < CH; ++ch) {
+      const bool ok = kFull || (col0 + ch * LPR * VEC < n);
+      if (ok) chmask |= 1u << ch;
+      choff[ch] = ok ? static_cast<uint32_t>(col0 + ch * LPR * VEC) * sizeof(DT) : 0u;
+    }
+    // lane base: B + first chunk's columns when kFull (other chunks are immediates), else B
+    unsigned long long bl_bits = reinterpret_cast<unsigned long long>(p.B) + (kFull ? choff[0] : 0u);
+    // opaque to the optimiser: keep base+lane offset as ONE 64-bit register so every gather
+    // address is a single IMAD.WIDE.U32 (col * row_bytes + base) instead of IMAD + 64-bit add
+    asm volatile("" : "+l"(bl_bits));
+    const char* __restrict__ Bl = reinterpret_cast<const char*>(bl_bits);
+
     const int2 ps = __ldg(&p.part[k]);
     const int2 pe = __ldg(&p.part[k + 1]);
     const int rs = ps.x, ns = ps.y, re = pe.x, ne = pe.y;
     const int cnt_nz = ne - ns;
-    const int cnt_row = re - rs + 1;  // crow[rs .. re]
+    const StagedTask<IdxT, ValT> tk = stage_task<true>(st, bar, phase, crow, col, val, rs, ns, re - rs + 1,
+                                                       cnt_nz, p.cols, lane, pol_stream);
+    // 16-byte LDS path: index chunk and value chunk must share their alignment phase
+    const bool vec_ok = kVecIdx && (((tk.pre_v - tk.pre_c) & 3) == 0);
+    // value byte address of the slot that pairs with index slot 0
+    const uint32_t val_s0 = val_sa + static_cast<uint32_t>((tk.pre_v - tk.pre_c) * static_cast<int>(sizeof(ValT)));
+    const bool started_earlier = static_cast<int>(tk.srow[0]) < ns;
 
-    // ---- stage the task's CSR slices: TMA bulk copies for the aligned bodies
-    int pre_c, head_c, body_c, pre_v, head_v, body_v, pre_r, head_r, body_r;
-    seg_plan(col + ns, cnt_nz, pre_c, head_c, body_c);
-    seg_plan(val + ns, cnt_nz, pre_v, head_v, body_v);
-    seg_plan(crow + rs, cnt_row, pre_r, head_r, body_r);
-    const uint32_t tx = static_cast<uint32_t>(body_c * sizeof(IdxT) + body_v * sizeof(ValT) +
-                                              body_r * sizeof(IdxT));
-    __syncwarp();  // every lane is done reading the previous task's stage
-    if (lane == 0 && tx != 0) {
-      mbar_arrive_expect_tx(bar, tx);
-      if (body_c) tma_bulk_g2s(st.col + pre_c + head_c, col + ns + head_c, body_c * sizeof(IdxT), bar, pol_stream);
-      if (body_v) tma_bulk_g2s(st.val + pre_v + head_v, val + ns + head_v, body_v * sizeof(ValT), bar, pol_stream);
-      if (body_r) tma_bulk_g2s(st.crow + pre_r + head_r, crow + rs + head_r, body_r * sizeof(IdxT), bar, pol_stream);
-    }
-    seg_copy_edges(st.col, col + ns, cnt_nz, pre_c, head_c, body_c, lane);
-    seg_copy_edges(st.val, val + ns, cnt_nz, pre_v, head_v, body_v, lane);
-    seg_copy_edges(st.crow, crow + rs, cnt_row, pre_r, head_r, body_r, lane);
-    if (tx != 0) {
-      mbar_wait(bar, phase);
-      phase ^= 1;
-    }
-    __syncwarp();
+    int e = 0;
+    for (int r = rs; r <= re; ++r) {
+      // rows rs..re-1 end in this task; r == re is the trailing partial row (if it has elements)
+      const int e_end = r < re ? static_cast<int>(tk.srow[r - rs + 1]) - ns : cnt_nz;
+      if (r == re && e_end <= e) break;
 
-    const IdxT* scol = st.col + pre_c;   // scol[e]  = col[ns + e]
-    const ValT* sval = st.val + pre_v;   // sval[e]  = val[ns + e]
-    const IdxT* srow = st.crow + pre_r;  // srow[i]  = crow[rs + i]
-
-    float acc[CH][VEC];
-
-    // acc += sum over elements e in [e0, e1) handled by this lane's group
-    auto accumulate = [&](int e0, int e1) {
+      float acc[CH][VEC];
 #pragma unroll
       for (int ch = 0; ch < CH; ++ch)
 #pragma unroll
         for (int i = 0; i < VEC; ++i) acc[ch][i] = 0.f;
-      int e = e0 + grp;
-      for (; e + (U - 1) * G < e1; e += U * G) {
-        IdxT c[U];
-        float v[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          c[u] = scol[e + u * G];
-          v[u] = to_float(sval[e + u * G]);
-          if (static_cast<unsigned long long>(c[u]) >= static_cast<unsigned long long>(p.cols)) { c[u] = 0; v[u] = 0.f; }
-        }
-        float x[U][CH][VEC];
-#pragma unroll
-        for (int u = 0; u < U; ++u)
-#pragma unroll
-          for (int ch = 0; ch < CH; ++ch)
-            if (chmask & (1u << ch))
-              RowVec<DT, VEC>::load(Bl + static_cast<size_t>(c[u]) * n + ch * LPR * VEC, x[u][ch]);
-#pragma unroll
-        for (int u = 0; u < U; ++u)
-#pragma unroll
-          for (int ch = 0; ch < CH; ++ch)
-            if (chmask & (1u << ch))
-#pragma unroll
-              for (int i = 0; i < VEC; ++i) acc[ch][i] = fmaf(v[u], x[u][ch][i], acc[ch][i]);
-      }
-      for (; e < e1; e += G) {
-        IdxT c = scol[e];
-        float v = to_float(sval[e]);
-        if (static_cast<unsigned long long>(c) >= static_cast<unsigned long long>(p.cols)) { c = 0; v = 0.f; }
+
+      auto fma_one = [&](int elem) {  // acc += val * B[col, lane columns] for one staged element
+        const IdxT c = tk.scol[elem];
+        const float v = to_float(tk.sval[elem]);
+        const char* brow = Bl + row_offset(c, row_bytes);
 #pragma unroll
         for (int ch = 0; ch < CH; ++ch)
-          if (chmask & (1u << ch)) {
-            float x[VEC];
-            RowVec<DT, VEC>::load(Bl + static_cast<size_t>(c) * n + ch * LPR * VEC, x);
+          RV::fma(acc[ch], v, load_b<DT, VEC>(brow + (kFull ? ch * kChunkBytes : choff[ch]), pol_b));
+      };
+
+      if (vec_ok) {
+        // slots s = pre_c + e; [a, b) is the 16-byte aligned middle, read 4 elements per LDS
+        const int s0 = tk.pre_c + e, s1 = tk.pre_c + e_end;
+        int a = (s0 + 3) & ~3;
+        if (a > s1) a = s1;
+        int b = s1 & ~3;
+        if (b < a) b = a;
+        for (int s = s0 + grp; s < a; s += G) fma_one(s - tk.pre_c);   // ragged head
+        for (int s = b + grp; s < s1; s += G) fma_one(s - tk.pre_c);   // ragged tail
+        // aligned chunks: chunk q goes to lane group q % G
+        uint32_t ca = col_sa + static_cast<uint32_t>(a + 4 * grp) * 4u;
+        const uint32_t cend = col_sa + static_cast<uint32_t>(b) * 4u;
+        if (ca < cend) {
+          uint32_t va = val_s0 + static_cast<uint32_t>(a + 4 * grp) * static_cast<uint32_t>(sizeof(ValT));
+          uint4 cn = lds128(ca);
+          do {
+            const uint32_t c4[4] = {cn.x, cn.y, cn.z, cn.w};
+            typename RV::Raw x[4][CH];
 #pragma unroll
-            for (int i = 0; i < VEC; ++i) acc[ch][i] = fmaf(v, x[i], acc[ch][i]);
-          }
+            for (int u = 0; u < 4; ++u) {
+              const char* brow = Bl + static_cast<unsigned long long>(c4[u]) * row_bytes;
+#pragma unroll
+              for (int ch = 0; ch < CH; ++ch)
+                x[u][ch] = load_b<DT, VEC>(brow + (kFull ? ch * kChunkBytes : choff[ch]), pol_b);
+            }
+            ca += 16u * G;
+            if (ca < cend) cn = lds128(ca);  // next chunk's indices, while the gathers fly
+            float v4[4];
+            if constexpr (sizeof(ValT) == 4) {
+              const uint4 w = lds128(va);
+              v4[0] = __uint_as_float(w.x); v4[1] = __uint_as_float(w.y);
+              v4[2] = __uint_as_float(w.z); v4[3] = __uint_as_float(w.w);
+            } else {
+              const uint2 w = lds64(va);
+              v4[0] = __uint_as_float(w.x << 16); v4[1] = __uint_as_float(w.x & 0xffff0000u);
+              v4[2] = __uint_as_float(w.y << 16); v4[3] = __uint_as_float(w.y & 0xffff0000u);
+            }
+            va += 4u * G * static_cast<uint32_t>(sizeof(ValT));
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+              for (int ch = 0; ch < CH; ++ch) RV::fma(acc[ch], v4[u], x[u][ch]);
+          } while (ca < cend);
+        }
+      } else {
+        for (int el = e + grp; el < e_end; el += G) fma_one(el);
       }
-      if constexpr (G > 1) {  // combine the G concurrent partial rows (fixed xor tree)
+      e = e_end;
+
+      if constexpr (G > 1) {  // combine the G groups' partial rows (fixed xor tree)
 #pragma unroll
         for (int off = LPR; off < 32; off <<= 1)
 #pragma unroll
@@ -202,35 +345,21 @@ __global__ void __launch_bounds__(WARPS * 32) spmm_merge_kernel(const FwdParams 
 #pragma unroll
             for (int i = 0; i < VEC; ++i) acc[ch][i] += __shfl_xor_sync(0xffffffffu, acc[ch][i], off);
       }
-    };
 
-    const bool started_earlier = static_cast<int>(srow[0]) < ns;
-    int e = 0;
-    for (int r = rs; r < re; ++r) {
-      const int e_end = static_cast<int>(srow[r - rs + 1]) - ns;
-      accumulate(e, e_end);
-      e = e_end;
       if (grp == 0) {
-        if (!kF32Out && r == rs && started_earlier) {
-          float* dst = headbuf + static_cast<size_t>(k) * n;
+        if (r == re || (!kF32Out && r == rs && started_earlier)) {
+          // fp32 scratch: carry[k] for the trailing partial row, head[k] for a bf16 row that
+          // started in an earlier task
+          float* dst = (r == re ? p.carry : p.head) + static_cast<size_t>(k) * n + col0;
 #pragma unroll
           for (int ch = 0; ch < CH; ++ch)
             if (chmask & (1u << ch)) store_f32<VEC>(dst + ch * LPR * VEC, acc[ch]);
         } else {
-          DT* dst = Cl + static_cast<size_t>(r) * n;
+          DT* dst = static_cast<DT*>(p.C) + static_cast<size_t>(r) * p.ldc + col0;
 #pragma unroll
           for (int ch = 0; ch < CH; ++ch)
-            if (chmask & (1u << ch)) RowVec<DT, VEC>::store_stream(dst + ch * LPR * VEC, acc[ch]);
+            if (chmask & (1u << ch)) RV::store_stream(dst + ch * LPR * VEC, acc[ch]);
         }
-      }
-    }
-    if (cnt_nz > e) {  // trailing partial row `re`
-      accumulate(e, cnt_nz);
-      if (grp == 0) {
-        float* dst = carry + static_cast<size_t>(k) * n;
-#pragma unroll
-        for (int ch = 0; ch < CH; ++ch)
-          if (chmask & (1u << ch)) store_f32<VEC>(dst + ch * LPR * VEC, acc[ch]);
       }
     }
   }
@@ -253,7 +382,7 @@ __global__ void __launch_bounds__(WARPS * 32) spmm_fixup_kernel(const FwdParams 
   int j = k - 1;         // tasks j..k-1 each hold >= 1 non-zero of row rs
   while (j > 0 && __ldg(&p.part[j]).y > cr) --j;
   const int n = p.n;
-  DT* crow_out = static_cast<DT*>(p.C) + static_cast<size_t>(rs) * n;
+  DT* crow_out = static_cast<DT*>(p.C) + static_cast<size_t>(rs) * p.ldc;
   for (int c0 = lane * VEC; c0 < n; c0 += 32 * VEC) {
     float sum[VEC];
 #pragma unroll

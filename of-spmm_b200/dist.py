@@ -1,0 +1,154 @@
+"""Multi-GPU SpMM inside one NVSwitch box: one process per GPU over
+``torch.distributed`` (NCCL over NVLink 5; gloo on CPU for the host-logic tests).
+
+Partitioning
+  * A (M×K) → ``world`` contiguous, **nnz-balanced whole-row blocks** from the device merge-path
+    partitioner (``row_blocks``); rank r keeps only its block's CSR.  Output rows stay local.
+    Contrast: the reference can only split rows in equal counts (BalancedSplitter,
+    oneflow/core/common/balanced_splitter.cpp:20-39) and its S(0)→B boxing needs dim0 % world == 0
+    (oneflow/core/boxing/ccl_boxing_function.cpp:115), which is why this lives here and not in SBP.
+  * B (K×n) is row-sharded in equal blocks of ceil(K/world) rows (zero-padded), which is what an
+    all-gather needs.
+
+Forward  C_blk = A_blk · B:   the dense operand is processed as ``panels`` column panels; the
+  all-gather of panel j+1 (NCCL, its own stream) is in flight while the SpMM of panel j runs
+  (``ofspmm_fwd_strided`` writes panel j straight into C_blk's columns).  The reference instead
+  finishes a blocking, unfused all-gather before the op is even issued
+  (oneflow/core/framework/op_interpreter/eager_global_op_interpreter.cpp:156-181).
+Backward dB = Aᵀ · dY:   each rank's row block yields a partial K×n; panel j is reduce-scattered
+  over NVLink while panel j+1 is being computed (the dual collective).
+
+The compute callbacks default to the CUDA ops; tests inject CPU stand-ins to exercise the
+partition / shard / pipeline logic under gloo with world_size 2.
+"""
+from __future__ import annotations
+
+from typing import Callable, List, Optional
+
+import torch
+import torch.distributed as dist
+
+from . import ops
+from .graphs import CsrMatrix
+
+
+def _default_spmm(crow, col, val, b, rows, cols, out):
+    return ops.spmm_csr_compute(crow, col, val, b, rows, cols, out=out)
+
+
+def _default_transpose(crow, col, val, rows, cols):
+    return ops.csr_transpose(crow, col, val, rows, cols)
+
+
+def shard_rows_count(k: int, world: int) -> int:
+    return (k + world - 1) // world
+
+
+class ShardedSpmm:
+    """Row-block-partitioned SpMM operator bound to one rank."""
+
+    def __init__(self, A: CsrMatrix, n: int, dtype: torch.dtype, rank: int, world: int, device,
+                 bwd: str = "transpose", panels: int = 2,
+                 spmm_fn: Callable = _default_spmm, transpose_fn: Callable = _default_transpose,
+                 group=None):
+        assert A.rows >= world, "fewer rows than ranks"
+        self.rank, self.world, self.device, self.group = rank, world, device, group
+        self.n, self.dtype = n, dtype
+        self.rows, self.cols = A.rows, A.cols
+        self.spmm_fn, self.bwd_mode = spmm_fn, bwd
+        # column panels must keep 16-byte alignment of every panel start (8 bf16 / 4 fp32)
+        vec = 8 if dtype == torch.bfloat16 else 4
+        panels = max(1, min(panels, n // vec if n >= vec else 1))
+        while n % (panels * vec) != 0 and panels > 1:
+            panels -= 1
+        self.panels = panels
+        self.w = n // panels
+        # nnz-balanced whole-row blocks (device partitioner when the graph is on the GPU)
+        self.bounds = ops.row_blocks(A.crow, A.nnz, world).cpu().tolist()
+        self.r0, self.r1 = int(self.bounds[rank]), int(self.bounds[rank + 1])
+        self.A_blk = A.row_slice(self.r0, self.r1)
+        self.shard = shard_rows_count(A.cols, world)
+        self.kp = self.shard * world  # padded K
+        self.At_blk = None
+        if bwd == "transpose":
+            t = transpose_fn(self.A_blk.crow, self.A_blk.col, self.A_blk.val, self.A_blk.rows, self.A_blk.cols)
+            self.At_blk = CsrMatrix(t[0], t[1], t[2], self.A_blk.cols, self.A_blk.rows)
+        m = self.A_blk.rows
+        # persistent buffers (allocated once: the op state of the multi-GPU path)
+        self._b_send = [torch.empty((self.shard, self.w), dtype=dtype, device=device) for _ in range(panels)]
+        self._b_full = [torch.empty((self.kp, self.w), dtype=dtype, device=device) for _ in range(panels)]
+        self._c = torch.empty((m, n), dtype=dtype, device=device)
+        self._db_part = [torch.empty((self.kp, self.w), dtype=dtype, device=device) for _ in range(panels)]
+        self._db_out = [torch.empty((self.shard, self.w), dtype=dtype, device=device) for _ in range(panels)]
+        self._db = torch.empty((self.shard, n), dtype=dtype, device=device)
+        self._nccl = dist.is_initialized() and dist.get_backend(group) == "nccl"
+
+    # ------------------------------------------------------------------ sharding helpers
+    def shard_rows(self, B_full: torch.Tensor) -> torch.Tensor:
+        """This rank's equal-size row shard of a K×n dense operand (zero-padded past K)."""
+        s0 = self.rank * self.shard
+        out = torch.zeros((self.shard, self.n), dtype=B_full.dtype, device=B_full.device)
+        hi = min(self.cols, s0 + self.shard)
+        if hi > s0:
+            out[: hi - s0] = B_full[s0:hi]
+        return out
+
+    def shard_rows_out(self, dY_full: torch.Tensor) -> torch.Tensor:
+        """The rows of an M×n tensor that belong to this rank's row block of A."""
+        return dY_full[self.r0:self.r1].contiguous()
+
+    def nnz_per_rank(self) -> List[int]:
+        return []  # filled by callers that hold the full crow; kept for API symmetry
+
+    # ------------------------------------------------------------------ collectives
+    def _all_gather(self, out: torch.Tensor, inp: torch.Tensor):
+        return dist.all_gather_into_tensor(out, inp, group=self.group, async_op=True)
+
+    def _reduce_scatter(self, out: torch.Tensor, inp: torch.Tensor):
+        if self._nccl:
+            return dist.reduce_scatter_tensor(out, inp, group=self.group, async_op=True)
+        # gloo has no reduce-scatter: all-reduce then keep the local shard (host-logic tests only)
+        dist.all_reduce(inp, group=self.group)
+        out.copy_(inp[self.rank * self.shard:(self.rank + 1) * self.shard])
+        return None
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, B_shard: torch.Tensor) -> torch.Tensor:
+        """C_blk[m, n] = A_blk · allgather(B_shard), panel-pipelined."""
+        A, w = self.A_blk, self.w
+        works = []
+        for j in range(self.panels):
+            self._b_send[j].copy_(B_shard[:, j * w:(j + 1) * w])
+            works.append(self._all_gather(self._b_full[j], self._b_send[j]))
+        for j in range(self.panels):
+            works[j].wait()  # compute stream waits for panel j only; later panels keep flowing
+            self.spmm_fn(A.crow, A.col, A.val, self._b_full[j][: self.cols], A.rows, A.cols,
+                         self._c[:, j * w:(j + 1) * w])
+        return self._c
+
+    # ------------------------------------------------------------------ backward wrt B
+    def backward(self, dY_blk: torch.Tensor) -> torch.Tensor:
+        """dB_shard[shard, n] = reduce_scatter(A_blkᵀ · dY_blk), panel-pipelined."""
+        w = self.w
+        works: List[Optional[object]] = []
+        for j in range(self.panels):
+            part = self._db_part[j]
+            if self.kp > self.cols:
+                part[self.cols:].zero_()
+            dyj = dY_blk[:, j * w:(j + 1) * w]
+            if self.At_blk is not None:
+                At = self.At_blk
+                self.spmm_fn(At.crow, At.col, At.val, dyj, At.rows, At.cols, part[: self.cols])
+            else:
+                A = self.A_blk
+                part[: self.cols].copy_(ops.spmm_csr_grad_b_compute(A.crow, A.col, A.val, dyj.contiguous(),
+                                                                   A.rows, A.cols))
+            works.append(self._reduce_scatter(self._db_out[j], part))
+        for j in range(self.panels):
+            if works[j] is not None:
+                works[j].wait()
+            self._db[:, j * w:(j + 1) * w].copy_(self._db_out[j])
+        return self._db
+
+    def step(self, B_shard: torch.Tensor, dY_blk: torch.Tensor):
+        return self.forward(B_shard), self.backward(dY_blk)

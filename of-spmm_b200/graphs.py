@@ -79,11 +79,11 @@ def _sample_distinct(deg: torch.Tensor, K: int, sampler, max_rounds: int = 16) -
     keys = torch.empty(0, dtype=torch.int64, device=dev)
     need = deg.clone()
     ar = torch.arange(M, device=dev)
-    for _ in range(max_rounds):
+    for rnd in range(max_rounds):
         if int(need.sum()) == 0:
             break
         rows = torch.repeat_interleave(ar, need)
-        cols = sampler(rows)
+        cols = sampler(rows, rnd)
         keys = torch.unique(torch.cat([keys, rows * K + cols]))
         have = torch.bincount(torch.div(keys, K, rounding_mode="floor"), minlength=M)
         need = (deg - have).clamp_(min=0)
@@ -97,7 +97,7 @@ def uniform_csr(M: int, K: int, density: float, seed: int = 1, device="cpu") -> 
     deg = torch.binomial(torch.full((M,), float(K), device=device), probs, generator=g).to(torch.int64)
     deg.clamp_(max=K)
 
-    def sampler(rows):
+    def sampler(rows, rnd):
         return torch.randint(0, K, (rows.numel(),), generator=g, device=device, dtype=torch.int64)
 
     return _keys_to_csr(_sample_distinct(deg, K, sampler), M, K, None, g)
@@ -152,9 +152,10 @@ def community_csr(M: int, nnz: int, sigma: float = 1.2, dmin: int = 1, dmax: int
     deg = lognormal_degrees(M, nnz, sigma, dmin, min(dmax, K), g, device)
     csize = (M + communities - 1) // communities
 
-    def sampler(rows):
+    def sampler(rows, rnd):
+        # top-up rounds >= 3 draw globally so rows wider than their community can still fill up
         n = rows.numel()
-        local = torch.rand(n, generator=g, device=device) < p_local
+        local = torch.rand(n, generator=g, device=device) < (p_local if rnd < 3 else 0.0)
         base = torch.div(rows, csize, rounding_mode="floor") * csize
         width = torch.clamp(K - base, max=csize)
         u = torch.rand(n, generator=g, device=device, dtype=torch.float64)

@@ -81,7 +81,10 @@ def _check_device(*tensors) -> None:
         if not t.is_cuda:
             # exactly one kernel is registered for this op and it is the CUDA one (no CPU kernel):
             raise OpInferError("spmm_csr: no kernel registered for device type cpu — tensors must be on a CUDA device")
-        _chk(t.is_contiguous(), "spmm_csr kernels take contiguous tensors")
+        # 1-D tensors contiguous; dense 2-D operands row-major with unit inner stride (a column
+        # slice of a wider matrix is fine: its row stride is passed on as the leading dimension)
+        ok = t.is_contiguous() or (t.dim() == 2 and t.stride(1) == 1 and t.stride(0) >= t.shape[1])
+        _chk(ok, "spmm_csr kernels take contiguous tensors (2-D operands: unit inner stride)")
         dev = dev or t.device
         _chk(t.device == dev, "all tensors must live on one device")
 
@@ -100,15 +103,22 @@ def spmm_csr_compute(a_crow, a_col, a_val, b, a_rows: int, a_cols: int,
     if out is None:
         out = torch.empty((m, n), dtype=dt, device=b.device)
     else:
-        _chk(out.shape == (m, n) and out.dtype == dt and out.is_contiguous() and out.device == b.device,
-             "out has the wrong shape / dtype / layout")
+        _chk(out.shape == (m, n) and out.dtype == dt and out.device == b.device,
+             "out has the wrong shape / dtype / device")
+        _check_device(out)
     L = _lib.lib()
     with torch.cuda.device(b.device):
         A = _csr_struct(a_crow, a_col, a_val, a_rows, a_cols)
         nbytes = L.ofspmm_fwd_workspace_bytes(a_rows, a_cols, A.nnz, n, _DENSE[dt])
         ws, wsp = _workspace(nbytes, b.device)
-        check(L.ofspmm_fwd(ctypes.byref(A), _ptr(b), _ptr(out), n, _DENSE[dt], wsp, nbytes, _stream_ptr(b)),
-              "spmm_csr")
+        ldb = b.stride(0) if b.shape[0] > 1 else max(n, 1)
+        ldc = out.stride(0) if out.shape[0] > 1 else max(n, 1)
+        if ldb == n and ldc == n:
+            rc = L.ofspmm_fwd(ctypes.byref(A), _ptr(b), _ptr(out), n, _DENSE[dt], wsp, nbytes, _stream_ptr(b))
+        else:
+            rc = L.ofspmm_fwd_strided(ctypes.byref(A), _ptr(b), ldb, _ptr(out), ldc, n, _DENSE[dt], wsp, nbytes,
+                                      _stream_ptr(b))
+        check(rc, "spmm_csr")
     return out
 
 

@@ -372,3 +372,29 @@ def test_full_size_reddit_properties():
     # SDDMM adjoint: <dval, val> == <dY, A·B>
     dv = ofs.sddmm_csr(A.crow, A.col, dY, B1, A.rows, A.cols)
     assert abs(float((dv.double() * A.val.double()).sum() - lhs)) <= 1e-6 * float((dY.double() * Ca.double()).abs().sum())
+
+
+# ------------------------------------------------------------------ strided dense operands (column panels)
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_forward_strided_column_panels(dtype):
+    """ofspmm_fwd_strided: B and C as column slices of wider row-major buffers (what the multi-GPU
+    path uses to pipeline column panels); must equal the contiguous call bit for bit."""
+    A = graphs.rmat_csr(12, 16, seed=4).to(DEV)
+    N, w = 128, 32
+    B = graphs.dense_operand(A.cols, N, 3, DEV, dtype)
+    want = ofs.spmm_csr(A.crow, A.col, A.val, B, A.rows, A.cols)
+    ops = __import__("importlib").import_module("of-spmm_b200.ops")
+    C = torch.full((A.rows, N + 32), 7.0, dtype=dtype, device=DEV)        # wider output buffer
+    for j in range(N // w):
+        ops.spmm_csr_compute(A.crow, A.col, A.val, B[:, j * w:(j + 1) * w], A.rows, A.cols,
+                             out=C[:, j * w:(j + 1) * w])
+    # a panel result equals the same columns of the full-width product up to summation order
+    # within a row (different lane grouping) → compare with tolerance, and exactly against a
+    # contiguous call of the same width
+    for j in range(N // w):
+        Bj = B[:, j * w:(j + 1) * w].contiguous()
+        assert torch.equal(C[:, j * w:(j + 1) * w], ofs.spmm_csr(A.crow, A.col, A.val, Bj, A.rows, A.cols))
+    tol = 1e-4 if dtype == torch.float32 else 3e-2
+    assert torch.allclose(C[:, :N].float(), want.float(), rtol=tol, atol=tol * 10)
+    assert (C[:, N:] == 7.0).all()                                          # nothing written outside
