@@ -1,0 +1,69 @@
+// oneflow/core/autograd/gradient_funcs/spmm_csr.cpp — OpExprGradFunction of spmm_csr
+// (SURVEY.md §8 a9).  Pattern: gradient_funcs/gather.cpp:29-72 and matmul.cpp:36-104; interface
+// oneflow/core/framework/op_expr_grad_function.h:84-140.  Python mirror:
+// of-spmm_b200/functional.py:_SpmmCsrFn.
+#include "oneflow/core/framework/op_expr_grad_function.h"
+#include "oneflow/core/functional/functional.h"
+
+namespace oneflow {
+namespace one {
+
+struct SpmmCsrCaptureState : public AutoGradCaptureState {
+  bool val_requires_grad = false;
+  bool b_requires_grad = false;
+  int64_t a_rows = 0;
+  int64_t a_cols = 0;
+  size_t crow_index = 0, col_index = 0, val_index = 0, b_index = 0;
+};
+
+class SpmmCsr : public OpExprGradFunction<SpmmCsrCaptureState> {
+ public:
+  Maybe<void> Init(const OpExpr& op) override {
+    const UserOpExpr* fw_op_expr = dynamic_cast<const UserOpExpr*>(&op);
+    CHECK_NOTNULL_OR_RETURN(fw_op_expr);  // NOLINT(maybe-need-error-msg)
+    base_attrs_ = MakeAttrMapFromUserOpConf(fw_op_expr->proto());
+    return Maybe<void>::Ok();
+  }
+
+  // inputs: a_crow, a_col, a_val, b — index inputs never receive a gradient
+  Maybe<void> Capture(SpmmCsrCaptureState* ctx, const TensorTuple& inputs, const TensorTuple& outputs,
+                      const AttrMap& attrs) const override {
+    ctx->val_requires_grad = inputs.at(2)->requires_grad();
+    ctx->b_requires_grad = inputs.at(3)->requires_grad();
+    if (!ctx->val_requires_grad && !ctx->b_requires_grad) { return Maybe<void>::Ok(); }
+    ComposedAttrMap composed_attrs(attrs, base_attrs_);
+    ctx->a_rows = JUST(composed_attrs.GetAttr<int64_t>("a_rows"));
+    ctx->a_cols = JUST(composed_attrs.GetAttr<int64_t>("a_cols"));
+    ctx->crow_index = ctx->SaveTensorForBackward(inputs.at(0));
+    ctx->col_index = ctx->SaveTensorForBackward(inputs.at(1));
+    if (ctx->b_requires_grad) { ctx->val_index = ctx->SaveTensorForBackward(inputs.at(2)); }
+    if (ctx->val_requires_grad) { ctx->b_index = ctx->SaveTensorForBackward(inputs.at(3)); }
+    return Maybe<void>::Ok();
+  }
+
+  Maybe<void> Apply(const SpmmCsrCaptureState* ctx, const TensorTuple& out_grads,
+                    TensorTuple* in_grads) const override {
+    if (!ctx->val_requires_grad && !ctx->b_requires_grad) { return Maybe<void>::Ok(); }
+    CHECK_EQ_OR_RETURN(out_grads.size(), 1);  // NOLINT(maybe-need-error-msg)
+    in_grads->resize(4);
+    const auto& crow = ctx->SavedTensors().at(ctx->crow_index);
+    const auto& col = ctx->SavedTensors().at(ctx->col_index);
+    if (ctx->val_requires_grad) {  // dval[p] = <dy[i,:], b[col[p],:]>
+      const auto& b = ctx->SavedTensors().at(ctx->b_index);
+      in_grads->at(2) = JUST(functional::SddmmCsr(crow, col, out_grads.at(0), b, ctx->a_rows, ctx->a_cols));
+    }
+    if (ctx->b_requires_grad) {    // db = A^T · dy
+      const auto& val = ctx->SavedTensors().at(ctx->val_index);
+      in_grads->at(3) = JUST(functional::SpmmCsrGradB(crow, col, val, out_grads.at(0), ctx->a_rows, ctx->a_cols));
+    }
+    return Maybe<void>::Ok();
+  }
+
+ private:
+  AttrMap base_attrs_;
+};
+
+REGISTER_OP_EXPR_GRAD_FUNCTION("spmm_csr", SpmmCsr);
+
+}  // namespace one
+}  // namespace oneflow
