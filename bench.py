@@ -202,6 +202,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--bwd", default="transpose", choices=["transpose", "atomic"])
+    ap.add_argument("--no-graph", action="store_true", help="N>1: run the sharded step eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--panels", type=int, default=2, help="N>1: column panels used to pipeline the collectives")
     args = ap.parse_args()
     args.warmup = max(3, args.warmup)
     if args.impl == "reference":
@@ -235,11 +237,19 @@ def main():
 
     if world > 1:
         dmod = __import__("importlib").import_module("of-spmm_b200.dist")
-        runner = dmod.ShardedSpmm(A, n, dtype, rank, world, dev, bwd=args.bwd)
+        runner = dmod.ShardedSpmm(A, n, dtype, rank, world, dev, bwd=args.bwd, panels=args.panels)
         B_in, dY_in = runner.shard_rows(B), runner.shard_rows_out(dY)
-        step = lambda: runner.step(B_in, dY_in)
-        fwd_only = lambda: runner.forward(B_in)
-        parallelism = f"row-block x{world} (nnz-balanced), B all-gather overlapped"
+        step_eager = lambda: runner.step(B_in, dY_in)
+        l0 = ofs.launch_count()
+        step_eager()
+        graph_launches_per_step = ofs.launch_count() - l0
+        if args.no_graph:
+            step, fwd_only = step_eager, (lambda: runner.forward(B_in))
+        else:  # one CUDA graph per step: kernels + copies + NCCL collectives, no host launch gaps
+            step = runner.capture(step_eager)
+            fwd_only = runner.capture(lambda: runner.forward(B_in))
+        parallelism = (f"row-block x{world} (nnz-balanced), {runner.panels} column panels, all-gather / "
+                       f"reduce-scatter pipelined with compute, " + ("eager" if args.no_graph else "CUDA-graph replay"))
     else:
         t0 = time.perf_counter()
         tr = ops.csr_transpose(A.crow, A.col, A.val, A.rows, A.cols) if args.bwd == "transpose" else None
@@ -280,6 +290,8 @@ def main():
     barrier()
     total_ms = ev[0].elapsed_time(ev[1])
     launches = ofs.launch_count() - launches0
+    if world > 1 and not args.no_graph and launches == 0:
+        launches = graph_launches_per_step * args.steps   # replayed from the captured graph
     # dominant kernel (forward): its own CUDA-event loop right after, same residency / clocks
     for i in range(args.steps):
         fwd_ev[i][0].record()

@@ -88,6 +88,12 @@ template <typename DT, int VEC> struct RowVec;
 template <> struct RowVec<float, 4> {
   using Raw = uint4;
   __device__ __forceinline__ static Raw load_raw(const float* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+  __device__ __forceinline__ static float dot(const float (&y)[4], const Raw& r, float acc) {
+    acc = fmaf(y[0], __uint_as_float(r.x), acc);
+    acc = fmaf(y[1], __uint_as_float(r.y), acc);
+    acc = fmaf(y[2], __uint_as_float(r.z), acc);
+    return fmaf(y[3], __uint_as_float(r.w), acc);
+  }
   __device__ __forceinline__ static void fma(float (&acc)[4], float v, const Raw& r) {
     acc[0] = fmaf(v, __uint_as_float(r.x), acc[0]);
     acc[1] = fmaf(v, __uint_as_float(r.y), acc[1]);
@@ -106,6 +112,7 @@ template <> struct RowVec<float, 4> {
 template <> struct RowVec<float, 1> {
   using Raw = float;
   __device__ __forceinline__ static Raw load_raw(const float* p) { return __ldg(p); }
+  __device__ __forceinline__ static float dot(const float (&y)[1], const Raw& r, float acc) { return fmaf(y[0], r, acc); }
   __device__ __forceinline__ static void fma(float (&acc)[1], float v, const Raw& r) { acc[0] = fmaf(v, r, acc[0]); }
   __device__ __forceinline__ static void load(const float* p, float (&out)[1]) { out[0] = __ldg(p); }
   __device__ __forceinline__ static void store_stream(float* p, const float (&v)[1]) { __stcs(p, v[0]); }
@@ -114,6 +121,15 @@ template <> struct RowVec<float, 1> {
 template <> struct RowVec<__nv_bfloat16, 8> {
   using Raw = uint4;
   __device__ __forceinline__ static Raw load_raw(const __nv_bfloat16* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+  __device__ __forceinline__ static float dot(const float (&y)[8], const Raw& r, float acc) {
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      acc = fmaf(y[2 * i], __uint_as_float(w[i] << 16), acc);
+      acc = fmaf(y[2 * i + 1], __uint_as_float(w[i] & 0xffff0000u), acc);
+    }
+    return acc;
+  }
   __device__ __forceinline__ static void fma(float (&acc)[8], float v, const Raw& r) {
     const uint32_t w[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
@@ -145,6 +161,9 @@ template <> struct RowVec<__nv_bfloat16, 8> {
 template <> struct RowVec<__nv_bfloat16, 1> {
   using Raw = unsigned short;
   __device__ __forceinline__ static Raw load_raw(const __nv_bfloat16* p) { return __ldg(reinterpret_cast<const unsigned short*>(p)); }
+  __device__ __forceinline__ static float dot(const float (&y)[1], const Raw& r, float acc) {
+    return fmaf(y[0], __uint_as_float(static_cast<uint32_t>(r) << 16), acc);
+  }
   __device__ __forceinline__ static void fma(float (&acc)[1], float v, const Raw& r) {
     acc[0] = fmaf(v, __uint_as_float(static_cast<uint32_t>(r) << 16), acc[0]);
   }

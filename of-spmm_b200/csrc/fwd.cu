@@ -6,12 +6,12 @@ namespace ofspmm {
 
 namespace {
 
-template <typename DT, typename ValT, typename IdxT, int VEC, int LPR, int CH, bool kFull>
+template <typename DT, typename ValT, typename IdxT, int VEC, int LPR, int CH, bool kFull, bool kRowPar = false>
 int launch_full(FwdParams p, int panels, cudaStream_t stream) {
   p.panels = panels;
   constexpr int ITEMS = kTaskItems;
   constexpr int WARPS = kWarpsPerCta;
-  auto kern = spmm_merge_kernel<DT, ValT, IdxT, VEC, LPR, CH, kFull, ITEMS, WARPS>;
+  auto kern = spmm_merge_kernel<DT, ValT, IdxT, VEC, LPR, CH, kFull, kRowPar, ITEMS, WARPS>;
   const size_t smem = sizeof(TaskStage<IdxT, ValT, ITEMS>) * WARPS + sizeof(uint64_t) * WARPS;
   OFSPMM_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   DevInfo dev;
@@ -29,7 +29,7 @@ int launch_full(FwdParams p, int panels, cudaStream_t stream) {
   OFSPMM_CUDA_OK(cudaGetLastError());
   // stitch rows that span several tasks
   auto fix = spmm_fixup_kernel<DT, IdxT, VEC, WARPS>;
-  fix<<<static_cast<unsigned>(ctas_needed), WARPS * 32, 0, stream>>>(p);
+  fix<<<static_cast<unsigned>((ctas_needed + 31) / 32), WARPS * 32, 0, stream>>>(p);  // one lane per task
   count_launch();
   OFSPMM_CUDA_OK(cudaGetLastError());
   return OFSPMM_OK;
@@ -53,6 +53,10 @@ int launch_typed(const FwdParams& p, bool aligned, cudaStream_t stream) {
 #ifdef OFSPMM_FORCE_PANEL16
     // tuning experiment: half-width column panels (B panel = half the bytes in L2)
     if (nvec % 16 == 0) return launch_one<DT, ValT, IdxT, VECW, 16, 1>(p, nvec / 16, stream);
+#endif
+#ifdef OFSPMM_FORCE_ROWPAR
+    // tuning experiment: row-parallel layout (8 lanes x 4 chunks per row, 4 rows in flight per warp)
+    if (nvec == 32) return launch_full<DT, ValT, IdxT, VECW, 8, 4, true, true>(p, 1, stream);
 #endif
     if (nvec <= 32) return launch_one<DT, ValT, IdxT, VECW, 32, 1>(p, 1, stream);
     if (nvec <= 64) return launch_one<DT, ValT, IdxT, VECW, 32, 2>(p, 1, stream);

@@ -14,7 +14,7 @@ namespace ofspmm {
 #define OFSPMM_ITEMS 256
 #endif
 #ifndef OFSPMM_WARPS
-#define OFSPMM_WARPS 8
+#define OFSPMM_WARPS 4
 #endif
 constexpr int kTaskItems = OFSPMM_ITEMS;  // merge items (row-ends + non-zeros) per warp task
 constexpr int kWarpsPerCta = OFSPMM_WARPS;

@@ -1,4 +1,4 @@
-// sddmm.cu — variant selection and launch of the SDDMM value-gradient kernel.
+// sddmm.cu — variant selection and launch of the SDDMM value-gradient kernels.
 #include "internal.h"
 #include "sddmm_bwd_kernels.cuh"
 
@@ -6,12 +6,9 @@ namespace ofspmm {
 
 namespace {
 
-template <typename DT, typename ValT, typename IdxT, int VEC, int LPR, int CH>
-int launch_one(const SddmmParams& p, cudaStream_t stream) {
-  constexpr int ITEMS = kTaskItems;
+template <typename Kern>
+int launch_persistent(Kern kern, const SddmmParams& p, size_t smem, cudaStream_t stream) {
   constexpr int WARPS = kWarpsPerCta;
-  auto kern = sddmm_merge_kernel<DT, ValT, IdxT, VEC, LPR, CH, ITEMS, WARPS>;
-  const size_t smem = sizeof(TaskStage<IdxT, float, ITEMS>) * WARPS + sizeof(uint64_t) * WARPS;
   OFSPMM_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   DevInfo dev;
   if (int rc = get_dev_info(&dev)) return rc;
@@ -27,6 +24,24 @@ int launch_one(const SddmmParams& p, cudaStream_t stream) {
   return OFSPMM_OK;
 }
 
+template <typename DT, typename ValT, typename IdxT, int VEC, int LPR, int CH>
+int launch_one(const SddmmParams& p, cudaStream_t stream) {
+  constexpr int ITEMS = kTaskItems;
+  constexpr int WARPS = kWarpsPerCta;
+  const size_t smem = sizeof(TaskStage<IdxT, float, ITEMS>) * WARPS + sizeof(uint64_t) * WARPS;
+  if (p.n % (LPR * VEC * CH) == 0)
+    return launch_persistent(sddmm_merge_kernel<DT, ValT, IdxT, VEC, LPR, CH, true, ITEMS, WARPS>, p, smem, stream);
+  return launch_persistent(sddmm_merge_kernel<DT, ValT, IdxT, VEC, LPR, CH, false, ITEMS, WARPS>, p, smem, stream);
+}
+
+template <typename DT, typename ValT, typename IdxT, int VEC>
+int launch_wide(const SddmmParams& p, cudaStream_t stream) {
+  constexpr int ITEMS = kTaskItems;
+  constexpr int WARPS = kWarpsPerCta;
+  const size_t smem = sizeof(TaskStage<IdxT, float, ITEMS>) * WARPS + sizeof(uint64_t) * WARPS;
+  return launch_persistent(sddmm_wide_kernel<DT, ValT, IdxT, VEC, ITEMS, WARPS>, p, smem, stream);
+}
+
 template <typename DT, typename ValT, typename IdxT>
 int launch_typed(const SddmmParams& p, bool aligned, cudaStream_t stream) {
   constexpr int VECW = 16 / sizeof(DT);
@@ -38,11 +53,11 @@ int launch_typed(const SddmmParams& p, bool aligned, cudaStream_t stream) {
     if (nvec <= 32) return launch_one<DT, ValT, IdxT, VECW, 32, 1>(p, stream);
     if (nvec <= 64) return launch_one<DT, ValT, IdxT, VECW, 32, 2>(p, stream);
     if (nvec <= 128) return launch_one<DT, ValT, IdxT, VECW, 32, 4>(p, stream);
-    return launch_one<DT, ValT, IdxT, VECW, 32, 0>(p, stream);
+    return launch_wide<DT, ValT, IdxT, VECW>(p, stream);
   }
   if (n <= 32) return launch_one<DT, ValT, IdxT, 1, 32, 1>(p, stream);
   if (n <= 128) return launch_one<DT, ValT, IdxT, 1, 32, 4>(p, stream);
-  return launch_one<DT, ValT, IdxT, 1, 32, 0>(p, stream);
+  return launch_wide<DT, ValT, IdxT, 1>(p, stream);
 }
 
 template <typename IdxT>

@@ -1,5 +1,5 @@
 // sddmm_bwd_kernels.cuh — SDDMM value gradient and the atomic A^T·dY scatter, both on the same
-// merge-path task list as the forward kernel (see spmm_kernels.cuh for the scheduling notes).
+// merge-path task list and TMA staging as the forward kernel (see spmm_kernels.cuh).
 #pragma once
 #include "spmm_kernels.cuh"
 
@@ -19,15 +19,29 @@ struct SddmmParams {
   int P;
 };
 
-// dval[p] = <dY[i,:], B[col[p],:]>.  LPR lanes span one dense row (CH chunks of VEC each; CH == 0
-// means "loop over n", used when the row does not fit the register tile).  The dY row chunk
-// stays in registers while the task walks the row's non-zeros; each non-zero costs one coalesced
-// gather of its B row, VEC*CH FMAs and a log2(LPR) xor-shuffle reduction.
-template <typename DT, typename ValT, typename IdxT, int VEC, int LPR, int CH, int ITEMS, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32) sddmm_merge_kernel(const SddmmParams p) {
+// Lanes of one group (LPR consecutive lanes).
+template <int LPR>
+__device__ __forceinline__ unsigned group_mask(int grp) {
+  if constexpr (LPR == 32) return 0xffffffffu;
+  return ((1u << LPR) - 1u) << (grp * LPR);
+}
+
+// dval[p] = <dY[i,:], B[col[p],:]>.
+// LPR lanes span one dense row (CH chunks of VEC each); the dY row chunk stays in registers while
+// the task walks the row's non-zeros.  Hot loop per 4 non-zeros and lane group: one LDS.128 of 4
+// column indices, 4·CH coalesced 16-byte gathers in flight, 4 partial dots, then a
+// transpose-reduce across the LPR lanes (log2(LPR)+1 shuffles for the 4 results instead of
+// 4·log2(LPR)).  Results are staged in shared memory (the stage's unused value array) and written
+// back coalesced; out-of-range columns produce 0 (the oracle's convention).
+template <typename DT, typename ValT, typename IdxT, int VEC, int LPR, int CH, bool kFull, int ITEMS, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, min_ctas_per_sm<DT, CH>())
+sddmm_merge_kernel(const SddmmParams p) {
   constexpr int G = 32 / LPR;
-  constexpr int CHR = CH > 0 ? CH : 1;
-  using Stage = TaskStage<IdxT, float, ITEMS>;  // val array reused as the output staging buffer
+  constexpr bool kVecIdx = sizeof(IdxT) == 4;
+  constexpr uint32_t kChunkBytes = LPR * VEC * sizeof(DT);
+  using Stage = TaskStage<IdxT, float, ITEMS>;  // .val doubles as the fp32 result staging buffer
+  using RV = RowVec<DT, VEC>;
+  static_assert(LPR >= 4, "transpose-reduce needs at least 4 lanes per row");
 
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Stage* stages = reinterpret_cast<Stage*>(smem_raw);
@@ -37,8 +51,10 @@ __global__ void __launch_bounds__(WARPS * 32) sddmm_merge_kernel(const SddmmPara
   const int lane = threadIdx.x & 31;
   const int grp = lane / LPR;
   const int lig = lane % LPR;
+  const unsigned gmask = group_mask<LPR>(grp);
   Stage& st = stages[warp];
   uint64_t* bar = &bars[warp];
+  const uint32_t col_sa = smem_u32(st.col);
   if (lane == 0) mbar_init(bar, 1);
   fence_mbar_init();
   __syncwarp();
@@ -46,15 +62,23 @@ __global__ void __launch_bounds__(WARPS * 32) sddmm_merge_kernel(const SddmmPara
   const uint64_t pol_stream = l2_policy_evict_first();
   const IdxT* __restrict__ crow = static_cast<const IdxT*>(p.crow);
   const IdxT* __restrict__ col = static_cast<const IdxT*>(p.col);
-  const DT* __restrict__ B = static_cast<const DT*>(p.B);
-  const DT* __restrict__ dY = static_cast<const DT*>(p.dY);
   ValT* __restrict__ dval = static_cast<ValT*>(p.dval);
   const int n = p.n;
-  const int c_lane = lig * VEC;
-  unsigned chmask = 0;
+  const uint32_t row_bytes = static_cast<uint32_t>(n) * sizeof(DT);
+
+  // this lane's columns; masked chunks point at column 0 with a zero dY chunk
+  const int col0 = lig * VEC;
+  uint32_t choff[CH];
+  bool chok[CH];
 #pragma unroll
-  for (int ch = 0; ch < CHR; ++ch)
-    if (c_lane + ch * LPR * VEC < n) chmask |= 1u << ch;
+  for (int ch = 0; ch < CH; ++ch) {
+    chok[ch] = kFull || (col0 + ch * LPR * VEC < n);
+    choff[ch] = chok[ch] ? static_cast<uint32_t>(col0 + ch * LPR * VEC) * sizeof(DT) : 0u;
+  }
+  unsigned long long bl_bits = reinterpret_cast<unsigned long long>(p.B) + (kFull ? choff[0] : 0u);
+  asm volatile("" : "+l"(bl_bits));  // one 64-bit register: gather address = IMAD.WIDE.U32
+  const char* __restrict__ Bl = reinterpret_cast<const char*>(bl_bits);
+  const char* __restrict__ Yl = static_cast<const char*>(p.dY);
 
   const int total_warps = gridDim.x * WARPS;
   uint32_t phase = 0;
@@ -64,82 +88,186 @@ __global__ void __launch_bounds__(WARPS * 32) sddmm_merge_kernel(const SddmmPara
     const int2 pe = __ldg(&p.part[k + 1]);
     const int rs = ps.x, ns = ps.y, re = pe.x, ne = pe.y;
     const int cnt_nz = ne - ns;
-    const int cnt_row = re - rs + 1;
     if (cnt_nz == 0) continue;
-
-    int pre_c, head_c, body_c, pre_r, head_r, body_r;
-    seg_plan(col + ns, cnt_nz, pre_c, head_c, body_c);
-    seg_plan(crow + rs, cnt_row, pre_r, head_r, body_r);
-    const uint32_t tx = static_cast<uint32_t>((body_c + body_r) * sizeof(IdxT));
-    __syncwarp();
-    if (lane == 0 && tx != 0) {
-      mbar_arrive_expect_tx(bar, tx);
-      if (body_c) tma_bulk_g2s(st.col + pre_c + head_c, col + ns + head_c, body_c * sizeof(IdxT), bar, pol_stream);
-      if (body_r) tma_bulk_g2s(st.crow + pre_r + head_r, crow + rs + head_r, body_r * sizeof(IdxT), bar, pol_stream);
-    }
-    seg_copy_edges(st.col, col + ns, cnt_nz, pre_c, head_c, body_c, lane);
-    seg_copy_edges(st.crow, crow + rs, cnt_row, pre_r, head_r, body_r, lane);
-    if (tx != 0) {
-      mbar_wait(bar, phase);
-      phase ^= 1;
-    }
-    __syncwarp();
-    const IdxT* scol = st.col + pre_c;
-    const IdxT* srow = st.crow + pre_r;
-    float* sout = st.val;  // sout[e] = result for non-zero ns + e
+    const StagedTask<IdxT, float> tk = stage_task<false>(st, bar, phase, crow, col, static_cast<const float*>(nullptr),
+                                                        rs, ns, re - rs + 1, cnt_nz, p.cols, lane, pol_stream);
+    float* sout = st.val;  // sout[e] = result of non-zero ns + e
 
     int e = 0;
     for (int r = rs; r <= re; ++r) {
-      const int e_end = r < re ? static_cast<int>(srow[r - rs + 1]) - ns : cnt_nz;
+      const int e_end = r < re ? static_cast<int>(tk.srow[r - rs + 1]) - ns : cnt_nz;
       if (e_end <= e) continue;
-      const DT* yrow = dY + static_cast<size_t>(r) * n + c_lane;
-      float y[CHR][VEC];
-      if constexpr (CH > 0) {
+      // dY row chunk → registers
+      float y[CH][VEC];
+      const char* yrow = Yl + static_cast<unsigned long long>(static_cast<uint32_t>(r)) * row_bytes;
 #pragma unroll
-        for (int ch = 0; ch < CH; ++ch) {
-          if (chmask & (1u << ch)) {
-            RowVec<DT, VEC>::load(yrow + ch * LPR * VEC, y[ch]);
-          } else {
+      for (int ch = 0; ch < CH; ++ch) {
+        if (chok[ch]) {
+          RV::load(reinterpret_cast<const DT*>(yrow + choff[ch]), y[ch]);
+        } else {
 #pragma unroll
-            for (int i = 0; i < VEC; ++i) y[ch][i] = 0.f;
-          }
+          for (int i = 0; i < VEC; ++i) y[ch][i] = 0.f;
         }
       }
-      for (int q = e + grp; q < e_end + grp; q += G) {  // uniform trip count across groups
-        const bool live = q < e_end;
-        IdxT c = live ? scol[q] : 0;
-        const bool ok = live && static_cast<unsigned long long>(c) < static_cast<unsigned long long>(p.cols);
-        if (!ok) c = 0;
-        const DT* brow = B + static_cast<size_t>(c) * n + c_lane;
-        float dot = 0.f;
-        if constexpr (CH > 0) {
-          float x[CH][VEC];
+
+      auto dot_one = [&](int elem) {  // full dot of one staged element, result in every group lane
+        const IdxT c = tk.scol[elem];
+        const char* brow = Bl + row_offset(c, row_bytes);
+        float d = 0.f;
 #pragma unroll
-          for (int ch = 0; ch < CH; ++ch)
-            if (chmask & (1u << ch)) RowVec<DT, VEC>::load(brow + ch * LPR * VEC, x[ch]);
+        for (int ch = 0; ch < CH; ++ch)
+          d = RV::dot(y[ch], load_b<DT, VEC>(brow + (kFull ? ch * kChunkBytes : choff[ch]), 0), d);
 #pragma unroll
-          for (int ch = 0; ch < CH; ++ch)
-            if (chmask & (1u << ch))
+        for (int off = LPR / 2; off > 0; off >>= 1) d += __shfl_xor_sync(gmask, d, off);
+        if (lig == 0) sout[elem] = d;
+      };
+
+      if constexpr (kVecIdx) {
+        // slots s = pre_c + e, read as 16-byte chunks of 4; chunk q of the row goes to group q % G.
+        // First / last chunk: slots outside the row are masked (no gather, no result written).
+        const int s0 = tk.pre_c + e, s1 = tk.pre_c + e_end;
+        const int cbase = s0 & ~3;
+        const int nchunks = ((s1 + 3) >> 2) - (s0 >> 2);
+        // 4 partial dots -> transpose-reduce over the LPR lanes -> writer lanes store valid slots
+        auto reduce_store = [&](float (&d)[4], int sa) {
+          constexpr int H = LPR / 2, Q = LPR / 4;
+          const bool up = (lig & H) != 0;
+          float k0 = up ? d[2] : d[0], k1 = up ? d[3] : d[1];
+          const float t0 = up ? d[0] : d[2], t1 = up ? d[1] : d[3];
+          k0 += __shfl_xor_sync(gmask, t0, H);
+          k1 += __shfl_xor_sync(gmask, t1, H);
+          const bool uq = (lig & Q) != 0;
+          float kv = uq ? k1 : k0;
+          const float tv = uq ? k0 : k1;
+          kv += __shfl_xor_sync(gmask, tv, Q);
 #pragma unroll
-              for (int i = 0; i < VEC; ++i) dot = fmaf(y[ch][i], x[ch][i], dot);
-        } else {
-          for (int c0 = 0; c_lane + c0 < n; c0 += LPR * VEC) {
-            float x[VEC], yy[VEC];
-            RowVec<DT, VEC>::load(brow + c0, x);
-            RowVec<DT, VEC>::load(yrow + c0, yy);
+          for (int off = Q / 2; off > 0; off >>= 1) kv += __shfl_xor_sync(gmask, kv, off);
+          const int slot = sa + (up ? 2 : 0) + (uq ? 1 : 0);
+          if ((lig & (Q - 1)) == 0 && slot >= s0 && slot < s1) sout[slot - tk.pre_c] = kv;
+        };
+        auto edge_chunk = [&](int q) {
+          const int sa = cbase + 4 * q;
+          const uint4 cn = lds128(col_sa + static_cast<uint32_t>(sa) * 4u);
+          const uint32_t c4[4] = {cn.x, cn.y, cn.z, cn.w};
+          float d[4];
 #pragma unroll
-            for (int i = 0; i < VEC; ++i) dot = fmaf(yy[i], x[i], dot);
+          for (int u = 0; u < 4; ++u) {
+            d[u] = 0.f;
+            if (sa + u >= s0 && sa + u < s1) {
+              const char* brow = Bl + static_cast<unsigned long long>(c4[u]) * row_bytes;
+#pragma unroll
+              for (int ch = 0; ch < CH; ++ch)
+                d[u] = RV::dot(y[ch], load_b<DT, VEC>(brow + (kFull ? ch * kChunkBytes : choff[ch]), 0), d[u]);
+            }
           }
-        }
+          reduce_store(d, sa);
+        };
+        if (grp == 0) edge_chunk(0);
+        int q = grp == 0 ? G : grp;
+        const int qend = nchunks - 1;
+        if (q < qend) {
+          uint32_t ca = col_sa + static_cast<uint32_t>(cbase + 4 * q) * 4u;
+          const uint32_t cend = col_sa + static_cast<uint32_t>(cbase + 4 * qend) * 4u;
+          int sa = cbase + 4 * q;
+          uint4 cn = lds128(ca);
+          do {
+            const uint32_t c4[4] = {cn.x, cn.y, cn.z, cn.w};
+            typename RV::Raw x[4][CH];
 #pragma unroll
-        for (int off = LPR / 2; off > 0; off >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, off);
-        if (live && lig == 0) sout[q] = ok ? dot : 0.f;
+            for (int u = 0; u < 4; ++u) {
+              const char* brow = Bl + static_cast<unsigned long long>(c4[u]) * row_bytes;
+#pragma unroll
+              for (int ch = 0; ch < CH; ++ch)
+                x[u][ch] = load_b<DT, VEC>(brow + (kFull ? ch * kChunkBytes : choff[ch]), 0);
+            }
+            ca += 16u * G;
+            if (ca < cend) cn = lds128(ca);
+            float d[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              d[u] = 0.f;
+#pragma unroll
+              for (int ch = 0; ch < CH; ++ch) d[u] = RV::dot(y[ch], x[u][ch], d[u]);
+            }
+            reduce_store(d, sa);
+            sa += 4 * G;
+            q += G;
+          } while (ca < cend);
+        }
+        if (nchunks > 1 && q == qend) edge_chunk(qend);
+      } else {
+        for (int el = e + grp; el < e_end; el += G) dot_one(el);
       }
       e = e_end;
     }
     __syncwarp();
-    // coalesced write-back of the task's results
-    for (int q = lane; q < cnt_nz; q += 32) dval[ns + q] = from_float<ValT>(sout[q]);
+    // coalesced write-back; out-of-range columns give 0
+    for (int q0 = 0; q0 < cnt_nz; q0 += 32) {
+      const unsigned bad = __shfl_sync(0xffffffffu, tk.badmask, q0 >> 5);
+      const int q = q0 + lane;
+      if (q < cnt_nz) dval[ns + q] = from_float<ValT>(((bad >> lane) & 1u) ? 0.f : sout[q]);
+    }
+  }
+}
+
+// Very wide dense rows (n beyond the register tile): loop over the row in LPR*VEC-column steps,
+// re-reading the dY chunk from L1 each time.
+template <typename DT, typename ValT, typename IdxT, int VEC, int ITEMS, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) sddmm_wide_kernel(const SddmmParams p) {
+  using Stage = TaskStage<IdxT, float, ITEMS>;
+  using RV = RowVec<DT, VEC>;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Stage* stages = reinterpret_cast<Stage*>(smem_raw);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + sizeof(Stage) * WARPS);
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  Stage& st = stages[warp];
+  uint64_t* bar = &bars[warp];
+  if (lane == 0) mbar_init(bar, 1);
+  fence_mbar_init();
+  __syncwarp();
+  const uint64_t pol_stream = l2_policy_evict_first();
+  const IdxT* __restrict__ crow = static_cast<const IdxT*>(p.crow);
+  const IdxT* __restrict__ col = static_cast<const IdxT*>(p.col);
+  const DT* __restrict__ B = static_cast<const DT*>(p.B);
+  const DT* __restrict__ dY = static_cast<const DT*>(p.dY);
+  ValT* __restrict__ dval = static_cast<ValT*>(p.dval);
+  const int n = p.n;
+  const int total_warps = gridDim.x * WARPS;
+  uint32_t phase = 0;
+  for (int k = blockIdx.x * WARPS + warp; k < p.P; k += total_warps) {
+    const int2 ps = __ldg(&p.part[k]);
+    const int2 pe = __ldg(&p.part[k + 1]);
+    const int rs = ps.x, ns = ps.y, re = pe.x, ne = pe.y;
+    const int cnt_nz = ne - ns;
+    if (cnt_nz == 0) continue;
+    const StagedTask<IdxT, float> tk = stage_task<false>(st, bar, phase, crow, col, static_cast<const float*>(nullptr),
+                                                        rs, ns, re - rs + 1, cnt_nz, p.cols, lane, pol_stream);
+    float* sout = st.val;
+    int e = 0;
+    for (int r = rs; r <= re; ++r) {
+      const int e_end = r < re ? static_cast<int>(tk.srow[r - rs + 1]) - ns : cnt_nz;
+      const DT* yrow = dY + static_cast<size_t>(r) * n;
+      for (int q = e; q < e_end; ++q) {
+        const DT* brow = B + static_cast<size_t>(tk.scol[q]) * n;
+        float d = 0.f;
+        for (int c0 = lane * VEC; c0 < n; c0 += 32 * VEC) {
+          float yy[VEC];
+          RV::load(yrow + c0, yy);
+          d = RV::dot(yy, RV::load_raw(brow + c0), d);
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) d += __shfl_xor_sync(0xffffffffu, d, off);
+        if (lane == 0) sout[q] = d;
+      }
+      if (e_end > e) e = e_end;
+    }
+    __syncwarp();
+    for (int q0 = 0; q0 < cnt_nz; q0 += 32) {
+      const unsigned bad = __shfl_sync(0xffffffffu, tk.badmask, q0 >> 5);
+      const int q = q0 + lane;
+      if (q < cnt_nz) dval[ns + q] = from_float<ValT>(((bad >> lane) & 1u) ? 0.f : sout[q]);
+    }
   }
 }
 
@@ -210,45 +338,21 @@ __global__ void __launch_bounds__(WARPS * 32) bwd_atomic_kernel(const BwdAtomicP
     const int2 pe = __ldg(&p.part[k + 1]);
     const int rs = ps.x, ns = ps.y, re = pe.x, ne = pe.y;
     const int cnt_nz = ne - ns;
-    const int cnt_row = re - rs + 1;
     if (cnt_nz == 0) continue;
-    int pre_c, head_c, body_c, pre_v, head_v, body_v, pre_r, head_r, body_r;
-    seg_plan(col + ns, cnt_nz, pre_c, head_c, body_c);
-    seg_plan(val + ns, cnt_nz, pre_v, head_v, body_v);
-    seg_plan(crow + rs, cnt_row, pre_r, head_r, body_r);
-    const uint32_t tx = static_cast<uint32_t>(body_c * sizeof(IdxT) + body_v * sizeof(ValT) +
-                                              body_r * sizeof(IdxT));
-    __syncwarp();
-    if (lane == 0 && tx != 0) {
-      mbar_arrive_expect_tx(bar, tx);
-      if (body_c) tma_bulk_g2s(st.col + pre_c + head_c, col + ns + head_c, body_c * sizeof(IdxT), bar, pol_stream);
-      if (body_v) tma_bulk_g2s(st.val + pre_v + head_v, val + ns + head_v, body_v * sizeof(ValT), bar, pol_stream);
-      if (body_r) tma_bulk_g2s(st.crow + pre_r + head_r, crow + rs + head_r, body_r * sizeof(IdxT), bar, pol_stream);
-    }
-    seg_copy_edges(st.col, col + ns, cnt_nz, pre_c, head_c, body_c, lane);
-    seg_copy_edges(st.val, val + ns, cnt_nz, pre_v, head_v, body_v, lane);
-    seg_copy_edges(st.crow, crow + rs, cnt_row, pre_r, head_r, body_r, lane);
-    if (tx != 0) {
-      mbar_wait(bar, phase);
-      phase ^= 1;
-    }
-    __syncwarp();
-    const IdxT* scol = st.col + pre_c;
-    const ValT* sval = st.val + pre_v;
-    const IdxT* srow = st.crow + pre_r;
-
+    // sanitised staging: out-of-range entries become (col 0, val 0) and add nothing
+    const StagedTask<IdxT, ValT> tk = stage_task<true>(st, bar, phase, crow, col, val, rs, ns, re - rs + 1,
+                                                       cnt_nz, p.cols, lane, pol_stream);
     int e = 0;
     for (int r = rs; r <= re; ++r) {
-      const int e_end = r < re ? static_cast<int>(srow[r - rs + 1]) - ns : cnt_nz;
+      const int e_end = r < re ? static_cast<int>(tk.srow[r - rs + 1]) - ns : cnt_nz;
       if (e_end <= e) continue;
       float y[CH][VEC];
 #pragma unroll
       for (int ch = 0; ch < CH; ++ch)
         if (chmask & (1u << ch)) RowVec<DT, VEC>::load(dYl + static_cast<size_t>(r) * n + ch * LPR * VEC, y[ch]);
       for (int q = e + grp; q < e_end; q += G) {
-        const IdxT c = scol[q];
-        if (static_cast<unsigned long long>(c) >= static_cast<unsigned long long>(p.cols)) continue;
-        const float v = to_float(sval[q]);
+        const IdxT c = tk.scol[q];
+        const float v = to_float(tk.sval[q]);
         float* dst = accl + static_cast<size_t>(c) * n;
 #pragma unroll
         for (int ch = 0; ch < CH; ++ch)

@@ -30,11 +30,20 @@
 #ifndef OFSPMM_B_LOAD
 #define OFSPMM_B_LOAD 0  // 0: ld.global.nc   1: + L1::no_allocate   2: + L2 evict_last policy
 #endif
-#ifndef OFSPMM_MIN_CTAS
-#define OFSPMM_MIN_CTAS 5
-#endif
 
 namespace ofspmm {
+
+// Resident CTAs per SM the kernels are compiled for (4 warps per CTA): sets the register cap.
+// Measured on B200 (tools/sweep_fwd.py, profiles/r1_tuning_sweeps.md): fp32 rows run best at 36
+// warps/SM with 54 registers, bf16 rows (8 accumulators + unpacking) at 32 warps/SM with 60.
+template <typename DT, int CH>
+constexpr int min_ctas_per_sm() {
+#ifdef OFSPMM_MIN_CTAS
+  return CH == 1 ? OFSPMM_MIN_CTAS : (CH == 2 ? 6 : 4);
+#else
+  return CH == 1 ? (sizeof(DT) == 4 ? 9 : 8) : (CH == 2 ? 6 : 4);
+#endif
+}
 
 struct FwdParams {
   const void* crow;
@@ -93,6 +102,8 @@ struct StagedTask {
   const ValT* sval;  // sval[e] = val[ns + e]   (unused when values are not staged)
   const IdxT* srow;  // srow[i] = crow[rs + i]
   int pre_c, pre_v;  // slot of element 0 inside st.col / st.val (address alignment phase)
+  // lane i holds the bit mask of out-of-range elements 32*i .. 32*i+31 of the task
+  unsigned badmask;
 };
 
 // Stages crow[rs..re], col[ns..ne) and (optionally) val[ns..ne) of a task: TMA bulk copies for
@@ -125,15 +136,24 @@ __device__ __forceinline__ StagedTask<IdxT, ValT> stage_task(
   }
   __syncwarp();
   // sanitise: indices outside [0, cols) contribute nothing (reference: segment-sum skips them)
-  for (int e = lane; e < cnt_nz; e += 32) {
-    const IdxT c = st.col[pre_c + e];
-    if (static_cast<unsigned long long>(c) >= static_cast<unsigned long long>(cols)) {
-      st.col[pre_c + e] = 0;
-      if constexpr (kWithVal) st.val[pre_v + e] = from_float<ValT>(0.f);
+  unsigned badmask = 0;
+  for (int e0 = 0; e0 < cnt_nz; e0 += 32) {
+    const int e = e0 + lane;
+    bool bad = false;
+    if (e < cnt_nz) {
+      const IdxT c = st.col[pre_c + e];
+      bad = static_cast<unsigned long long>(c) >= static_cast<unsigned long long>(cols);
+      if (bad) {
+        st.col[pre_c + e] = 0;
+        if constexpr (kWithVal) st.val[pre_v + e] = from_float<ValT>(0.f);
+      }
     }
+    const unsigned m = __ballot_sync(0xffffffffu, bad);
+    if (lane == (e0 >> 5)) badmask = m;
   }
   __syncwarp();
   StagedTask<IdxT, ValT> t;
+  t.badmask = badmask;
   t.scol = st.col + pre_c;
   t.sval = st.val + pre_v;
   t.srow = st.crow + pre_r;
@@ -192,8 +212,8 @@ __device__ __forceinline__ uint2 lds64(uint32_t addr) {
 // kFull: n is a whole number of LPR*VEC*CH-column tiles, so no lane is ever masked and the chunk
 // offsets are immediates.  Otherwise masked chunks are pointed at column 0 (a valid address:
 // their loads are harmless duplicates) and only the stores are predicated.
-template <typename DT, typename ValT, typename IdxT, int VEC, int LPR, int CH, bool kFull, int ITEMS, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32, CH == 1 ? OFSPMM_MIN_CTAS : (CH == 2 ? 3 : 2))
+template <typename DT, typename ValT, typename IdxT, int VEC, int LPR, int CH, bool kFull, bool kRowPar, int ITEMS, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, min_ctas_per_sm<DT, CH>())
 spmm_merge_kernel(const FwdParams p) {
   constexpr int G = 32 / LPR;  // groups of lanes working on different non-zeros
   constexpr bool kF32Out = sizeof(DT) == 4;
@@ -267,11 +287,17 @@ spmm_merge_kernel(const FwdParams p) {
     const uint32_t val_s0 = val_sa + static_cast<uint32_t>((tk.pre_v - tk.pre_c) * static_cast<int>(sizeof(ValT)));
     const bool started_earlier = static_cast<int>(tk.srow[0]) < ns;
 
-    int e = 0;
-    for (int r = rs; r <= re; ++r) {
+    // nnz-parallel (kRowPar == false): every group walks every row, chunk q of a row goes to group
+    // q % G and the groups' partial rows are combined with __shfl_xor at the row end.
+    // row-parallel (kRowPar == true, short-row graphs): group g owns rows rs+g, rs+g+G, ... and
+    // keeps G independent rows in flight per warp; no cross-group reduction.
+    constexpr int kChunkStride = kRowPar ? 1 : G;
+    const int chunk_first = kRowPar ? 0 : grp;
+    for (int r = kRowPar ? rs + grp : rs; r <= re; r += (kRowPar ? G : 1)) {
       // rows rs..re-1 end in this task; r == re is the trailing partial row (if it has elements)
-      const int e_end = r < re ? static_cast<int>(tk.srow[r - rs + 1]) - ns : cnt_nz;
-      if (r == re && e_end <= e) break;
+      const int e0 = r == rs ? 0 : static_cast<int>(tk.srow[r - rs]) - ns;
+      const int e1 = r < re ? static_cast<int>(tk.srow[r - rs + 1]) - ns : cnt_nz;
+      if (r == re && e1 <= e0) break;
 
       float acc[CH][VEC];
 #pragma unroll
@@ -279,65 +305,105 @@ spmm_merge_kernel(const FwdParams p) {
 #pragma unroll
         for (int i = 0; i < VEC; ++i) acc[ch][i] = 0.f;
 
-      auto fma_one = [&](int elem) {  // acc += val * B[col, lane columns] for one staged element
-        const IdxT c = tk.scol[elem];
-        const float v = to_float(tk.sval[elem]);
-        const char* brow = Bl + row_offset(c, row_bytes);
-#pragma unroll
-        for (int ch = 0; ch < CH; ++ch)
-          RV::fma(acc[ch], v, load_b<DT, VEC>(brow + (kFull ? ch * kChunkBytes : choff[ch]), pol_b));
-      };
-
       if (vec_ok) {
-        // slots s = pre_c + e; [a, b) is the 16-byte aligned middle, read 4 elements per LDS
-        const int s0 = tk.pre_c + e, s1 = tk.pre_c + e_end;
-        int a = (s0 + 3) & ~3;
-        if (a > s1) a = s1;
-        int b = s1 & ~3;
-        if (b < a) b = a;
-        for (int s = s0 + grp; s < a; s += G) fma_one(s - tk.pre_c);   // ragged head
-        for (int s = b + grp; s < s1; s += G) fma_one(s - tk.pre_c);   // ragged tail
-        // aligned chunks: chunk q goes to lane group q % G
-        uint32_t ca = col_sa + static_cast<uint32_t>(a + 4 * grp) * 4u;
-        const uint32_t cend = col_sa + static_cast<uint32_t>(b) * 4u;
-        if (ca < cend) {
-          uint32_t va = val_s0 + static_cast<uint32_t>(a + 4 * grp) * static_cast<uint32_t>(sizeof(ValT));
-          uint4 cn = lds128(ca);
-          do {
-            const uint32_t c4[4] = {cn.x, cn.y, cn.z, cn.w};
-            typename RV::Raw x[4][CH];
+        // slots s = pre_c + e.  The row's elements are read as 16-byte chunks of 4 slots; the
+        // first / last chunk may contain slots of neighbouring rows (or staging padding), which
+        // are masked: no load is issued and the value is forced to 0.
+        const int s0 = tk.pre_c + e0, s1 = tk.pre_c + e1;
+        const int cbase = s0 & ~3;
+        const int nchunks = s1 > s0 ? ((s1 + 3) >> 2) - (s0 >> 2) : 0;
+        auto load_vals = [&](int sa, float (&v4)[4]) {
+          const uint32_t va = val_s0 + static_cast<uint32_t>(sa) * static_cast<uint32_t>(sizeof(ValT));
+          if constexpr (sizeof(ValT) == 4) {
+            const uint4 w = lds128(va);
+            v4[0] = __uint_as_float(w.x); v4[1] = __uint_as_float(w.y);
+            v4[2] = __uint_as_float(w.z); v4[3] = __uint_as_float(w.w);
+          } else {
+            const uint2 w = lds64(va);
+            v4[0] = __uint_as_float(w.x << 16); v4[1] = __uint_as_float(w.x & 0xffff0000u);
+            v4[2] = __uint_as_float(w.y << 16); v4[3] = __uint_as_float(w.y & 0xffff0000u);
+          }
+        };
+        // edge chunk (first / last of the row): per-slot predicated gathers, masked values
+        auto edge_chunk = [&](int q) {
+          const int sa = cbase + 4 * q;
+          const uint4 cn = lds128(col_sa + static_cast<uint32_t>(sa) * 4u);
+          const uint32_t c4[4] = {cn.x, cn.y, cn.z, cn.w};
+          typename RV::Raw x[4][CH];
+          bool ok[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const char* brow = Bl + static_cast<unsigned long long>(c4[u]) * row_bytes;
+          for (int u = 0; u < 4; ++u) {
+            ok[u] = sa + u >= s0 && sa + u < s1;
+            const char* brow = Bl + static_cast<unsigned long long>(c4[u]) * row_bytes;
 #pragma unroll
-              for (int ch = 0; ch < CH; ++ch)
-                x[u][ch] = load_b<DT, VEC>(brow + (kFull ? ch * kChunkBytes : choff[ch]), pol_b);
+            for (int ch = 0; ch < CH; ++ch) {
+              x[u][ch] = typename RV::Raw{};
+              if (ok[u]) x[u][ch] = load_b<DT, VEC>(brow + (kFull ? ch * kChunkBytes : choff[ch]), pol_b);
             }
-            ca += 16u * G;
-            if (ca < cend) cn = lds128(ca);  // next chunk's indices, while the gathers fly
-            float v4[4];
-            if constexpr (sizeof(ValT) == 4) {
-              const uint4 w = lds128(va);
-              v4[0] = __uint_as_float(w.x); v4[1] = __uint_as_float(w.y);
-              v4[2] = __uint_as_float(w.z); v4[3] = __uint_as_float(w.w);
-            } else {
-              const uint2 w = lds64(va);
-              v4[0] = __uint_as_float(w.x << 16); v4[1] = __uint_as_float(w.x & 0xffff0000u);
-              v4[2] = __uint_as_float(w.y << 16); v4[3] = __uint_as_float(w.y & 0xffff0000u);
-            }
-            va += 4u * G * static_cast<uint32_t>(sizeof(ValT));
+          }
+          float v4[4];
+          load_vals(sa, v4);
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
+          for (int u = 0; u < 4; ++u) {
+            const float v = ok[u] ? v4[u] : 0.f;
 #pragma unroll
-              for (int ch = 0; ch < CH; ++ch) RV::fma(acc[ch], v4[u], x[u][ch]);
-          } while (ca < cend);
+            for (int ch = 0; ch < CH; ++ch) RV::fma(acc[ch], v, x[u][ch]);
+          }
+        };
+        if (nchunks > 0) {
+          if (chunk_first == 0) edge_chunk(0);
+          // interior chunks 1 .. nchunks-2 are full: unpredicated, next indices prefetched.
+          // Only the index-chunk address `ca` is carried through the loop (the value address is
+          // derived from it) to keep the register budget for the four gathers in flight.
+          const int q0 = chunk_first == 0 ? kChunkStride : chunk_first;
+          uint32_t ca = col_sa + static_cast<uint32_t>(cbase + 4 * q0) * 4u;
+          const uint32_t cend = col_sa + static_cast<uint32_t>(cbase + 4 * (nchunks - 1)) * 4u;
+          if (ca < cend) {
+            uint4 cn = lds128(ca);
+            do {
+              const uint32_t c4[4] = {cn.x, cn.y, cn.z, cn.w};
+              typename RV::Raw x[4][CH];
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const char* brow = Bl + static_cast<unsigned long long>(c4[u]) * row_bytes;
+#pragma unroll
+                for (int ch = 0; ch < CH; ++ch)
+                  x[u][ch] = load_b<DT, VEC>(brow + (kFull ? ch * kChunkBytes : choff[ch]), pol_b);
+              }
+              // value chunk that pairs with index chunk `ca`
+              const uint32_t va = sizeof(ValT) == 4 ? ca + (val_s0 - col_sa) : val_s0 + ((ca - col_sa) >> 1);
+              ca += 16u * kChunkStride;
+              if (ca < cend) cn = lds128(ca);  // next chunk's indices, while the gathers fly
+              float v4[4];
+              if constexpr (sizeof(ValT) == 4) {
+                const uint4 w = lds128(va);
+                v4[0] = __uint_as_float(w.x); v4[1] = __uint_as_float(w.y);
+                v4[2] = __uint_as_float(w.z); v4[3] = __uint_as_float(w.w);
+              } else {
+                const uint2 w = lds64(va);
+                v4[0] = __uint_as_float(w.x << 16); v4[1] = __uint_as_float(w.x & 0xffff0000u);
+                v4[2] = __uint_as_float(w.y << 16); v4[3] = __uint_as_float(w.y & 0xffff0000u);
+              }
+#pragma unroll
+              for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int ch = 0; ch < CH; ++ch) RV::fma(acc[ch], v4[u], x[u][ch]);
+            } while (ca < cend);
+          }
+          if (nchunks > 1 && ca == cend) edge_chunk(nchunks - 1);  // this group owns the last chunk
         }
       } else {
-        for (int el = e + grp; el < e_end; el += G) fma_one(el);
+        for (int el = e0 + chunk_first; el < e1; el += kChunkStride) {
+          const IdxT c = tk.scol[el];
+          const float v = to_float(tk.sval[el]);
+          const char* brow = Bl + row_offset(c, row_bytes);
+#pragma unroll
+          for (int ch = 0; ch < CH; ++ch)
+            RV::fma(acc[ch], v, load_b<DT, VEC>(brow + (kFull ? ch * kChunkBytes : choff[ch]), pol_b));
+        }
       }
-      e = e_end;
 
-      if constexpr (G > 1) {  // combine the G groups' partial rows (fixed xor tree)
+      if constexpr (G > 1 && !kRowPar) {  // combine the G groups' partial rows (fixed xor tree)
 #pragma unroll
         for (int off = LPR; off < 32; off <<= 1)
 #pragma unroll
@@ -346,7 +412,7 @@ spmm_merge_kernel(const FwdParams p) {
             for (int i = 0; i < VEC; ++i) acc[ch][i] += __shfl_xor_sync(0xffffffffu, acc[ch][i], off);
       }
 
-      if (grp == 0) {
+      if (kRowPar || grp == 0) {
         if (r == re || (!kF32Out && r == rs && started_earlier)) {
           // fp32 scratch: carry[k] for the trailing partial row, head[k] for a bf16 row that
           // started in an earlier task
@@ -366,42 +432,68 @@ spmm_merge_kernel(const FwdParams p) {
 }
 
 // Adds the carries of every row that spans several tasks, in ascending task order, on top of the
-// row's final segment.  One warp per task k that *ends* a row which started earlier.
+// row's final segment (a deterministic segmented reduction).  Each LANE inspects one task k: if k
+// ends a row that started in an earlier task, the lane finds the first task j of that row; the
+// warp then stitches the flagged rows one after another, all 32 lanes across the dense width.
 template <typename DT, typename IdxT, int VEC, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) spmm_fixup_kernel(const FwdParams p) {
   constexpr bool kF32Out = sizeof(DT) == 4;
-  const int k = blockIdx.x * WARPS + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
-  if (k <= 0 || k >= p.P) return;
-  const int2 ps = __ldg(&p.part[k]);
-  const int rs = ps.x, ns = ps.y;
-  const int re = __ldg(&p.part[k + 1]).x;
-  if (re <= rs) return;  // no row ends here
-  const int cr = static_cast<int>(static_cast<const IdxT*>(p.crow)[rs]);
-  if (cr >= ns) return;  // the row started in this task: already complete
-  int j = k - 1;         // tasks j..k-1 each hold >= 1 non-zero of row rs
-  while (j > 0 && __ldg(&p.part[j]).y > cr) --j;
+  const int k = (blockIdx.x * WARPS + (threadIdx.x >> 5)) * 32 + lane;
+  bool need = false;
+  int j = 0, rs = 0;
+  if (k >= 1 && k < p.P) {
+    const int2 ps = __ldg(&p.part[k]);
+    const int re = __ldg(&p.part[k + 1]).x;
+    if (re > ps.x) {  // a row ends in task k
+      const int cr = static_cast<int>(static_cast<const IdxT*>(p.crow)[ps.x]);
+      if (cr < ps.y) {  // ... and it started before task k
+        need = true;
+        rs = ps.x;
+        // first task holding a non-zero of the row = smallest j with part[j+1].y > cr
+        j = k - 1;
+        int steps = 0;
+        while (j > 0 && steps < 4 && __ldg(&p.part[j]).y > cr) { --j; ++steps; }
+        if (j > 0 && __ldg(&p.part[j]).y > cr) {  // hub row: finish with a binary search
+          int lo = 0, hi = j;                    // invariant: part[hi].y > cr, answer in [lo, hi)
+          while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (__ldg(&p.part[mid + 1]).y > cr) hi = mid; else lo = mid + 1;
+          }
+          j = lo;
+        }
+      }
+    }
+  }
+  unsigned todo = __ballot_sync(0xffffffffu, need);
   const int n = p.n;
-  DT* crow_out = static_cast<DT*>(p.C) + static_cast<size_t>(rs) * p.ldc;
-  for (int c0 = lane * VEC; c0 < n; c0 += 32 * VEC) {
-    float sum[VEC];
+  while (todo != 0) {
+    const int src = __ffs(todo) - 1;
+    todo &= todo - 1;
+    const int kk = __shfl_sync(0xffffffffu, k, src);
+    const int jj = __shfl_sync(0xffffffffu, j, src);
+    const int row = __shfl_sync(0xffffffffu, rs, src);
+    DT* crow_out = static_cast<DT*>(p.C) + static_cast<size_t>(row) * p.ldc;
+    for (int c0 = lane * VEC; c0 < n; c0 += 32 * VEC) {
+      float sum[VEC];
 #pragma unroll
-    for (int i = 0; i < VEC; ++i) sum[i] = 0.f;
-    for (int t = j; t < k; ++t) {
-      float x[VEC];
-      load_f32<VEC>(p.carry + static_cast<size_t>(t) * n + c0, x);
+      for (int i = 0; i < VEC; ++i) sum[i] = 0.f;
+      for (int t = jj; t < kk; ++t) {
+        float x[VEC];
+        load_f32<VEC>(p.carry + static_cast<size_t>(t) * n + c0, x);
 #pragma unroll
-      for (int i = 0; i < VEC; ++i) sum[i] += x[i];
+        for (int i = 0; i < VEC; ++i) sum[i] += x[i];
+      }
+      float h[VEC];
+      if constexpr (kF32Out) {
+        load_f32<VEC>(reinterpret_cast<const float*>(crow_out) + c0, h);
+      } else {
+        load_f32<VEC>(p.head + static_cast<size_t>(kk) * n + c0, h);
+      }
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) sum[i] += h[i];
+      RowVec<DT, VEC>::store_stream(crow_out + c0, sum);
     }
-    float h[VEC];
-    if constexpr (kF32Out) {
-      load_f32<VEC>(reinterpret_cast<const float*>(crow_out) + c0, h);
-    } else {
-      load_f32<VEC>(p.head + static_cast<size_t>(k) * n + c0, h);
-    }
-#pragma unroll
-    for (int i = 0; i < VEC; ++i) sum[i] += h[i];
-    RowVec<DT, VEC>::store_stream(crow_out + c0, sum);
   }
 }
 
