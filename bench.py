@@ -192,6 +192,26 @@ def run_reference(args):
     }))
 
 
+def _teardown(world):
+    """Leave the process group without ever hanging the launcher: a watchdog force-exits if NCCL
+    teardown does not return (seen after CUDA-graph capture of collectives)."""
+    if world <= 1:
+        return
+    import torch.distributed as dist
+
+    def _bail():
+        sys.stdout.flush()
+        os._exit(0)
+    t = threading.Timer(20.0, _bail)
+    t.daemon = True
+    t.start()
+    try:
+        dist.destroy_process_group()
+    except Exception:
+        pass
+    t.cancel()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -202,7 +222,11 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--bwd", default="transpose", choices=["transpose", "atomic"])
-    ap.add_argument("--no-graph", action="store_true", help="N>1: run the sharded step eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--graph", action="store_true",
+                    help="N>1: replay the sharded step from a CUDA graph (experimental: measured no faster than eager "
+                         "on 8 B200s, and NCCL teardown after capture can hang — off by default)")
+    ap.add_argument("--comm", default="nccl", choices=["nccl", "peer"],
+                    help="N>1: NCCL all-gather / reduce-scatter kernels, or copy-engine pulls over symmetric (peer) memory")
     ap.add_argument("--panels", type=int, default=2, help="N>1: column panels used to pipeline the collectives")
     args = ap.parse_args()
     args.warmup = max(3, args.warmup)
@@ -237,19 +261,19 @@ def main():
 
     if world > 1:
         dmod = __import__("importlib").import_module("of-spmm_b200.dist")
-        runner = dmod.ShardedSpmm(A, n, dtype, rank, world, dev, bwd=args.bwd, panels=args.panels)
+        runner = dmod.ShardedSpmm(A, n, dtype, rank, world, dev, bwd=args.bwd, panels=args.panels, comm=args.comm)
         B_in, dY_in = runner.shard_rows(B), runner.shard_rows_out(dY)
         step_eager = lambda: runner.step(B_in, dY_in)
         l0 = ofs.launch_count()
         step_eager()
         graph_launches_per_step = ofs.launch_count() - l0
-        if args.no_graph:
+        if not args.graph:
             step, fwd_only = step_eager, (lambda: runner.forward(B_in))
         else:  # one CUDA graph per step: kernels + copies + NCCL collectives, no host launch gaps
             step = runner.capture(step_eager)
             fwd_only = runner.capture(lambda: runner.forward(B_in))
-        parallelism = (f"row-block x{world} (nnz-balanced), {runner.panels} column panels, all-gather / "
-                       f"reduce-scatter pipelined with compute, " + ("eager" if args.no_graph else "CUDA-graph replay"))
+        parallelism = (f"row-block x{world} (nnz-balanced), {runner.panels} column panels, comm={runner.comm}, all-gather / "
+                       f"reduce-scatter pipelined with compute, " + ("CUDA-graph replay" if args.graph else "eager launches"))
     else:
         t0 = time.perf_counter()
         tr = ops.csr_transpose(A.crow, A.col, A.val, A.rows, A.cols) if args.bwd == "transpose" else None
@@ -290,7 +314,7 @@ def main():
     barrier()
     total_ms = ev[0].elapsed_time(ev[1])
     launches = ofs.launch_count() - launches0
-    if world > 1 and not args.no_graph and launches == 0:
+    if world > 1 and args.graph and launches == 0:
         launches = graph_launches_per_step * args.steps   # replayed from the captured graph
     # dominant kernel (forward): its own CUDA-event loop right after, same residency / clocks
     for i in range(args.steps):
@@ -352,9 +376,7 @@ def main():
                        "transpose for fresh inputs), device -> pinned host"}
 
     if rank != 0:
-        if world > 1:
-            import torch.distributed as dist
-            dist.destroy_process_group()
+        _teardown(world)
         return
 
     peak, peak_src = _peaks()
@@ -394,10 +416,8 @@ def main():
         out["e2e"] = e2e
     if not args.no_cpu_baseline and world == 1:
         out["cpu_baseline"] = _cpu_baseline(A, B, dY, n)
-    print(json.dumps(out))
-    if world > 1:
-        import torch.distributed as dist
-        dist.destroy_process_group()
+    print(json.dumps(out), flush=True)
+    _teardown(world)
 
 
 if __name__ == "__main__":

@@ -1,4 +1,6 @@
 // fwd.cu — variant selection and launch of the merge-path SpMM kernels (spmm_kernels.cuh).
+#include <stdlib.h>
+
 #include "internal.h"
 #include "spmm_kernels.cuh"
 
@@ -23,7 +25,18 @@ int launch_full(FwdParams p, int panels, cudaStream_t stream) {
   const int64_t ctas_needed = (static_cast<int64_t>(p.P) + WARPS - 1) / WARPS;
   const int64_t ctas_all = (static_cast<int64_t>(p.P) * panels + WARPS - 1) / WARPS;
   const int64_t resident = static_cast<int64_t>(dev.sms) * occ;
-  const int gx = static_cast<int>(ctas_all < resident ? ctas_all : resident);
+  int64_t gx64 = ctas_all < resident ? ctas_all : resident;
+  // OFSPMM_TASKS_PER_WARP=k (env, tuning): non-persistent grid whose CTAs retire after ~k tasks
+  // per warp, so kernels of a higher-priority stream (NCCL collectives of the next column panel)
+  // can get SMs while this kernel is still running.  Default: persistent.
+  if (const char* env = getenv("OFSPMM_TASKS_PER_WARP")) {
+    const long k = strtol(env, nullptr, 10);
+    if (k > 0) {
+      const int64_t want = (ctas_all + k - 1) / k;
+      if (want > gx64) gx64 = want;
+    }
+  }
+  const int gx = static_cast<int>(gx64);
   kern<<<gx, WARPS * 32, smem, stream>>>(p);
   count_launch();
   OFSPMM_CUDA_OK(cudaGetLastError());

@@ -44,13 +44,73 @@ def shard_rows_count(k: int, world: int) -> int:
     return (k + world - 1) // world
 
 
+class _PeerExchange:
+    """Collectives over NVSwitch peer memory without SMs: every rank exposes its send buffers
+    through CUDA symmetric memory (``torch.distributed._symmetric_memory``), synchronises with a
+    stream-ordered device barrier and *pulls* the peers' blocks with plain device-to-device copies
+    on a side stream — those run on the copy engines, so the persistent SpMM kernel keeps all 148
+    SMs while the next panel is in flight.  (NCCL's all-gather kernel needs SMs of its own; when
+    the persistent compute grid already owns them the two serialise instead of overlapping.)"""
+
+    def __init__(self, shard: int, kp: int, w: int, panels: int, dtype, device, rank: int, world: int, group):
+        import torch.distributed._symmetric_memory as symm
+        self.rank, self.world, self.shard, self.w, self.panels = rank, world, shard, w, panels
+        gname = (group or dist.group.WORLD).group_name
+        # outgoing B panels (forward) and partial dB panels (backward), visible to every peer
+        self.send = symm.empty((panels, shard, w), dtype=dtype, device=device)
+        self.part = symm.empty((panels, kp, w), dtype=dtype, device=device)
+        self.h_send = symm.rendezvous(self.send, gname)
+        self.h_part = symm.rendezvous(self.part, gname)
+        self.peer_send = [self.h_send.get_buffer(r, (panels, shard, w), dtype) for r in range(world)]
+        self.peer_part = [self.h_part.get_buffer(r, (panels, kp, w), dtype) for r in range(world)]
+        self.copy_stream = torch.cuda.Stream(device=device)
+        self.stage = torch.empty((world, shard, w), dtype=dtype, device=device)
+
+    def begin_forward(self):
+        # every peer has finished pulling the previous step's panels before they are overwritten
+        self.h_send.barrier(channel=0)
+
+    def all_gather_panel(self, j: int, out_full: torch.Tensor) -> torch.cuda.Event:
+        """send[j] was filled on the current stream; returns the event after which out_full
+        (kp x w) holds every rank's panel j."""
+        self.h_send.barrier(channel=1 + j)          # all ranks have filled their panel j
+        cur = torch.cuda.current_stream()
+        self.copy_stream.wait_stream(cur)
+        with torch.cuda.stream(self.copy_stream):
+            for step in range(self.world):
+                r = (self.rank + step) % self.world   # own block first, then a ring of peers
+                out_full[r * self.shard:(r + 1) * self.shard].copy_(self.peer_send[r][j], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self.copy_stream)
+        return ev
+
+    def begin_backward(self):
+        self.h_part.barrier(channel=0)
+
+    def reduce_scatter_panel(self, j: int, out_shard: torch.Tensor) -> torch.cuda.Event:
+        """part[j] (this rank's partial kp x w) was written on the current stream; out_shard
+        (shard x w) = sum over ranks of their partial rows of this rank's shard, fixed order."""
+        self.h_part.barrier(channel=1 + j)          # every rank's partial panel j is complete
+        cur = torch.cuda.current_stream()
+        self.copy_stream.wait_stream(cur)
+        lo, hi = self.rank * self.shard, (self.rank + 1) * self.shard
+        with torch.cuda.stream(self.copy_stream):
+            for step in range(self.world):
+                r = (self.rank + step) % self.world
+                self.stage[r].copy_(self.peer_part[r][j, lo:hi], non_blocking=True)
+            torch.sum(self.stage, dim=0, out=out_shard)   # rank order 0..world-1: deterministic
+            ev = torch.cuda.Event()
+            ev.record(self.copy_stream)
+        return ev
+
+
 class ShardedSpmm:
     """Row-block-partitioned SpMM operator bound to one rank."""
 
     def __init__(self, A: CsrMatrix, n: int, dtype: torch.dtype, rank: int, world: int, device,
                  bwd: str = "transpose", panels: int = 2,
                  spmm_fn: Callable = _default_spmm, transpose_fn: Callable = _default_transpose,
-                 group=None):
+                 group=None, comm: str = "nccl"):
         assert A.rows >= world, "fewer rows than ranks"
         self.rank, self.world, self.device, self.group = rank, world, device, group
         self.n, self.dtype = n, dtype
@@ -82,6 +142,15 @@ class ShardedSpmm:
         self._db_out = [torch.empty((self.shard, self.w), dtype=dtype, device=device) for _ in range(panels)]
         self._db = torch.empty((self.shard, n), dtype=dtype, device=device)
         self._nccl = dist.is_initialized() and dist.get_backend(group) == "nccl"
+        # comm = "peer": copy-engine pulls over symmetric memory instead of NCCL kernels
+        self.comm, self._peer = "nccl" if self._nccl else "gloo", None
+        if comm == "peer" and self._nccl:
+            try:
+                self._peer = _PeerExchange(self.shard, self.kp, self.w, panels, dtype, device, rank, world, group)
+                self.comm = "peer"
+            except Exception as e:  # pragma: no cover - needs NVLink peers
+                import warnings
+                warnings.warn(f"symmetric-memory peer exchange unavailable ({e}); using NCCL collectives")
 
     # ------------------------------------------------------------------ sharding helpers
     def shard_rows(self, B_full: torch.Tensor) -> torch.Tensor:
@@ -116,6 +185,18 @@ class ShardedSpmm:
     def forward(self, B_shard: torch.Tensor) -> torch.Tensor:
         """C_blk[m, n] = A_blk · allgather(B_shard), panel-pipelined."""
         A, w = self.A_blk, self.w
+        if self._peer is not None:
+            px = self._peer
+            px.begin_forward()
+            events = []
+            for j in range(self.panels):
+                px.send[j].copy_(B_shard[:, j * w:(j + 1) * w])
+                events.append(px.all_gather_panel(j, self._b_full[j]))
+            for j in range(self.panels):
+                torch.cuda.current_stream().wait_event(events[j])
+                self.spmm_fn(A.crow, A.col, A.val, self._b_full[j][: self.cols], A.rows, A.cols,
+                             self._c[:, j * w:(j + 1) * w])
+            return self._c
         works = []
         for j in range(self.panels):
             self._b_send[j].copy_(B_shard[:, j * w:(j + 1) * w])
@@ -130,6 +211,20 @@ class ShardedSpmm:
     def backward(self, dY_blk: torch.Tensor) -> torch.Tensor:
         """dB_shard[shard, n] = reduce_scatter(A_blkᵀ · dY_blk), panel-pipelined."""
         w = self.w
+        if self._peer is not None and self.At_blk is not None:
+            px, At = self._peer, self.At_blk
+            px.begin_backward()
+            events = []
+            for j in range(self.panels):
+                part = px.part[j]
+                if self.kp > self.cols:
+                    part[self.cols:].zero_()
+                self.spmm_fn(At.crow, At.col, At.val, dY_blk[:, j * w:(j + 1) * w], At.rows, At.cols, part[: self.cols])
+                events.append(px.reduce_scatter_panel(j, self._db_out[j]))
+            for j in range(self.panels):
+                torch.cuda.current_stream().wait_event(events[j])
+                self._db[:, j * w:(j + 1) * w].copy_(self._db_out[j])
+            return self._db
         works: List[Optional[object]] = []
         for j in range(self.panels):
             part = self._db_part[j]
