@@ -245,8 +245,46 @@ class ShardedSpmm:
             self._db[:, j * w:(j + 1) * w].copy_(self._db_out[j])
         return self._db
 
-    def step(self, B_shard: torch.Tensor, dY_blk: torch.Tensor):
-        return self.forward(B_shard), self.backward(dY_blk)
+    def step(self, B_shard: torch.Tensor, dY_blk: torch.Tensor, overlap: bool = True):
+        """One benchmark step: C_blk = A_blk·allgather(B) and dB_shard = reduce_scatter(A_blkᵀ·dY).
+        The two halves are independent, so with ``overlap`` the collectives of one hide behind the
+        compute of the other:  all-gather(B) ‖ A_blkᵀ·dY,  then  reduce-scatter(dB) ‖ A_blk·B.
+        (Measured on 8 B200s, cfg2: splitting the dense width into column panels to overlap inside
+        one product costs more in narrower gathers than the overlap returns; whole-width products
+        with cross-product overlap are faster — profiles/r1_multigpu.md.)"""
+        if not overlap or self.At_blk is None or self.panels != 1:
+            return self.forward(B_shard), self.backward(dY_blk)
+        A, At, n = self.A_blk, self.At_blk, self.n
+        if self._peer is not None:
+            px = self._peer
+            cur = torch.cuda.current_stream()
+            px.begin_forward()
+            px.send[0].copy_(B_shard)
+            ev_ag = px.all_gather_panel(0, self._b_full[0])           # copy engines, side stream
+            px.begin_backward()
+            part = px.part[0]
+            if self.kp > self.cols:
+                part[self.cols:].zero_()
+            self.spmm_fn(At.crow, At.col, At.val, dY_blk, At.rows, At.cols, part[: self.cols])
+            ev_rs = px.reduce_scatter_panel(0, self._db_out[0])      # pulls + ordered sum, side stream
+            cur.wait_event(ev_ag)
+            self.spmm_fn(A.crow, A.col, A.val, self._b_full[0][: self.cols], A.rows, A.cols, self._c)
+            cur.wait_event(ev_rs)
+            self._db.copy_(self._db_out[0])
+            return self._c, self._db
+        self._b_send[0].copy_(B_shard)
+        w_ag = self._all_gather(self._b_full[0], self._b_send[0])     # NCCL stream
+        part = self._db_part[0]
+        if self.kp > self.cols:
+            part[self.cols:].zero_()
+        self.spmm_fn(At.crow, At.col, At.val, dY_blk, At.rows, At.cols, part[: self.cols])
+        w_rs = self._reduce_scatter(self._db_out[0], part)
+        w_ag.wait()
+        self.spmm_fn(A.crow, A.col, A.val, self._b_full[0][: self.cols], A.rows, A.cols, self._c)
+        if w_rs is not None:
+            w_rs.wait()
+        self._db.copy_(self._db_out[0])
+        return self._c, self._db
 
     def capture(self, fn: Callable[[], object], warmup: int = 3):
         """Capture ``fn`` (a closure over static input tensors, e.g. ``lambda: self.step(B, dY)``)

@@ -56,8 +56,11 @@ def _worker(rank, world, port, n, panels, q):
         C_blk, dB_shard = sh.step(sh.shard_rows(B), sh.shard_rows_out(dY))
         q.put((rank, sh.bounds, sh.r0, sh.r1, sh.shard, C_blk.clone().numpy(), dB_shard.clone().numpy()))
         dist.barrier()
-    finally:
         dist.destroy_process_group()
+    except Exception:   # report instead of leaving the parent (and the peer rank) waiting
+        import traceback
+        q.put(("error", rank, traceback.format_exc()))
+        os._exit(1)
 
 
 @pytest.mark.parametrize("world,n,panels", [(2, 16, 2), (2, 12, 1), (3, 32, 4)])
@@ -71,7 +74,14 @@ def test_sharded_spmm_gloo(world, n, panels):
     procs = [ctx.Process(target=_worker, args=(r, world, port, n, panels, q)) for r in range(world)]
     for p in procs:
         p.start()
-    results = [q.get(timeout=180) for _ in range(world)]
+    results = []
+    for _ in range(world):
+        r = q.get(timeout=120)
+        if r[0] == "error":
+            for p in procs:
+                p.kill()
+            raise AssertionError(f"rank {r[1]} failed:\n{r[2]}")
+        results.append(r)
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
