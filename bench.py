@@ -185,7 +185,8 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "rows": A.rows, "nnz": nnz, "n": n,
+        "config": {"workload": args.workload, "rows": A.rows, "cols": A.cols, "nnz": nnz, "n": n,
+                   "step": "forward C=A*B + backward dB=A^T*dY", "parallelism": f"{base['cores']} host threads",
                    "note": "ms_per_step extrapolated from the sampled rate to the full workload"},
         "cpu_baseline": base,
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -227,7 +228,9 @@ def main():
                          "on 8 B200s, and NCCL teardown after capture can hang — off by default)")
     ap.add_argument("--comm", default="nccl", choices=["nccl", "peer"],
                     help="N>1: NCCL all-gather / reduce-scatter kernels, or copy-engine pulls over symmetric (peer) memory")
-    ap.add_argument("--panels", type=int, default=2, help="N>1: column panels used to pipeline the collectives")
+    ap.add_argument("--panels", type=int, default=1,
+                    help="N>1: column panels used to pipeline a collective with its own product (1 = whole width; the "
+                         "collectives then overlap with the other product of the step)")
     args = ap.parse_args()
     args.warmup = max(3, args.warmup)
     if args.impl == "reference":
@@ -272,8 +275,9 @@ def main():
         else:  # one CUDA graph per step: kernels + copies + NCCL collectives, no host launch gaps
             step = runner.capture(step_eager)
             fwd_only = runner.capture(lambda: runner.forward(B_in))
-        parallelism = (f"row-block x{world} (nnz-balanced), {runner.panels} column panels, comm={runner.comm}, all-gather / "
-                       f"reduce-scatter pipelined with compute, " + ("CUDA-graph replay" if args.graph else "eager launches"))
+        parallelism = (f"row-block x{world} (nnz-balanced whole rows), B/dB row-sharded, comm={runner.comm}, "
+                       f"{runner.panels} column panel(s), all-gather(B) overlapped with A^T*dY and reduce-scatter(dB) "
+                       f"overlapped with A*B, " + ("CUDA-graph replay" if args.graph else "eager launches"))
     else:
         t0 = time.perf_counter()
         tr = ops.csr_transpose(A.crow, A.col, A.val, A.rows, A.cols) if args.bwd == "transpose" else None

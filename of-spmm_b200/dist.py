@@ -10,13 +10,19 @@ Partitioning
   * B (K×n) is row-sharded in equal blocks of ceil(K/world) rows (zero-padded), which is what an
     all-gather needs.
 
-Forward  C_blk = A_blk · B:   the dense operand is processed as ``panels`` column panels; the
-  all-gather of panel j+1 (NCCL, its own stream) is in flight while the SpMM of panel j runs
-  (``ofspmm_fwd_strided`` writes panel j straight into C_blk's columns).  The reference instead
-  finishes a blocking, unfused all-gather before the op is even issued
-  (oneflow/core/framework/op_interpreter/eager_global_op_interpreter.cpp:156-181).
-Backward dB = Aᵀ · dY:   each rank's row block yields a partial K×n; panel j is reduce-scattered
-  over NVLink while panel j+1 is being computed (the dual collective).
+Collectives and overlap (measured on 8 B200s, profiles/r1_multigpu.md)
+  * ``forward``: all-gather of the B shards, then ``C_blk = A_blk · B``.  ``backward``: partial
+    ``A_blkᵀ·dY_blk`` (K×n), then reduce-scatter — the dual collective.
+  * ``step`` (both products of a training step) hides the collectives of one product behind the
+    compute of the other: all-gather(B) ‖ A_blkᵀ·dY, then reduce-scatter(dB) ‖ A_blk·B.  The
+    reference instead finishes a blocking, unfused all-gather before the op is even issued
+    (oneflow/core/framework/op_interpreter/eager_global_op_interpreter.cpp:156-181).
+  * ``panels`` > 1 additionally pipelines a collective with its *own* product over column panels of
+    the dense operand (``ofspmm_fwd_strided`` writes panel j straight into C_blk's columns).
+    Measured slower than whole-width products on cfg2, so the default is 1.
+  * NCCL kernels need SMs; a persistent compute grid owns all of them, so by default the compute
+    kernels run as short-lived CTAs while collectives are in flight (``tasks_per_warp``), or the
+    exchange uses copy engines over symmetric peer memory (``comm="peer"``).
 
 The compute callbacks default to the CUDA ops; tests inject CPU stand-ins to exercise the
 partition / shard / pipeline logic under gloo with world_size 2.
@@ -108,10 +114,17 @@ class ShardedSpmm:
     """Row-block-partitioned SpMM operator bound to one rank."""
 
     def __init__(self, A: CsrMatrix, n: int, dtype: torch.dtype, rank: int, world: int, device,
-                 bwd: str = "transpose", panels: int = 2,
+                 bwd: str = "transpose", panels: int = 1,
                  spmm_fn: Callable = _default_spmm, transpose_fn: Callable = _default_transpose,
-                 group=None, comm: str = "nccl"):
+                 group=None, comm: str = "nccl", tasks_per_warp: int = 2):
         assert A.rows >= world, "fewer rows than ranks"
+        # Launch policy of the compute kernels while collectives are in flight: CTAs that retire
+        # after ~tasks_per_warp tasks per warp instead of one persistent wave, so the NCCL kernels
+        # (higher-priority stream) get SMs as soon as they are ready.  8 B200s, cfg2: 1.19 ms →
+        # 0.98 ms per step (profiles/r1_multigpu.md).  The library reads the knob at every launch.
+        if world > 1 and tasks_per_warp > 0 and comm == "nccl":
+            import os
+            os.environ.setdefault("OFSPMM_TASKS_PER_WARP", str(tasks_per_warp))
         self.rank, self.world, self.device, self.group = rank, world, device, group
         self.n, self.dtype = n, dtype
         self.rows, self.cols = A.rows, A.cols
