@@ -1,0 +1,324 @@
+// glue_harness.cpp — compiles the OneFlow glue sources (of-spmm_b200/oneflow_glue/spmm_op.cpp,
+// spmm_kernels.cpp) against tests/mock_oneflow and drives them the way the reference's framework
+// would: op inference through InferContext / SbpContext, kernel lookup through the
+// REGISTER_USER_KERNEL predicates, InferTmpSize, then OpKernel::Compute(KernelComputeContext*)
+// on a CUDA stream.  TEST INFRASTRUCTURE (reads like a reference test: build inputs, run the op,
+// compare with a plain loop).
+//
+//   glue_harness host   — everything that needs no GPU (inference, errors, SBP, registry)
+//   glue_harness gpu    — additionally runs spmm_csr / spmm_csr_grad_b / sddmm_csr kernels
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <random>
+
+#include "oneflow/core/ep/cuda/cuda_stream.h"
+#include "oneflow/core/framework/framework.h"
+#include "oneflow/core/framework/op_generated.h"
+#include "ofspmm.h"
+
+namespace oneflow {
+namespace mock {
+void Fatal(const std::string& msg) {
+  std::fprintf(stderr, "FATAL: %s\n", msg.c_str());
+  std::exit(70);
+}
+}  // namespace mock
+namespace user_op {
+std::vector<KernelRegistration>& KernelRegistry() {
+  static std::vector<KernelRegistration> r;
+  return r;
+}
+}  // namespace user_op
+}  // namespace oneflow
+
+using namespace oneflow;
+
+#define EXPECT(cond)                                                        \
+  do {                                                                      \
+    if (!(cond)) {                                                          \
+      std::fprintf(stderr, "%s:%d: EXPECT failed: %s\n", __FILE__, __LINE__, #cond); \
+      std::exit(1);                                                         \
+    }                                                                       \
+  } while (0)
+
+namespace {
+
+struct TensorDescs {
+  std::map<std::string, Shape> shapes;
+  std::map<std::string, DataType> dtypes;
+  std::map<std::string, int64_t> attrs;
+};
+
+class MockInferContext final : public user_op::InferContext {
+ public:
+  explicit MockInferContext(TensorDescs* d) : d_(d) {}
+  const Shape& InputShape(const std::string& n, int32_t) const override { return d_->shapes.at(n); }
+  void SetOutputShape(const std::string& n, int32_t, const Shape& s) override { d_->shapes[n] = s; }
+  DataType InputDType(const std::string& n, int32_t) const override { return d_->dtypes.at(n); }
+  void SetOutputDType(const std::string& n, int32_t, DataType t) override { d_->dtypes[n] = t; }
+ protected:
+  const int64_t& AttrInt64(const std::string& n) const override { return d_->attrs.at(n); }
+ private:
+  TensorDescs* d_;
+};
+
+class MockSbpContext final : public user_op::SbpContext {
+ public:
+  MockSbpContext(user_op::SbpSignatureBuilder::Args in, user_op::SbpSignatureBuilder::Args out)
+      : in_(std::move(in)), out_(std::move(out)) {}
+  const user_op::SbpSignatureBuilder::Args& inputs() const override { return in_; }
+  const user_op::SbpSignatureBuilder::Args& outputs() const override { return out_; }
+ private:
+  user_op::SbpSignatureBuilder::Args in_, out_;
+};
+
+TensorDescs SpmmDescs(int64_t rows, int64_t cols, int64_t nnz, int64_t n, DataType dense, DataType idx) {
+  TensorDescs d;
+  d.shapes["a_crow"] = Shape({rows + 1});
+  d.shapes["a_col"] = Shape({nnz});
+  d.shapes["a_val"] = Shape({nnz});
+  d.shapes["b"] = Shape({cols, n});
+  d.shapes["dy"] = Shape({rows, n});
+  d.dtypes["a_crow"] = idx;
+  d.dtypes["a_col"] = idx;
+  d.dtypes["a_val"] = kFloat;
+  d.dtypes["b"] = dense;
+  d.dtypes["dy"] = dense;
+  d.attrs["a_rows"] = rows;
+  d.attrs["a_cols"] = cols;
+  return d;
+}
+
+const user_op::KernelRegistration* FindKernel(const std::string& op, const user_op::KernelMatchQuery& q, int* matches) {
+  const user_op::KernelRegistration* found = nullptr;
+  *matches = 0;
+  for (const auto& r : user_op::KernelRegistry())
+    if (r.op == op && r.matched(q)) { found = &r; ++*matches; }
+  return found;
+}
+
+void HostChecks() {
+  // ---- shape / dtype inference
+  TensorDescs d = SpmmDescs(300, 200, 1234, 64, kFloat, kInt32);
+  MockInferContext ic(&d);
+  EXPECT(SpmmCsrOp::InferLogicalTensorDesc(&ic).IsOk());
+  EXPECT(d.shapes.at("out") == Shape({300, 64}));
+  EXPECT(SpmmCsrOp::InferDataType(&ic).IsOk());
+  EXPECT(d.dtypes.at("out") == kFloat);
+  EXPECT(SpmmCsrGradBOp::InferLogicalTensorDesc(&ic).IsOk());
+  EXPECT(d.shapes.at("db") == Shape({200, 64}));
+  EXPECT(SddmmCsrOp::InferLogicalTensorDesc(&ic).IsOk());
+  EXPECT(d.shapes.at("dval") == Shape({1234}));
+  // errors surface as failed Maybe<void> with the message of the failing CHECK
+  TensorDescs bad = SpmmDescs(300, 200, 1234, 64, kFloat, kInt32);
+  bad.attrs["a_cols"] = 7;
+  MockInferContext ic_bad(&bad);
+  Maybe<void> m = SpmmCsrOp::InferLogicalTensorDesc(&ic_bad);
+  EXPECT(!m.IsOk() && m.msg().find("a_cols") != std::string::npos);
+  bad = SpmmDescs(300, 200, 1234, 64, kFloat, kInt32);
+  bad.shapes["a_crow"] = Shape({300});
+  MockInferContext ic_bad2(&bad);
+  m = SpmmCsrOp::InferLogicalTensorDesc(&ic_bad2);
+  EXPECT(!m.IsOk() && m.msg().find("a_rows+1") != std::string::npos);
+  bad = SpmmDescs(300, 200, 1234, 64, kFloat, kInt32);
+  bad.dtypes["a_crow"] = kFloat;
+  MockInferContext ic_bad3(&bad);
+  m = SpmmCsrOp::InferDataType(&ic_bad3);
+  EXPECT(!m.IsOk() && m.msg().find("index dtype") != std::string::npos);
+  // ---- SBP: CSR arrays broadcast, dense side column-split; SDDMM column split -> partial sum
+  MockSbpContext sc({{"a_crow", 0}, {"a_col", 0}, {"a_val", 0}, {"b", 0}}, {{"out", 0}});
+  EXPECT(SpmmCsrOp::GetSbp(&sc).IsOk());
+  EXPECT(sc.signatures.size() == 2);
+  EXPECT(sc.signatures[0].find("b:S(1)") != std::string::npos && sc.signatures[0].find("out:S(1)") != std::string::npos);
+  EXPECT(sc.signatures[0].find("a_col:B") != std::string::npos);
+  MockSbpContext sd({{"a_crow", 0}, {"a_col", 0}, {"dy", 0}, {"b", 0}}, {{"dval", 0}});
+  EXPECT(SddmmCsrOp::GetSbp(&sd).IsOk());
+  EXPECT(sd.signatures[0].find("dval:P") != std::string::npos);
+  // ---- index inputs never require grad (ModifyInputArg)
+  std::map<std::string, user_op::InputArgModifier> mods;
+  auto getter = [&](const std::string& n, int32_t) { return &mods[n]; };
+  EXPECT(SpmmCsrOp::ModifyInputArg(getter, user_op::UserOpConfWrapper()).IsOk());
+  EXPECT(!mods["a_crow"].requires_grad() && !mods["a_col"].requires_grad());
+  // ---- registry: exactly one kernel per (CUDA, dense dtype, index dtype); none for CPU
+  int matches = 0;
+  for (const char* op : {"spmm_csr", "spmm_csr_grad_b", "sddmm_csr"}) {
+    const char* dense_arg = std::string(op) == "spmm_csr_grad_b" ? "dy" : "b";
+    for (DataType dense : {kFloat, kBFloat16})
+      for (DataType idx : {kInt32, kInt64}) {
+        user_op::KernelMatchQuery q{DeviceType::kCUDA, {{dense_arg, dense}, {"a_col", idx}}};
+        EXPECT(FindKernel(op, q, &matches) != nullptr && matches == 1);
+      }
+    user_op::KernelMatchQuery cpu{DeviceType::kCPU, {{dense_arg, kFloat}, {"a_col", kInt32}}};
+    FindKernel(op, cpu, &matches);
+    EXPECT(matches == 0);  // no CPU kernel on this path
+    user_op::KernelMatchQuery f16{DeviceType::kCUDA, {{dense_arg, kFloat16}, {"a_col", kInt32}}};
+    FindKernel(op, f16, &matches);
+    EXPECT(matches == 0);
+  }
+  // ---- tmp_buffer size comes from the library's workspace query
+  user_op::KernelMatchQuery q{DeviceType::kCUDA, {{"b", kFloat}, {"a_col", kInt32}}};
+  const auto* reg = FindKernel("spmm_csr", q, &matches);
+  TensorDescs d2 = SpmmDescs(300, 200, 1234, 64, kFloat, kInt32);
+  MockInferContext ic2(&d2);
+  EXPECT(reg->infer_tmp_size(&ic2) == ofspmm_fwd_workspace_bytes(300, 200, 1234, 64, OFSPMM_DTYPE_FLOAT));
+  std::printf("glue host checks ok: %zu kernel registrations\n", user_op::KernelRegistry().size());
+}
+
+// ------------------------------------------------------------------ GPU part
+#define CUDA_OK(expr)                                                                    \
+  do {                                                                                   \
+    cudaError_t e_ = (expr);                                                             \
+    if (e_ != cudaSuccess) {                                                             \
+      std::fprintf(stderr, "%s:%d: %s\n", __FILE__, __LINE__, cudaGetErrorString(e_));   \
+      std::exit(2);                                                                      \
+    }                                                                                    \
+  } while (0)
+
+class CudaMallocDevice final : public ep::Device {
+ public:
+  Maybe<void> Alloc(const ep::AllocationOptions&, void** ptr, size_t size) override {
+    if (cudaMalloc(ptr, size ? size : 1) != cudaSuccess) return Maybe<void>::Error("cudaMalloc failed");
+    ++live;
+    return Maybe<void>::Ok();
+  }
+  void Free(const ep::AllocationOptions&, void* ptr) override {
+    cudaFree(ptr);
+    --live;
+  }
+  int live = 0;
+};
+
+class DevTensor final : public user_op::Tensor {
+ public:
+  DevTensor(Shape s, DataType t, const void* host, size_t bytes) : shape_(std::move(s)), dtype_(t), bytes_(bytes) {
+    CUDA_OK(cudaMalloc(&ptr_, bytes ? bytes : 1));
+    if (host != nullptr && bytes) CUDA_OK(cudaMemcpy(ptr_, host, bytes, cudaMemcpyHostToDevice));
+  }
+  ~DevTensor() { cudaFree(ptr_); }
+  ShapeView shape_view() const override { return shape_; }
+  DataType data_type() const override { return dtype_; }
+  const void* raw_dptr() const override { return ptr_; }
+  void* mut_raw_dptr() override { return ptr_; }
+  void ToHost(void* dst) const { CUDA_OK(cudaMemcpy(dst, ptr_, bytes_, cudaMemcpyDeviceToHost)); }
+ private:
+  Shape shape_;
+  DataType dtype_;
+  size_t bytes_;
+  void* ptr_ = nullptr;
+};
+
+class MockComputeContext final : public user_op::KernelComputeContext {
+ public:
+  MockComputeContext(ep::Stream* s, std::map<std::string, int64_t> attrs) : stream_(s), attrs_(std::move(attrs)) {}
+  user_op::Tensor* Tensor4ArgNameAndIndex(const std::string& n, int32_t) override {
+    auto it = tensors.find(n);
+    return it == tensors.end() ? nullptr : it->second;
+  }
+  ep::Stream* stream() override { return stream_; }
+  std::map<std::string, user_op::Tensor*> tensors;
+ protected:
+  const int64_t& AttrInt64(const std::string& n) const override { return attrs_.at(n); }
+ private:
+  ep::Stream* stream_;
+  std::map<std::string, int64_t> attrs_;
+};
+
+void GpuChecks() {
+  const int64_t M = 700, K = 500, N = 64;
+  std::mt19937 rng(7);
+  std::uniform_real_distribution<float> uni(-1.f, 1.f);
+  std::vector<int32_t> crow(M + 1, 0), col;
+  std::vector<float> val;
+  for (int64_t i = 0; i < M; ++i) {
+    const int len = i % 97 == 0 ? 400 : static_cast<int>(rng() % 12);  // a few long rows, some empty
+    std::vector<int32_t> cs;
+    for (int t = 0; t < len; ++t) cs.push_back(static_cast<int32_t>(rng() % K));
+    std::sort(cs.begin(), cs.end());
+    cs.erase(std::unique(cs.begin(), cs.end()), cs.end());
+    for (int32_t c : cs) { col.push_back(c); val.push_back(uni(rng)); }
+    crow[i + 1] = static_cast<int32_t>(col.size());
+  }
+  const int64_t nnz = static_cast<int64_t>(col.size());
+  std::vector<float> B(K * N), dY(M * N);
+  for (auto& x : B) x = uni(rng);
+  for (auto& x : dY) x = 0.5f * (uni(rng) + 1.f);
+  // plain-loop expectations (double accumulate)
+  std::vector<double> C(M * N, 0.0), dB(K * N, 0.0), dval(nnz, 0.0);
+  for (int64_t i = 0; i < M; ++i)
+    for (int32_t p = crow[i]; p < crow[i + 1]; ++p)
+      for (int64_t j = 0; j < N; ++j) {
+        C[i * N + j] += static_cast<double>(val[p]) * B[col[p] * N + j];
+        dB[col[p] * N + j] += static_cast<double>(val[p]) * dY[i * N + j];
+        dval[p] += static_cast<double>(dY[i * N + j]) * B[col[p] * N + j];
+      }
+
+  cudaStream_t cs;
+  CUDA_OK(cudaStreamCreate(&cs));
+  CudaMallocDevice device;
+  ep::CudaStream stream(cs, &device);
+  DevTensor t_crow(Shape({M + 1}), kInt32, crow.data(), crow.size() * 4);
+  DevTensor t_col(Shape({nnz}), kInt32, col.data(), col.size() * 4);
+  DevTensor t_val(Shape({nnz}), kFloat, val.data(), val.size() * 4);
+  DevTensor t_b(Shape({K, N}), kFloat, B.data(), B.size() * 4);
+  DevTensor t_dy(Shape({M, N}), kFloat, dY.data(), dY.size() * 4);
+  DevTensor t_out(Shape({M, N}), kFloat, nullptr, C.size() * 4);
+  DevTensor t_db(Shape({K, N}), kFloat, nullptr, dB.size() * 4);
+  DevTensor t_dval(Shape({nnz}), kFloat, nullptr, dval.size() * 4);
+  TensorDescs d = SpmmDescs(M, K, nnz, N, kFloat, kInt32);
+  MockInferContext ic(&d);
+  int matches = 0;
+
+  auto run = [&](const char* op, const char* dense_arg, std::map<std::string, user_op::Tensor*> tensors, int repeat) {
+    user_op::KernelMatchQuery q{DeviceType::kCUDA, {{dense_arg, kFloat}, {"a_col", kInt32}}};
+    const auto* reg = FindKernel(op, q, &matches);
+    EXPECT(reg != nullptr && matches == 1);
+    const size_t tmp = reg->infer_tmp_size(&ic);
+    DevTensor t_tmp(Shape({static_cast<int64_t>(tmp)}), kChar, nullptr, tmp);
+    tensors["tmp_buffer"] = &t_tmp;
+    MockComputeContext ctx(&stream, {{"a_rows", M}, {"a_cols", K}});
+    ctx.tensors = tensors;
+    std::unique_ptr<user_op::OpKernel> kernel = reg->create();
+    user_op::KernelInitContext init;
+    std::shared_ptr<user_op::OpKernelState> state = kernel->CreateOpKernelState(&init);
+    for (int r = 0; r < repeat; ++r) kernel->Compute(&ctx, state.get(), nullptr);  // state reused across calls
+    CUDA_OK(cudaStreamSynchronize(cs));
+  };
+  auto max_err = [](const std::vector<float>& got, const std::vector<double>& want) {
+    double e = 0;
+    for (size_t i = 0; i < got.size(); ++i) e = std::max(e, std::fabs(got[i] - want[i]) / (1.0 + std::fabs(want[i])));
+    return e;
+  };
+
+  run("spmm_csr", "b", {{"a_crow", &t_crow}, {"a_col", &t_col}, {"a_val", &t_val}, {"b", &t_b}, {"out", &t_out}}, 1);
+  std::vector<float> got(C.size());
+  t_out.ToHost(got.data());
+  EXPECT(max_err(got, C) < 2e-5);
+
+  run("spmm_csr_grad_b", "dy", {{"a_crow", &t_crow}, {"a_col", &t_col}, {"a_val", &t_val}, {"dy", &t_dy}, {"db", &t_db}}, 2);
+  got.resize(dB.size());
+  t_db.ToHost(got.data());
+  EXPECT(max_err(got, dB) < 2e-5);
+  EXPECT(device.live == 0);  // the transpose state released its device buffers with the kernel state
+
+  run("sddmm_csr", "b", {{"a_crow", &t_crow}, {"a_col", &t_col}, {"dy", &t_dy}, {"b", &t_b}, {"dval", &t_dval}}, 1);
+  got.resize(dval.size());
+  t_dval.ToHost(got.data());
+  EXPECT(max_err(got, dval) < 2e-5);
+  CUDA_OK(cudaStreamDestroy(cs));
+  std::printf("glue gpu checks ok: spmm_csr / spmm_csr_grad_b / sddmm_csr through OpKernel::Compute, "
+              "%llu library launches\n", static_cast<unsigned long long>(ofspmm_launch_count()));
+}
+
+}  // namespace
+
+int main(int argc, char** argv) {
+  const std::string mode = argc > 1 ? argv[1] : "host";
+  HostChecks();
+  if (mode == "gpu") GpuChecks();
+  return 0;
+}

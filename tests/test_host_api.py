@@ -123,3 +123,17 @@ def test_generators_are_seeded_and_well_formed():
     assert torch.equal(a.col, b.col) and torch.equal(a.val, b.val)
     full = ofs.graphs.expected_alg_bytes(232965, 232965, 114615892, 128, 4)
     assert abs(full["m2"] / 1e9 - 59.72) < 0.01 and abs(full["m1"] / 1e9 - 1.156) < 0.001
+
+
+def test_header_is_plain_c_and_links_from_c(tmp_path):
+    """include/ofspmm.h compiles as C11 (-pedantic) and a C program can link the library and call
+    the host-side entry points — the boundary carries no C++ / CUDA / torch types."""
+    import subprocess
+    exe = tmp_path / "abi_host_check"
+    libdir = os.path.dirname(ofs.LIB_PATH)
+    subprocess.run(["gcc", "-std=c11", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "c", "abi_host_check.c"), "-o", str(exe),
+                    "-L", libdir, "-lofspmm_b200", f"-Wl,-rpath,{libdir}"], check=True, capture_output=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "abi_host_check ok" in out.stdout
