@@ -7,9 +7,6 @@
 
 namespace ofspmm {
 
-constexpr int kWarpSize = 32;
-constexpr int kNumSmsB200 = 148;
-
 // ---------------------------------------------------------------- shared-memory / mbarrier / TMA
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {

@@ -179,9 +179,6 @@ class ShardedSpmm:
         """The rows of an M×n tensor that belong to this rank's row block of A."""
         return dY_full[self.r0:self.r1].contiguous()
 
-    def nnz_per_rank(self) -> List[int]:
-        return []  # filled by callers that hold the full crow; kept for API symmetry
-
     # ------------------------------------------------------------------ collectives
     def _all_gather(self, out: torch.Tensor, inp: torch.Tensor):
         return dist.all_gather_into_tensor(out, inp, group=self.group, async_op=True)
