@@ -137,3 +137,39 @@ def test_header_is_plain_c_and_links_from_c(tmp_path):
     out = subprocess.run([str(exe)], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "abi_host_check ok" in out.stdout
+
+
+def test_partition_host_property_based():
+    """Hypothesis: for arbitrary row-length profiles (empty rows, hub rows, empty matrices) and
+    part counts, the C-ABI host partitioner equals the oracle bit for bit, equals a brute-force
+    walk of the merge list, and its split points are monotone and consistent with crow."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=120, deadline=None)
+    @given(lens=st.lists(st.one_of(st.just(0), st.integers(0, 6), st.integers(0, 300)), min_size=0, max_size=60),
+           parts=st.integers(1, 40), wide=st.booleans())
+    def check(lens, parts, wide):
+        dt = np.int64 if wide else np.int32
+        crow = np.concatenate([[0], np.cumsum(lens)]).astype(dt)
+        M, nnz = len(lens), int(crow[-1])
+        r, z = ofs.merge_path_partition_host(torch.from_numpy(crow), nnz, parts)
+        r, z = r.numpy(), z.numpy()
+        ro, zo = O.merge_path_partition(crow, parts)
+        assert np.array_equal(r, ro) and np.array_equal(z, zo)
+        total = M + nnz
+        ipw = -(-total // parts) if total else 0
+        assert np.array_equal(r + z, np.minimum(np.arange(parts + 1) * ipw, total))
+        assert (np.diff(r) >= 0).all() and (np.diff(z) >= 0).all()
+        assert r[-1] == M and z[-1] == nnz
+        # brute-force merge order: a row-end is consumed as soon as all its non-zeros are
+        i = j = 0
+        order = [(0, 0)]
+        while i < M or j < nnz:
+            if i < M and crow[i + 1] <= j:
+                i += 1
+            else:
+                j += 1
+            order.append((i, j))
+        for k in range(parts + 1):
+            assert (r[k], z[k]) == order[min(k * ipw, total)]
+    check()
