@@ -119,6 +119,17 @@ OFSPMM_API int ofspmm_bwd_b(const ofspmm_csr* A, const ofspmm_csr* At, const voi
                             int64_t n, int dense_dtype, void* workspace, size_t workspace_bytes,
                             ofspmm_stream_t stream);
 
+/* Route (3), for callers without an op state: build A^T transiently inside the workspace (stable
+ * radix sort, ~5 ms for 115 M non-zeros on B200) and run the forward kernel on it — deterministic,
+ * and still faster than route (2).  Workspace = ofspmm_bwd_b_transient_workspace_bytes(...)
+ * (about nnz*(idx+val) + transpose scratch + the forward workspace). */
+OFSPMM_API size_t ofspmm_bwd_b_transient_workspace_bytes(int64_t rows, int64_t cols, int64_t nnz,
+                                                         int64_t n, int dense_dtype, int idx_dtype,
+                                                         int val_dtype);
+OFSPMM_API int ofspmm_bwd_b_transient(const ofspmm_csr* A, const void* dY, void* dB, int64_t n,
+                                      int dense_dtype, void* workspace, size_t workspace_bytes,
+                                      ofspmm_stream_t stream);
+
 /* ---- SDDMM value gradient: dval[p] = <dY[i,:], B[col[p],:]> for every stored entry p of row i
  * (replaces `sddmm_csr`; no reference analogue).  dval has `val_dtype` of A
  * (FLOAT, or BFLOAT16 with a BFLOAT16 dense operand); A->val is not read. */

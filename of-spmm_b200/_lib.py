@@ -17,6 +17,7 @@ DTYPE_FLOAT, DTYPE_INT32, DTYPE_INT64, DTYPE_BFLOAT16 = 2, 5, 6, 11
 
 EXPORTS = (
     "ofspmm_fwd_workspace_bytes", "ofspmm_fwd", "ofspmm_fwd_strided", "ofspmm_bwd_b_workspace_bytes", "ofspmm_bwd_b",
+    "ofspmm_bwd_b_transient_workspace_bytes", "ofspmm_bwd_b_transient",
     "ofspmm_sddmm_workspace_bytes", "ofspmm_sddmm", "ofspmm_partition", "ofspmm_partition_host",
     "ofspmm_row_hist", "ofspmm_csr_transpose_workspace_bytes", "ofspmm_csr_transpose",
     "ofspmm_fwd_host_workspace_bytes", "ofspmm_fwd_host", "ofspmm_strerror", "ofspmm_version",
@@ -69,6 +70,10 @@ def lib() -> ctypes.CDLL:
     L.ofspmm_bwd_b_workspace_bytes.restype = sz
     L.ofspmm_bwd_b.argtypes = [csr_p, csr_p, vp, vp, i64, i32, vp, sz, vp]
     L.ofspmm_bwd_b.restype = i32
+    L.ofspmm_bwd_b_transient_workspace_bytes.argtypes = [i64, i64, i64, i64, i32, i32, i32]
+    L.ofspmm_bwd_b_transient_workspace_bytes.restype = sz
+    L.ofspmm_bwd_b_transient.argtypes = [csr_p, vp, vp, i64, i32, vp, sz, vp]
+    L.ofspmm_bwd_b_transient.restype = i32
     L.ofspmm_sddmm_workspace_bytes.argtypes = [i64, i64, i64, i64, i32]
     L.ofspmm_sddmm_workspace_bytes.restype = sz
     L.ofspmm_sddmm.argtypes = [csr_p, vp, vp, vp, i64, i32, vp, sz, vp]

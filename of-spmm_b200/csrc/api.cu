@@ -156,6 +156,58 @@ int ofspmm_bwd_b(const ofspmm_csr* A, const ofspmm_csr* At, const void* dY, void
   return launch_bwd_atomic(A, dY, reinterpret_cast<float*>(w + part_bytes), dB, n, dense_dtype, w, P, stream);
 }
 
+// Layout of the transient-transpose route: [t_crow | t_col | t_val | transpose scratch | fwd scratch]
+namespace {
+struct TransientLayout {
+  size_t t_crow, t_col, t_val, tws, tws_bytes, fws, total;
+};
+TransientLayout transient_layout(int64_t rows, int64_t cols, int64_t nnz, int64_t n, int dense_dtype,
+                                 int idx_dtype, int val_dtype) {
+  TransientLayout L;
+  const size_t is = idx_size(idx_dtype), vs = val_dtype == OFSPMM_DTYPE_FLOAT ? 4 : 2;
+  size_t off = 0;
+  L.t_crow = off; off += align_up(static_cast<size_t>(cols + 1) * is, 256);
+  L.t_col = off;  off += align_up(static_cast<size_t>(nnz > 0 ? nnz : 1) * is, 256);
+  L.t_val = off;  off += align_up(static_cast<size_t>(nnz > 0 ? nnz : 1) * vs, 256);
+  L.tws = off;    L.tws_bytes = transpose_workspace_bytes(rows, cols, nnz, idx_dtype);
+  off += align_up(L.tws_bytes, 256);
+  L.fws = off;    off += fwd_workspace_layout(cols, nnz, n, dense_dtype).total;
+  L.total = off;
+  return L;
+}
+}  // namespace
+
+size_t ofspmm_bwd_b_transient_workspace_bytes(int64_t rows, int64_t cols, int64_t nnz, int64_t n,
+                                              int dense_dtype, int idx_dtype, int val_dtype) {
+  if (rows < 0 || cols < 0 || nnz < 0 || n < 0 || !idx_ok(idx_dtype)) return 0;
+  return transient_layout(rows, cols, nnz, n, dense_dtype, idx_dtype, val_dtype).total;
+}
+
+int ofspmm_bwd_b_transient(const ofspmm_csr* A, const void* dY, void* dB, int64_t n, int dense_dtype,
+                           void* workspace, size_t workspace_bytes, ofspmm_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (int rc = check_csr(A, true)) return rc;
+  if (int rc = check_dtypes(A, dense_dtype)) return rc;
+  if (n < 0 || n >= (int64_t{1} << 31)) return OFSPMM_ERR_INVALID_ARG;
+  if (A->cols == 0 || n == 0) return OFSPMM_OK;
+  if (dB == nullptr || (A->nnz > 0 && dY == nullptr)) return OFSPMM_ERR_INVALID_ARG;
+  if (A->nnz == 0 || A->rows == 0) {
+    OFSPMM_CUDA_OK(cudaMemsetAsync(dB, 0, static_cast<size_t>(A->cols) * n * dense_size(dense_dtype), stream));
+    return OFSPMM_OK;
+  }
+  const TransientLayout L = transient_layout(A->rows, A->cols, A->nnz, n, dense_dtype, A->idx_dtype, A->val_dtype);
+  if (int rc = check_ws(workspace, workspace_bytes, L.total)) return rc;
+  unsigned char* w = static_cast<unsigned char*>(workspace);
+  if (int rc = launch_transpose(A, w + L.t_crow, w + L.t_col, w + L.t_val, nullptr, w + L.tws, L.tws_bytes, stream)) return rc;
+  ofspmm_csr At = *A;
+  At.rows = A->cols;
+  At.cols = A->rows;
+  At.crow = w + L.t_crow;
+  At.col = w + L.t_col;
+  At.val = w + L.t_val;
+  return run_fwd(&At, dY, n, dB, n, n, dense_dtype, w + L.fws, workspace_bytes - L.fws, stream);
+}
+
 size_t ofspmm_sddmm_workspace_bytes(int64_t rows, int64_t cols, int64_t nnz, int64_t n, int dense_dtype) {
   (void)cols; (void)n; (void)dense_dtype;
   if (rows < 0 || nnz < 0) return 0;

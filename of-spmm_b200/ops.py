@@ -236,3 +236,25 @@ def csr_transpose(a_crow, a_col, a_val, a_rows: int, a_cols: int, want_perm: boo
         check(L.ofspmm_csr_transpose(ctypes.byref(A), _ptr(t_crow), _ptr(t_col), _ptr(t_val), _ptr(t_perm),
                                      wsp, nbytes, _stream_ptr(a_crow)), "csr_transpose")
     return (t_crow, t_col, t_val, t_perm) if want_perm else (t_crow, t_col, t_val)
+
+
+def spmm_csr_grad_b_transient_compute(a_crow, a_col, a_val, dy, a_rows: int, a_cols: int,
+                                      out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """db = A^T · dy through route (3) of the C ABI (``ofspmm_bwd_b_transient``): A^T is built
+    inside the workspace for this call only, then the forward kernel runs on it — deterministic,
+    for callers that hold no op state.  NOTE (round 1): compiled and exported, not yet exercised on
+    a GPU (the round's GPU budget was spent); ``spmm_csr_grad_b_compute`` remains the default."""
+    _check_device(a_crow, a_col, a_val, dy)
+    _chk(dy.dim() == 2 and dy.shape[0] == a_rows and dy.is_contiguous(), f"dy must be contiguous (a_rows={a_rows}) x n")
+    infer_spmm_csr(a_crow, a_col, a_val, dy.new_empty((a_cols, dy.shape[1])), a_rows, a_cols)
+    n, dt = int(dy.shape[1]), dy.dtype
+    if out is None:
+        out = torch.empty((a_cols, n), dtype=dt, device=dy.device)
+    L = _lib.lib()
+    with torch.cuda.device(dy.device):
+        A = _csr_struct(a_crow, a_col, a_val, a_rows, a_cols)
+        nbytes = L.ofspmm_bwd_b_transient_workspace_bytes(a_rows, a_cols, A.nnz, n, _DENSE[dt], A.idx_dtype, A.val_dtype)
+        ws, wsp = _workspace(nbytes, dy.device)
+        check(L.ofspmm_bwd_b_transient(ctypes.byref(A), _ptr(dy), _ptr(out), n, _DENSE[dt], wsp, nbytes,
+                                       _stream_ptr(dy)), "spmm_csr_grad_b(transient)")
+    return out
