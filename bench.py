@@ -193,6 +193,81 @@ def run_reference(args):
     }))
 
 
+def _e2e_pipelined(args, ofs, ops, A, B, dY, n, dtype, dev, flops_step, blocks=8):
+    """EXPERIMENTAL (--e2e-mode pipelined; not yet validated on a GPU in round 1): stream the CSR to
+    the device in nnz-balanced row blocks so the H2D copy of block i+1 overlaps the forward of block
+    i and the D2H of block i-1; A^T·dY runs once the whole CSR and dY have arrived (transient
+    transpose route).  Same bytes per step as the simple mode."""
+    import torch
+    host = {k: v.cpu().pin_memory() for k, v in dict(crow=A.crow, col=A.col, val=A.val, B=B, dY=dY).items()}
+    C_h = torch.empty((A.rows, n), dtype=dtype).pin_memory()
+    dB_h = torch.empty((A.cols, n), dtype=dtype).pin_memory()
+    h2d = sum(v.numel() * v.element_size() for v in host.values())
+    d2h = C_h.numel() * C_h.element_size() + dB_h.numel() * dB_h.element_size()
+    d = {k: torch.empty_like(v, device=dev) for k, v in host.items()}
+    C_d = torch.empty((A.rows, n), dtype=dtype, device=dev)
+    dB_d = torch.empty((A.cols, n), dtype=dtype, device=dev)
+    bounds = ofs.row_blocks(host["crow"], A.nnz, blocks).tolist()      # host twin of the partitioner
+    offs = [int(host["crow"][r]) for r in bounds]
+    s_in, s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    torch.cuda.synchronize()
+
+    def e2e_step():
+        cur = torch.cuda.current_stream()
+        s_in.wait_stream(cur)
+        ev_in, ev_c = [], []
+        with torch.cuda.stream(s_in):
+            d["B"].copy_(host["B"], non_blocking=True)
+            for i in range(blocks):
+                r0, r1, p0, p1 = bounds[i], bounds[i + 1], offs[i], offs[i + 1]
+                d["crow"][r0:r1 + 1].copy_(host["crow"][r0:r1 + 1], non_blocking=True)
+                d["col"][p0:p1].copy_(host["col"][p0:p1], non_blocking=True)
+                d["val"][p0:p1].copy_(host["val"][p0:p1], non_blocking=True)
+                e = torch.cuda.Event()
+                e.record(s_in)
+                ev_in.append(e)
+            d["dY"].copy_(host["dY"], non_blocking=True)
+            ev_dy = torch.cuda.Event()
+            ev_dy.record(s_in)
+        for i in range(blocks):
+            r0, r1, p0, p1 = bounds[i], bounds[i + 1], offs[i], offs[i + 1]
+            cur.wait_event(ev_in[i])
+            if r1 > r0:
+                crow_blk = d["crow"][r0:r1 + 1] - d["crow"][r0:r0 + 1]
+                ops.spmm_csr_compute(crow_blk, d["col"][p0:p1], d["val"][p0:p1], d["B"], r1 - r0, A.cols, out=C_d[r0:r1])
+            e = torch.cuda.Event()
+            e.record(cur)
+            ev_c.append(e)
+        cur.wait_event(ev_dy)
+        ops.spmm_csr_grad_b_transient_compute(d["crow"], d["col"], d["val"], d["dY"], A.rows, A.cols, out=dB_d)
+        ev_b = torch.cuda.Event()
+        ev_b.record(cur)
+        with torch.cuda.stream(s_out):
+            for i in range(blocks):
+                r0, r1 = bounds[i], bounds[i + 1]
+                s_out.wait_event(ev_c[i])
+                C_h[r0:r1].copy_(C_d[r0:r1], non_blocking=True)
+            s_out.wait_event(ev_b)
+            dB_h.copy_(dB_d, non_blocking=True)
+        cur.wait_stream(s_out)
+
+    for _ in range(3):
+        e2e_step()
+    torch.cuda.synchronize()
+    k = max(3, min(args.steps, 10))
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(k):
+        e2e_step()
+    b.record()
+    torch.cuda.synchronize()
+    e2e_ms = a.elapsed_time(b) / k
+    return {"value": flops_step / (e2e_ms * 1e-3) / 1e9, "unit": UNIT, "h2d_bytes_per_step": h2d,
+            "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms,
+            "path": f"pinned host -> device in {blocks} nnz-balanced row blocks on a copy stream, forward per block as "
+                    "it lands, A^T*dY via transient transpose, C blocks / dB -> pinned host on a third stream"}
+
+
 def _teardown(world):
     """Leave the process group without ever hanging the launcher: a watchdog force-exits if NCCL
     teardown does not return (seen after CUDA-graph capture of collectives)."""
@@ -223,6 +298,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--bwd", default="transpose", choices=["transpose", "atomic"])
+    ap.add_argument("--e2e-mode", default="simple", choices=["simple", "pipelined"],
+                    help="pipelined = experimental row-block streaming of the CSR (see _e2e_pipelined)")
     ap.add_argument("--graph", action="store_true",
                     help="N>1: replay the sharded step from a CUDA graph (experimental: measured no faster than eager "
                          "on 8 B200s, and NCCL teardown after capture can hang — off by default)")
@@ -355,7 +432,9 @@ def main():
 
     # ---- e2e through the public op API with pinned host buffers (N=1 path; per rank for N>1)
     e2e = None
-    if not args.no_e2e and world == 1:
+    if not args.no_e2e and world == 1 and args.e2e_mode == "pipelined":
+        e2e = _e2e_pipelined(args, ofs, ops, A, B, dY, n, dtype, dev, flops_step)
+    elif not args.no_e2e and world == 1:
         host = {k: v.cpu().pin_memory() for k, v in dict(crow=A.crow, col=A.col, val=A.val, B=B, dY=dY).items()}
         C_h = torch.empty((A.rows, n), dtype=dtype).pin_memory()
         dB_h = torch.empty((A.cols, n), dtype=dtype).pin_memory()
