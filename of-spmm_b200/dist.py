@@ -29,7 +29,7 @@ partition / shard / pipeline logic under gloo with world_size 2.
 """
 from __future__ import annotations
 
-from typing import Callable, List, Optional
+from typing import Callable, List, Optional  # noqa: F401
 
 import torch
 import torch.distributed as dist

@@ -8,7 +8,6 @@ edge counts and degree clips are generator parameters (SURVEY.md §8d "Provenanc
 """
 from __future__ import annotations
 
-import math
 from dataclasses import dataclass
 from typing import Optional
 

@@ -2,7 +2,6 @@
 torch CSR, tests/golden/make_golden.py) and against scipy / torch live on seeded inputs."""
 import numpy as np
 import pytest
-import scipy.sparse as sp
 import torch
 
 import ofspmm_b200 as ofs
