@@ -13,3 +13,4 @@ from ._lib import LIB_PATH, OfspmmError, OfspmmLibraryError, launch_count  # noq
 from .functional import SpmmOpKernelState, sddmm_csr, spmm_csr, spmm_csr_grad_b  # noqa: F401
 from .ops import (OpInferError, csr_transpose, merge_path_partition, merge_path_partition_host,  # noqa: F401
                   row_blocks, row_hist)
+from . import formats  # noqa: E402,F401

@@ -1,0 +1,144 @@
+"""Data formats either side of the SpMM path: getting a graph *into*
+the CSR arrays the op consumes, and persisting it.
+
+* ``coo_to_csr``           edge list (row, col[, val]) → CSR, duplicates coalesced, columns sorted
+                            within a row — device-agnostic torch (sort + segment ops; runs on the GPU
+                            for the 10⁸-edge graphs of BASELINE.json, on the CPU in the tests).
+* ``add_self_loops`` / ``sym_normalize`` / ``row_normalize``   the GCN preprocessing steps.
+* ``save_csr_npz`` / ``load_csr_npz``   on-disk interchange in the *scipy.sparse.save_npz* layout
+                            (keys ``data, indices, indptr, shape, format``), so a real Reddit /
+                            ogbn-products adjacency exported with SciPy, DGL or PyG drops in where
+                            the synthetic generators are used today.  (The reference's only
+                            persistence is pickle + per-tensor files,
+                            python/oneflow/framework/check_point_v2.py:109-153.)
+* ``load_edge_list``       whitespace / comma separated ``src dst [weight]`` text → CSR.
+
+One-off construction utilities, not on the per-step path: plain torch / numpy, no custom kernels.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+
+from .graphs import CsrMatrix
+
+
+def coo_to_csr(row: torch.Tensor, col: torch.Tensor, val: Optional[torch.Tensor], shape: Tuple[int, int],
+               coalesce: str = "sum", index_dtype: torch.dtype = torch.int32) -> CsrMatrix:
+    """Edge list → CSR.  Duplicate (row, col) pairs are merged: ``coalesce`` = "sum" (Graph500 /
+    scipy convention), "max", or "first".  Entries outside the shape raise; output columns are
+    sorted and unique within each row."""
+    M, K = int(shape[0]), int(shape[1])
+    row, col = row.to(torch.int64).flatten(), col.to(torch.int64).flatten()
+    if row.numel() != col.numel() or (val is not None and val.numel() != row.numel()):
+        raise ValueError("row, col and val must have the same number of entries")
+    if row.numel() and (int(row.min()) < 0 or int(row.max()) >= M or int(col.min()) < 0 or int(col.max()) >= K):
+        raise ValueError(f"edge index outside the {M} x {K} matrix")
+    dev = row.device
+    if val is None:
+        val = torch.ones(row.numel(), dtype=torch.float32, device=dev)
+    val = val.flatten()
+    key = row * K + col
+    key, order = torch.sort(key, stable=True)
+    val = val[order]
+    ukey, inverse, counts = torch.unique_consecutive(key, return_inverse=True, return_counts=True)
+    if ukey.numel() == key.numel():
+        uval = val
+    elif coalesce == "sum":
+        uval = torch.zeros(ukey.numel(), dtype=val.dtype, device=dev).index_add_(0, inverse, val)
+    elif coalesce == "max":
+        uval = torch.full((ukey.numel(),), float("-inf"), dtype=val.dtype, device=dev).scatter_reduce_(0, inverse, val, "amax")
+    elif coalesce == "first":
+        first = torch.cumsum(counts, 0) - counts
+        uval = val[first]
+    else:
+        raise ValueError(f"unknown coalesce mode {coalesce!r}")
+    urow = torch.div(ukey, K, rounding_mode="floor")
+    crow = torch.zeros(M + 1, dtype=torch.int64, device=dev)
+    crow[1:] = torch.cumsum(torch.bincount(urow, minlength=M), 0)
+    if index_dtype == torch.int32 and int(crow[-1]) >= 2 ** 31 - 1:
+        raise ValueError("nnz does not fit int32 row offsets; pass index_dtype=torch.int64")
+    return CsrMatrix(crow.to(index_dtype), (ukey - urow * K).to(index_dtype), uval, M, K)
+
+
+def csr_to_coo(A: CsrMatrix) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    rows = torch.repeat_interleave(torch.arange(A.rows, device=A.crow.device), A.row_lengths())
+    return rows, A.col.to(torch.int64), A.val
+
+
+def add_self_loops(A: CsrMatrix, weight: float = 1.0) -> CsrMatrix:
+    """A + weight·I on the structural level: existing diagonal entries keep their value (GCN's
+    "add remaining self loops")."""
+    if A.rows != A.cols:
+        raise ValueError("self loops need a square matrix")
+    r, c, v = csr_to_coo(A)
+    d = torch.arange(A.rows, device=r.device)
+    return coo_to_csr(torch.cat([r, d]), torch.cat([c, d]),
+                      torch.cat([v, torch.full((A.rows,), weight, dtype=v.dtype, device=r.device)]),
+                      (A.rows, A.cols), coalesce="first", index_dtype=A.crow.dtype)
+
+
+def sym_normalize(A: CsrMatrix) -> CsrMatrix:
+    """D^-1/2 · A · D^-1/2 with D = diag(row sums of |A|) — the GCN propagation matrix."""
+    r, c, v = csr_to_coo(A)
+    deg = torch.zeros(A.rows, dtype=torch.float32, device=r.device).index_add_(0, r, v.abs().float())
+    dinv = torch.where(deg > 0, deg.rsqrt(), torch.zeros_like(deg))
+    return CsrMatrix(A.crow, A.col, (v.float() * dinv[r] * dinv[c]).to(v.dtype), A.rows, A.cols)
+
+
+def row_normalize(A: CsrMatrix) -> CsrMatrix:
+    """D^-1 · A (mean aggregation)."""
+    r, _, v = csr_to_coo(A)
+    deg = torch.zeros(A.rows, dtype=torch.float32, device=r.device).index_add_(0, r, v.abs().float())
+    dinv = torch.where(deg > 0, 1.0 / deg, torch.zeros_like(deg))
+    return CsrMatrix(A.crow, A.col, (v.float() * dinv[r]).to(v.dtype), A.rows, A.cols)
+
+
+def save_csr_npz(path: str, A: CsrMatrix, compressed: bool = True) -> None:
+    """Write A in scipy.sparse.save_npz's layout (readable by scipy.sparse.load_npz)."""
+    arrays = dict(data=A.val.detach().float().cpu().numpy(), indices=A.col.cpu().numpy(), indptr=A.crow.cpu().numpy(),
+                  shape=np.array([A.rows, A.cols], dtype=np.int64), format=np.array("csr".encode("ascii")))
+    (np.savez_compressed if compressed else np.savez)(path, **arrays)
+
+
+def load_csr_npz(path: str, device="cpu", index_dtype: torch.dtype = torch.int32) -> CsrMatrix:
+    """Read a scipy.sparse.save_npz file (csr directly; csc / coo are converted).  Columns are
+    sorted within rows and duplicates summed, as the op expects."""
+    with np.load(path, allow_pickle=False) as z:
+        fmt = z["format"].item()
+        fmt = fmt.decode("ascii") if isinstance(fmt, bytes) else str(fmt)
+        shape = tuple(int(x) for x in z["shape"])
+        if fmt == "csr":
+            indptr, indices, data = z["indptr"], z["indices"], z["data"]
+            rows = np.repeat(np.arange(shape[0], dtype=np.int64), np.diff(indptr))
+            cols = indices.astype(np.int64)
+        elif fmt == "csc":
+            indptr, indices, data = z["indptr"], z["indices"], z["data"]
+            cols = np.repeat(np.arange(shape[1], dtype=np.int64), np.diff(indptr))
+            rows = indices.astype(np.int64)
+        elif fmt == "coo":
+            rows, cols, data = z["row"].astype(np.int64), z["col"].astype(np.int64), z["data"]
+        else:
+            raise ValueError(f"unsupported scipy sparse format {fmt!r}")
+    A = coo_to_csr(torch.from_numpy(rows), torch.from_numpy(cols), torch.from_numpy(np.asarray(data, dtype=np.float32)),
+                   shape, coalesce="sum", index_dtype=index_dtype)
+    return A.to(device)
+
+
+def load_edge_list(path: str, num_nodes: Optional[int] = None, symmetric: bool = False, device="cpu",
+                   delimiter: Optional[str] = None) -> CsrMatrix:
+    """``src dst [weight]`` per line ('#' comments) → square CSR; ``symmetric`` adds the reverse edges."""
+    arr = np.loadtxt(path, comments="#", delimiter=delimiter, ndmin=2)
+    if arr.size == 0:
+        n = int(num_nodes or 0)
+        return CsrMatrix(torch.zeros(n + 1, dtype=torch.int32), torch.zeros(0, dtype=torch.int32), torch.zeros(0), n, n).to(device)
+    src, dst = arr[:, 0].astype(np.int64), arr[:, 1].astype(np.int64)
+    w = arr[:, 2].astype(np.float32) if arr.shape[1] > 2 else np.ones(len(src), np.float32)
+    if symmetric:
+        src, dst, w = np.concatenate([src, dst]), np.concatenate([dst, src]), np.concatenate([w, w])
+    n = int(num_nodes) if num_nodes is not None else int(max(src.max(), dst.max())) + 1
+    A = coo_to_csr(torch.from_numpy(src), torch.from_numpy(dst), torch.from_numpy(w), (n, n),
+                   coalesce="max" if symmetric else "sum")
+    return A.to(device)
