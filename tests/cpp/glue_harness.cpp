@@ -17,6 +17,7 @@
 #include <random>
 
 #include "oneflow/core/ep/cuda/cuda_stream.h"
+#include "oneflow/core/framework/autograd_mock.h"
 #include "oneflow/core/framework/framework.h"
 #include "oneflow/core/framework/op_generated.h"
 #include "ofspmm.h"
@@ -34,6 +35,22 @@ std::vector<KernelRegistration>& KernelRegistry() {
   return r;
 }
 }  // namespace user_op
+namespace one {
+std::vector<DispatchRecord>& DispatchLog() {
+  static std::vector<DispatchRecord> r;
+  return r;
+}
+std::map<std::string, std::function<OpExprGradFunctionIf*()>>& GradFunctionRegistry() {
+  static std::map<std::string, std::function<OpExprGradFunctionIf*()>> r;
+  return r;
+}
+namespace functional {
+std::map<std::string, SpmmFn>& FunctionLibraryStore() {
+  static std::map<std::string, SpmmFn> r;
+  return r;
+}
+}  // namespace functional
+}  // namespace one
 }  // namespace oneflow
 
 using namespace oneflow;
@@ -167,6 +184,62 @@ void HostChecks() {
   MockInferContext ic2(&d2);
   EXPECT(reg->infer_tmp_size(&ic2) == ofspmm_fwd_workspace_bytes(300, 200, 1234, 64, OFSPMM_DTYPE_FLOAT));
   std::printf("glue host checks ok: %zu kernel registrations\n", user_op::KernelRegistry().size());
+}
+
+// ------------------------------------------------------------------ functional layer + grad function
+// (SURVEY.md §8 a8 / a9): functor -> Dispatch with the right op, input order and attrs; the grad
+// function saves only what it needs and dispatches sddmm_csr / spmm_csr_grad_b iff required.
+void AutogradChecks() {
+  using one::Tensor;
+  auto T = [](const char* name, std::vector<int64_t> dims, bool rg) { return std::make_shared<Tensor>(name, std::move(dims), rg); };
+  auto& log = one::DispatchLog();
+  auto crow = T("crow", {301}, false), col = T("col", {1234}, false);
+  // ---- functor: flow._C.spmm_csr(...)
+  log.clear();
+  auto out = one::functional::SpmmCsr(crow, col, T("val", {1234}, true), T("b", {200, 64}, true), 300, 200);
+  EXPECT(out.IsOk() && log.size() == 1 && log[0].op == "spmm_csr");
+  EXPECT((log[0].inputs == std::vector<std::string>{"crow", "col", "val", "b"}));
+  EXPECT(log[0].attrs.at("a_rows") == 300 && log[0].attrs.at("a_cols") == 200);
+  auto bad = one::functional::SpmmCsr(crow, col, T("val", {1234}, true), T("b", {200}, true), 300, 200);
+  EXPECT(!bad.IsOk() && bad.msg().find("RuntimeError") != std::string::npos && bad.msg().find("2-D") != std::string::npos);
+  bad = one::functional::SpmmCsr(crow, col, T("val", {1234}, true), T("b", {7, 64}, true), 300, 200);
+  EXPECT(!bad.IsOk() && bad.msg().find("a_cols") != std::string::npos);
+
+  // ---- grad function registered for "spmm_csr"
+  EXPECT(one::GradFunctionRegistry().count("spmm_csr") == 1);
+  one::UserOpExpr fw;
+  fw.op_type_name = "spmm_csr";
+  fw.proto_.attrs.ints = {{"a_rows", 300}, {"a_cols", 200}};
+  auto run_case = [&](bool val_rg, bool b_rg, one::TensorTuple* in_grads) {
+    std::unique_ptr<one::OpExprGradFunctionIf> g(one::GradFunctionRegistry().at("spmm_csr")());
+    EXPECT(g->Init(fw).IsOk());
+    auto state = g->MakeCustomState();
+    one::TensorTuple inputs = {crow, col, T("val", {1234}, val_rg), T("b", {200, 64}, b_rg)};
+    one::TensorTuple outputs = {T("out", {300, 64}, val_rg || b_rg)};
+    EXPECT(g->CaptureIf(state.get(), inputs, outputs, AttrMap()).IsOk());
+    log.clear();
+    in_grads->assign(4, nullptr);
+    EXPECT(g->ApplyIf(state.get(), {T("dy", {300, 64}, false)}, in_grads).IsOk());
+    return state->SavedTensors().size();
+  };
+  one::TensorTuple ig;
+  // both need grad: SDDMM for the values, A^T·dy for b; index inputs get nothing
+  size_t saved = run_case(true, true, &ig);
+  EXPECT(saved == 4 && log.size() == 2);
+  EXPECT(log[0].op == "sddmm_csr" && (log[0].inputs == std::vector<std::string>{"crow", "col", "dy", "b"}));
+  EXPECT(log[1].op == "spmm_csr_grad_b" && (log[1].inputs == std::vector<std::string>{"crow", "col", "val", "dy"}));
+  EXPECT(log[1].attrs.at("a_rows") == 300 && log[1].attrs.at("a_cols") == 200);
+  EXPECT(ig[0] == nullptr && ig[1] == nullptr && ig[2] != nullptr && ig[3] != nullptr);
+  // only b: no SDDMM, b itself is not saved
+  saved = run_case(false, true, &ig);
+  EXPECT(saved == 3 && log.size() == 1 && log[0].op == "spmm_csr_grad_b" && ig[2] == nullptr && ig[3] != nullptr);
+  // only the values: no A^T·dy, the values themselves are not saved
+  saved = run_case(true, false, &ig);
+  EXPECT(saved == 3 && log.size() == 1 && log[0].op == "sddmm_csr" && ig[2] != nullptr && ig[3] == nullptr);
+  // nothing requires grad: nothing saved, nothing dispatched
+  saved = run_case(false, false, &ig);
+  EXPECT(saved == 0 && log.empty());
+  std::printf("glue autograd checks ok: functors + OpExprGradFunction dispatch as specified\n");
 }
 
 // ------------------------------------------------------------------ GPU part
@@ -319,6 +392,7 @@ void GpuChecks() {
 int main(int argc, char** argv) {
   const std::string mode = argc > 1 ? argv[1] : "host";
   HostChecks();
+  AutogradChecks();
   if (mode == "gpu") GpuChecks();
   return 0;
 }

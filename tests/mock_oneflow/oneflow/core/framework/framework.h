@@ -11,6 +11,7 @@
 #include <memory>
 #include <sstream>
 #include <string>
+#include <type_traits>
 #include <utility>
 #include <vector>
 
@@ -23,26 +24,58 @@ enum DataType { kInvalidDataType = 0, kChar = 1, kFloat = 2, kDouble = 3, kInt8 
 enum class DeviceType { kInvalidDevice = 0, kCPU = 1, kCUDA = 2, kMockDevice = 3 };
 inline bool IsIndexDataType(DataType t) { return t == kInt32 || t == kInt64; }  // data_type_seq.h:50-52
 
-// ---- Maybe<void> / JUST / CHECK_*_OR_RETURN (oneflow/core/common/maybe.h:331, just.h:110-125)
-template <typename T> class Maybe;
-template <> class Maybe<void> {
+// ---- Maybe<T> / JUST / CHECK_*_OR_RETURN (oneflow/core/common/maybe.h:331, just.h:110-125).
+// Like the reference: JUST(x) of a Maybe<class T> yields std::shared_ptr<T>, of a scalar yields T.
+namespace mock {
+struct ErrorCarrier { std::string msg; };
+[[noreturn]] void Fatal(const std::string& msg);
+}  // namespace mock
+template <typename T, typename Enable = void> class Maybe;
+template <> class Maybe<void, void> {
  public:
+  Maybe() = default;
+  Maybe(const mock::ErrorCarrier& e) : ok_(false), msg_(e.msg) {}  // NOLINT
   static Maybe Ok() { return Maybe(); }
-  static Maybe Error(std::string msg) { Maybe m; m.ok_ = false; m.msg_ = std::move(msg); return m; }
+  static Maybe Error(std::string msg) { return Maybe(mock::ErrorCarrier{std::move(msg)}); }
   bool IsOk() const { return ok_; }
   const std::string& msg() const { return msg_; }
+  void Value() const {}
  private:
   bool ok_ = true;
   std::string msg_;
 };
+template <typename T> class Maybe<T, typename std::enable_if<std::is_scalar<T>::value>::type> {
+ public:
+  Maybe(T v) : v_(v) {}  // NOLINT
+  Maybe(const mock::ErrorCarrier& e) : ok_(false), msg_(e.msg) {}  // NOLINT
+  bool IsOk() const { return ok_; }
+  const std::string& msg() const { return msg_; }
+  T Value() const { return v_; }
+ private:
+  T v_{};
+  bool ok_ = true;
+  std::string msg_;
+};
+template <typename T> class Maybe<T, typename std::enable_if<std::is_class<T>::value>::type> {
+ public:
+  Maybe(std::shared_ptr<T> v) : v_(std::move(v)) {}  // NOLINT
+  Maybe(const mock::ErrorCarrier& e) : ok_(false), msg_(e.msg) {}  // NOLINT
+  bool IsOk() const { return ok_; }
+  const std::string& msg() const { return msg_; }
+  std::shared_ptr<T> Value() const { return v_; }
+ private:
+  std::shared_ptr<T> v_;
+  bool ok_ = true;
+  std::string msg_;
+};
+struct Error { static const char* RuntimeError() { return "RuntimeError: "; } };
 namespace mock {
-struct ErrorStream {  // collects `<< msg` and converts to a failed Maybe<void>
+struct ErrorStream {  // collects `<< msg` and converts to a failed Maybe<T>
   explicit ErrorStream(const char* cond) { ss << "Check failed: " << cond << " "; }
   template <typename T> ErrorStream& operator<<(const T& v) { ss << v; return *this; }
-  operator Maybe<void>() const { return Maybe<void>::Error(ss.str()); }
+  template <typename T> operator Maybe<T>() const { return Maybe<T>(ErrorCarrier{ss.str()}); }
   std::ostringstream ss;
 };
-[[noreturn]] void Fatal(const std::string& msg);
 struct FatalStream {  // glog-style fatal CHECK
   explicit FatalStream(const char* cond) { ss << "Check failed: " << cond << " "; }
   template <typename T> FatalStream& operator<<(const T& v) { ss << v; return *this; }
@@ -54,8 +87,9 @@ struct FatalStream {  // glog-style fatal CHECK
 #define CHECK_EQ_OR_RETURN(a, b) CHECK_OR_RETURN((a) == (b))
 #define CHECK_GE_OR_RETURN(a, b) CHECK_OR_RETURN((a) >= (b))
 #define CHECK_NOTNULL_OR_RETURN(p) CHECK_OR_RETURN((p) != nullptr)
-#define JUST(expr) do { auto just_maybe = (expr); if (!just_maybe.IsOk()) return just_maybe; } while (0)
-#define CHECK_JUST(expr) do { auto cj = (expr); if (!cj.IsOk()) ::oneflow::mock::Fatal(cj.msg()); } while (0)
+// GNU statement expressions, as in the reference's just.h
+#define JUST(expr) ({ auto&& just_m_ = (expr); if (!just_m_.IsOk()) return ::oneflow::mock::ErrorCarrier{just_m_.msg()}; just_m_.Value(); })
+#define CHECK_JUST(expr) ({ auto&& cj_m_ = (expr); if (!cj_m_.IsOk()) ::oneflow::mock::Fatal(cj_m_.msg()); cj_m_.Value(); })
 #define CHECK_EQ(a, b) if ((a) == (b)) {} else ::oneflow::mock::FatalStream(#a " == " #b)
 #define CHECK_NOTNULL(p) if ((p) != nullptr) {} else ::oneflow::mock::FatalStream(#p " != nullptr")
 

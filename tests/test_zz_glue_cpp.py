@@ -1,4 +1,4 @@
-"""The C++ OneFlow glue (of-spmm_b200/oneflow_glue/spmm_op.cpp + spmm_kernels.cpp) compiled against
+"""The C++ OneFlow glue (of-spmm_b200/oneflow_glue/spmm_{op,kernels,functor,grad}.cpp) compiled against
 the minimal framework stand-in in tests/mock_oneflow and driven like the reference's framework
 drives a user op (tests/cpp/glue_harness.cpp): inference, SBP, REGISTER_USER_KERNEL predicates,
 InferTmpSize on the CPU; OpKernel::Compute on a CUDA stream on the GPU box."""
@@ -20,7 +20,8 @@ def _build(tmp_path):
     cmd = ["g++", "-std=c++17", "-O1", "-Wall", "-DWITH_CUDA", "-I", os.path.join(ROOT, "tests", "mock_oneflow"),
            "-I", os.path.join(ROOT, "include"), "-I", os.path.join(CUDA, "include"),
            os.path.join(ROOT, "tests", "cpp", "glue_harness.cpp"), os.path.join(GLUE, "spmm_op.cpp"),
-           os.path.join(GLUE, "spmm_kernels.cpp"), "-o", exe, "-L", libdir, "-lofspmm_b200", f"-Wl,-rpath,{libdir}",
+           os.path.join(GLUE, "spmm_kernels.cpp"), os.path.join(GLUE, "spmm_functor.cpp"),
+           os.path.join(GLUE, "spmm_grad.cpp"), "-o", exe, "-L", libdir, "-lofspmm_b200", f"-Wl,-rpath,{libdir}",
            "-L", os.path.join(CUDA, "lib64"), "-lcudart_static", "-ldl", "-lrt", "-lpthread"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-3000:]
@@ -31,6 +32,7 @@ def test_glue_compiles_and_host_side_behaves(tmp_path):
     out = subprocess.run([_build(tmp_path), "host"], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "glue host checks ok: 12 kernel registrations" in out.stdout
+    assert "glue autograd checks ok" in out.stdout          # functors + OpExprGradFunction
 
 
 @pytest.mark.gpu
