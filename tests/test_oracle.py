@@ -138,3 +138,22 @@ def test_bf16_helpers_match_torch():
     back = O.bf16_to_f32(ours)
     assert np.array_equal(back[~nan], x.to(torch.bfloat16).float().numpy()[~nan])
     assert np.isnan(back[nan]).all()
+
+
+def test_sbp_signatures_of_the_glue_are_semantically_valid():
+    """The GetSbp signatures in oneflow_glue/spmm_op.cpp, checked on the maths with the oracle:
+    B×4 ⊗ S(1)(b) → S(1)(out) for spmm_csr / spmm_csr_grad_b (a column split of the dense side
+    commutes with the row-wise linear map), and S(1)(dy), S(1)(b) → P(dval) for sddmm_csr (a split
+    of the contraction axis makes the result a partial sum)."""
+    A = graphs.uniform_csr(300, 200, 0.05, seed=12)
+    crow, col, val = A.crow.numpy(), A.col.numpy(), A.val.numpy()
+    B = graphs.dense_operand(200, 48, 12).numpy()
+    dY = graphs.upstream_grad(300, 48, 12).numpy()
+    halves = [slice(0, 20), slice(20, 48)]          # uneven split on purpose
+    C = O.spmm_f32(crow, col, val, B)
+    assert np.array_equal(np.concatenate([O.spmm_f32(crow, col, val, np.ascontiguousarray(B[:, h])) for h in halves], 1), C)
+    dB = O.spmm_t_f32(crow, col, val, dY, 200)
+    assert np.array_equal(np.concatenate([O.spmm_t_f32(crow, col, val, np.ascontiguousarray(dY[:, h]), 200) for h in halves], 1), dB)
+    dv64, _ = O.sddmm_f64(crow, col, dY, B)
+    parts = [O.sddmm_f64(crow, col, np.ascontiguousarray(dY[:, h]), np.ascontiguousarray(B[:, h]))[0] for h in halves]
+    np.testing.assert_allclose(parts[0] + parts[1], dv64, rtol=1e-12, atol=1e-12)
