@@ -537,6 +537,7 @@ def main():
                      "model": "M2 gather model: nnz*(idx+val) + (M+1)*idx + nnz*N*s + M*N*s bytes per launch "
                               "(SURVEY.md 8d); B-row gathers are mostly L2 hits, so achieved may exceed the HBM copy "
                               "peak - see traffic (ncu dram bytes) and DESIGN.md",
+                     "frac_of_nominal_8tbs": achieved / 8000.0,
                      "alg_bytes": fwd_bytes, "m1_compulsory_bytes": alg["m1"],
                      "m1_gbs": alg["m1"] / (fwd_ms * 1e-3) / 1e9 / max(1, world)},
         "gpu_launches": int(launches),
