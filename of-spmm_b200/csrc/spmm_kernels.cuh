@@ -121,6 +121,12 @@ __device__ __forceinline__ StagedTask<IdxT, ValT> stage_task(
   const uint32_t tx = static_cast<uint32_t>(body_c * sizeof(IdxT) + body_v * sizeof(ValT) +
                                             body_r * sizeof(IdxT));
   __syncwarp();  // every lane is done reading the previous task's stage
+#ifdef OFSPMM_PROXY_FENCE
+  // formal-model nicety (off by default, see ROUND_NOTES.md): order this warp's earlier generic-proxy
+  // shared-memory stores (sanitise pass, ragged edges, SDDMM staging) before the async-proxy writes
+  // of the next bulk copies into the same bytes
+  if (lane == 0) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#endif
   if (lane == 0 && tx != 0) {
     mbar_arrive_expect_tx(bar, tx);
     if (body_c) tma_bulk_g2s(st.col + pre_c + head_c, col + ns + head_c, body_c * sizeof(IdxT), bar, pol_stream);
@@ -358,6 +364,42 @@ spmm_merge_kernel(const FwdParams p) {
           const int q0 = chunk_first == 0 ? kChunkStride : chunk_first;
           uint32_t ca = col_sa + static_cast<uint32_t>(cbase + 4 * q0) * 4u;
           const uint32_t cend = col_sa + static_cast<uint32_t>(cbase + 4 * (nchunks - 1)) * 4u;
+#if defined(OFSPMM_CHUNKS_PER_ITER) && OFSPMM_CHUNKS_PER_ITER == 2
+          // tuning experiment (off by default): two index chunks = eight gathers in flight per
+          // iteration; the single-chunk loop below then only handles an odd leftover chunk
+          while (ca + 16u * kChunkStride < cend) {
+            const uint4 ca4 = lds128(ca), cb4 = lds128(ca + 16u * kChunkStride);
+            const uint32_t c8[8] = {ca4.x, ca4.y, ca4.z, ca4.w, cb4.x, cb4.y, cb4.z, cb4.w};
+            typename RV::Raw x8[8][CH];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const char* brow = Bl + static_cast<unsigned long long>(c8[u]) * row_bytes;
+#pragma unroll
+              for (int ch = 0; ch < CH; ++ch)
+                x8[u][ch] = load_b<DT, VEC>(brow + (kFull ? ch * kChunkBytes : choff[ch]), pol_b);
+            }
+            float v8[8];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const uint32_t cah = ca + h * 16u * kChunkStride;
+              const uint32_t va = sizeof(ValT) == 4 ? cah + (val_s0 - col_sa) : val_s0 + ((cah - col_sa) >> 1);
+              if constexpr (sizeof(ValT) == 4) {
+                const uint4 w = lds128(va);
+                v8[4 * h + 0] = __uint_as_float(w.x); v8[4 * h + 1] = __uint_as_float(w.y);
+                v8[4 * h + 2] = __uint_as_float(w.z); v8[4 * h + 3] = __uint_as_float(w.w);
+              } else {
+                const uint2 w = lds64(va);
+                v8[4 * h + 0] = __uint_as_float(w.x << 16); v8[4 * h + 1] = __uint_as_float(w.x & 0xffff0000u);
+                v8[4 * h + 2] = __uint_as_float(w.y << 16); v8[4 * h + 3] = __uint_as_float(w.y & 0xffff0000u);
+              }
+            }
+            ca += 32u * kChunkStride;
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+#pragma unroll
+              for (int ch = 0; ch < CH; ++ch) RV::fma(acc[ch], v8[u], x8[u][ch]);
+          }
+#endif
           if (ca < cend) {
             uint4 cn = lds128(ca);
             do {
