@@ -25,9 +25,21 @@ _c_int = ctypes.c_int
 _vp = ctypes.c_void_p
 
 
+def _cpu_tag() -> str:
+    """Short hash of this host's CPU model + ISA flags: a -march=native build is only valid on the
+    machine type that built it (the repo snapshot, built files included, travels to other boxes)."""
+    import hashlib
+    try:
+        with open("/proc/cpuinfo") as f:
+            lines = [ln for ln in f if ln.startswith(("model name", "flags"))][:2]
+    except OSError:
+        lines = []
+    return hashlib.sha1("".join(lines).encode()).hexdigest()[:10]
+
+
 def build(native: bool = False, force: bool = False) -> str:
     """Compile the oracle with gcc if the shared object is missing or older than its source."""
-    name = "libofspmm_oracle_native.so" if native else "libofspmm_oracle.so"
+    name = f"libofspmm_oracle_native_{_cpu_tag()}.so" if native else "libofspmm_oracle.so"
     so = os.path.join(_OUT, name)
     if not force and os.path.exists(so) and os.path.getmtime(so) >= os.path.getmtime(_SRC):
         return so
