@@ -542,6 +542,8 @@ def main():
                      "m1_gbs": alg["m1"] / (fwd_ms * 1e-3) / 1e9 / max(1, world)},
         "gpu_launches": int(launches),
         "clocks": clocks,
+        "reference_cuda_path": "n/a: the reference snapshot has no SpMM kernel and OneFlow does not build offline "
+                               "(SURVEY.md 0.1-0.2); the CPU arm is `bench.py --impl reference`",
     }
     if world == 1:
         out["plan_ms_one_off"] = plan_ms
