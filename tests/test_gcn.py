@@ -60,7 +60,7 @@ def test_gcn_forward_backward_gpu_matches_dense():
     # hidden width of configs[4] on a Reddit twin: runs and stays finite
     A2 = ofs.graphs.gcn_normalize(ofs.graphs.add_self_loops(ofs.graphs.reddit_like(256, seed=2))).to("cuda:0")
     X2 = ofs.graphs.dense_operand(A2.rows, 602, 4, "cuda:0")
-    y2 = torch.randint(0, 41, (A2.rows,), device="cuda:0")
+    y2 = torch.randint(0, 41, (A2.rows,), generator=torch.Generator().manual_seed(2)).to("cuda:0")
     m2 = gcn.GCN2(A2)
     l0 = float(m2.train_step(X2, y2, lr=0.1))
     l1 = float(m2.train_step(X2, y2, lr=0.1))
