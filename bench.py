@@ -150,7 +150,18 @@ def _cpu_baseline(A, B, dY, n, seconds_target=12.0):
     rows = max(probe_rows, min(M, rows))
     t, nnz_s = run(rows)
     flops = 2.0 * 2.0 * nnz_s * n
+    # the reference's default CPU_THREADING_RUNTIME is SEQ (CMakeLists.txt:54): also time the plain
+    # single-thread loop, on a 1/16 sample so the whole baseline stays within seconds
+    rows1 = max(1, rows // 16)
+    p1 = int(crow_all[rows1])
+    t0 = time.perf_counter()
+    O.spmm_f32(crow_all[:rows1 + 1], A.col[:p1].cpu().numpy(), A.val[:p1].float().cpu().numpy(), Bh, A.cols,
+               threads=1, native=native)
+    O.spmm_t_f32(crow_all[:rows1 + 1], A.col[:p1].cpu().numpy(), A.val[:p1].float().cpu().numpy(),
+                 dY[:rows1].float().cpu().numpy(), A.cols, threads=1, native=native)
+    t1 = max(time.perf_counter() - t0, 1e-9)
     return {"value": flops / t / 1e9, "unit": UNIT, "cores": cores, "kind": "port",
+            "single_thread_value": 2.0 * 2.0 * p1 * n / t1 / 1e9,
             "sample": f"first {rows} of {M} rows ({nnz_s} nnz), fwd (rows split over {cores} threads) + A^T*dY "
                       f"(per-thread accumulators), {t:.2f} s, oracle built {'-march=native' if native else 'x86-64-v3'}"}
 
