@@ -26,7 +26,9 @@
  *   - outputs are fully overwritten (the framework does not zero them,
  *     oneflow/core/vm/op_call_instruction_policy.cpp:78-85);
  *   - column indices outside [0, cols) are skipped, as the reference's segment-sum skips
- *     out-of-range ids (oneflow/user/kernels/unsorted_segment_sum_kernel_util.cpp:35-39).
+ *     out-of-range ids (oneflow/user/kernels/unsorted_segment_sum_kernel_util.cpp:35-39): nothing
+ *     is loaded for such an entry, in every product and in the transpose (where they end up behind
+ *     the last row of A^T with column -1).
  *
  * dtype codes reuse OneFlow's DataType numbering (oneflow/core/common/data_type.proto:4-17) so
  * the glue passes `tensor->data_type()` through unchanged.
@@ -83,6 +85,46 @@ typedef struct ofspmm_csr {
   int32_t val_dtype;
 } ofspmm_csr;
 
+/* ---- Per-call options of the *_ex entry points.  Zero-initialise for the defaults; a NULL
+ * `opts` means all defaults.  Everything a launch depends on is in the arguments: the library
+ * reads no environment variable and keeps no mutable global (SURVEY.md §8b "Threading"). */
+enum {
+  OFSPMM_FWD_ACCUMULATE = 1, /* C += A·B instead of C = A·B (second pass of a column-bucketed product) */
+  OFSPMM_FWD_BIAS = 2,       /* fused epilogue: + bias[j] (opts->bias: n elements of the dense dtype)    */
+  OFSPMM_FWD_RELU = 4,       /* fused epilogue: max(., 0), after the bias (GCNConv; precedent for a
+                                fused epilogue: oneflow/user/kernels/cublas_fused_mlp_kernel.cu)        */
+  OFSPMM_ORDER_DYNAMIC = 8,  /* persistent grid draws its tasks from a counter, in launch order         */
+  OFSPMM_ORDER_STATIC = 16   /* persistent grid uses the fixed interleave (warp w: tasks w, w+W, ...)   */
+};
+/* Task order when neither ORDER bit is set (measured default). */
+#ifndef OFSPMM_DEFAULT_DYNAMIC_ORDER
+#define OFSPMM_DEFAULT_DYNAMIC_ORDER 1
+#endif
+
+/* Kernel variant of the forward-shaped products.  AUTO decides from (rows, nnz, n, dtype); with the
+ * row-length histogram on the host, ofspmm_choose_variant() returns an EXPLICIT code. */
+enum {
+  OFSPMM_VARIANT_AUTO = 0,
+  OFSPMM_VARIANT_ITEMS64 = 1,  /* 64 merge items per warp task (small problems: 4x more warps)      */
+  OFSPMM_VARIANT_ROWPAR = 2,   /* sub-warp per row instead of nnz-parallel groups (short rows x
+                                  narrow dense operand)                                              */
+  OFSPMM_VARIANT_UNROLL8 = 4,  /* eight B-row gathers in flight per lane group (long rows, fp32)     */
+  OFSPMM_VARIANT_EXPLICIT = 0x100
+};
+
+typedef struct ofspmm_opts {
+  uint32_t flags;         /* OFSPMM_FWD_* | OFSPMM_ORDER_*                                           */
+  int32_t tasks_per_warp; /* 0: persistent grid.  k > 0: CTAs retire after ~k tasks per warp, so a
+                             kernel on another stream (a collective, the peer pull) gets SMs while
+                             this one runs                                                          */
+  int32_t variant;        /* OFSPMM_VARIANT_AUTO or a code from ofspmm_choose_variant               */
+  int32_t reserved;
+  const void* plan;       /* device plan from ofspmm_plan_build for THIS (crow, variant); NULL: the
+                             partition is recomputed inside the call                                */
+  size_t plan_bytes;
+  const void* bias;       /* OFSPMM_FWD_BIAS: n elements of the dense dtype                          */
+} ofspmm_opts;
+
 /* ---- SpMM forward: C[rows × n] = A · B[cols × n]  (replaces the `spmm_csr` kernel body; data
  * movement analogue in the reference: GatherForwardGpu + UnsortedSegmentRowSumGpu,
  * oneflow/user/kernels/gather_kernel_util.cu:28-41,
@@ -102,6 +144,29 @@ OFSPMM_API int ofspmm_fwd(const ofspmm_csr* A, const void* B, void* C, int64_t n
 OFSPMM_API int ofspmm_fwd_strided(const ofspmm_csr* A, const void* B, int64_t ldb, void* C,
                                   int64_t ldc, int64_t n, int dense_dtype, void* workspace,
                                   size_t workspace_bytes, ofspmm_stream_t stream);
+
+/* Forward with options: strides as in ofspmm_fwd_strided, plus variant / plan / launch policy /
+ * fused epilogue.  Workspace = ofspmm_fwd_ex_workspace_bytes(..., opts->variant). */
+OFSPMM_API size_t ofspmm_fwd_ex_workspace_bytes(int64_t rows, int64_t cols, int64_t nnz, int64_t n,
+                                                int dense_dtype, int variant);
+OFSPMM_API int ofspmm_fwd_ex(const ofspmm_csr* A, const void* B, int64_t ldb, void* C, int64_t ldc,
+                             int64_t n, int dense_dtype, const ofspmm_opts* opts, void* workspace,
+                             size_t workspace_bytes, ofspmm_stream_t stream);
+
+/* ---- Plan: the task partition of one (crow, variant), computed once and kept by the caller in
+ * the op's OpKernelState (oneflow/user/kernels/stateful_opkernel.cpp:919-928) for as long as `crow`
+ * is unchanged; every product then skips the partition kernel.  Device buffer of
+ * ofspmm_plan_bytes(), 16-byte aligned, read-only to the products (safe to share between streams). */
+OFSPMM_API size_t ofspmm_plan_bytes(int64_t rows, int64_t nnz, int64_t n, int dense_dtype, int variant);
+OFSPMM_API int ofspmm_plan_build(const void* crow, int idx_dtype, int64_t rows, int64_t nnz, int64_t n,
+                                 int dense_dtype, int variant, void* plan, size_t plan_bytes,
+                                 ofspmm_stream_t stream);
+
+/* ---- Variant choice from the row-length histogram (north_star (2)).  `hist32_host` = the 32
+ * counters of ofspmm_row_hist copied to the HOST (once, when the op state is built — never inside a
+ * captured call); NULL gives the AUTO decision.  Pure host function, no CUDA call. */
+OFSPMM_API int ofspmm_choose_variant(const int64_t* hist32_host, int64_t rows, int64_t nnz, int64_t n,
+                                     int dense_dtype);
 
 /* ---- Backward wrt the dense operand: dB[cols × n] = A^T · dY[rows × n]  (replaces
  * `spmm_csr_grad_b`; reference analogue = memset + atomic scatter-add,
@@ -130,6 +195,17 @@ OFSPMM_API int ofspmm_bwd_b_transient(const ofspmm_csr* A, const void* dY, void*
                                       int dense_dtype, void* workspace, size_t workspace_bytes,
                                       ofspmm_stream_t stream);
 
+/* Route (1'), the one the OneFlow glue uses: the caller caches only the STRUCTURE of A^T
+ * (t_crow[cols+1], t_col[nnz], t_perm[nnz] from ofspmm_csr_transpose — ordinary tensors owned by
+ * the framework) and the values are re-gathered from A->val through t_perm on every call, so
+ * in-place updates of a_val are always seen and no hidden pointer-keyed cache exists. */
+OFSPMM_API size_t ofspmm_bwd_b_cached_workspace_bytes(int64_t rows, int64_t cols, int64_t nnz,
+                                                      int64_t n, int dense_dtype, int val_dtype);
+OFSPMM_API int ofspmm_bwd_b_cached(const ofspmm_csr* A, const void* t_crow, const void* t_col,
+                                   const void* t_perm, const void* dY, void* dB, int64_t n,
+                                   int dense_dtype, const ofspmm_opts* opts, void* workspace,
+                                   size_t workspace_bytes, ofspmm_stream_t stream);
+
 /* ---- SDDMM value gradient: dval[p] = <dY[i,:], B[col[p],:]> for every stored entry p of row i
  * (replaces `sddmm_csr`; no reference analogue).  dval has `val_dtype` of A
  * (FLOAT, or BFLOAT16 with a BFLOAT16 dense operand); A->val is not read. */
@@ -138,6 +214,10 @@ OFSPMM_API size_t ofspmm_sddmm_workspace_bytes(int64_t rows, int64_t cols, int64
 OFSPMM_API int ofspmm_sddmm(const ofspmm_csr* A, const void* dY, const void* B, void* dval,
                             int64_t n, int dense_dtype, void* workspace, size_t workspace_bytes,
                             ofspmm_stream_t stream);
+
+OFSPMM_API int ofspmm_sddmm_ex(const ofspmm_csr* A, const void* dY, const void* B, void* dval,
+                               int64_t n, int dense_dtype, const ofspmm_opts* opts, void* workspace,
+                               size_t workspace_bytes, ofspmm_stream_t stream);
 
 /* ---- Merge-path / nnz-balanced partitioner.  Splits the merged list of
  * (row-end, non-zero) items into `parts` equal spans; writes parts+1 split points
@@ -153,8 +233,8 @@ OFSPMM_API int ofspmm_partition_host(const void* crow_host, int idx_dtype, int64
                                      int64_t* out_nz_host);
 
 /* ---- Row-length histogram in log2 buckets: hist[0] = empty rows, hist[b] = rows with
- * 2^(b-1) <= len < 2^b (b = 1..31).  32 device int64 counters, overwritten.  Feeds the kernel
- * variant choice. */
+ * 2^(b-1) <= len < 2^b (b = 1..31).  32 device int64 counters, overwritten.  Copied to the host
+ * once (op-state construction) it feeds ofspmm_choose_variant. */
 OFSPMM_API int ofspmm_row_hist(const void* crow, int idx_dtype, int64_t rows, int64_t* hist32,
                                ofspmm_stream_t stream);
 
@@ -168,6 +248,23 @@ OFSPMM_API size_t ofspmm_csr_transpose_workspace_bytes(int64_t rows, int64_t col
 OFSPMM_API int ofspmm_csr_transpose(const ofspmm_csr* A, void* t_crow, void* t_col, void* t_val,
                                     void* t_perm, void* workspace, size_t workspace_bytes,
                                     ofspmm_stream_t stream);
+
+/* ---- Row exchange of the multi-GPU path.  `src` may be a PEER-mapped device
+ * pointer (CUDA IPC / symmetric memory): the kernels read it with ordinary 16-byte loads over
+ * NVLink / NVSwitch.  list == NULL means the identity (rows 0..count-1).  max_ctas caps the grid so
+ * the copy shares the GPU with the product it overlaps (0: library default).
+ *   gather:       dst[i, :]                       = src[list[i] - idx_offset, :]
+ *   scatter-add:  dst[list[i] - idx_offset, :]   += src[i, :]      (entries of `list` distinct)
+ * The reference gathers the WHOLE operand on every rank with a blocking ncclAllGather before the op
+ * (oneflow/core/boxing/ccl_boxing_function.cpp:183-197, oneflow/user/kernels/nccl_logical_kernels.cpp:194-200);
+ * here a rank pulls only the rows its block touches, while its local columns are already computing. */
+OFSPMM_API int ofspmm_gather_rows(void* dst, int64_t ld_dst, const void* src, int64_t ld_src,
+                                  const void* list, int idx_dtype, int64_t idx_offset, int64_t count,
+                                  int64_t n, int dense_dtype, int max_ctas, ofspmm_stream_t stream);
+OFSPMM_API int ofspmm_scatter_add_rows(void* dst, int64_t ld_dst, const void* src, int64_t ld_src,
+                                       const void* list, int idx_dtype, int64_t idx_offset,
+                                       int64_t count, int64_t n, int dense_dtype, int max_ctas,
+                                       ofspmm_stream_t stream);
 
 /* ---- Host-buffer convenience entry (what a CPU-tensor caller / the e2e benchmark uses): copies
  * the CSR arrays and B from HOST memory (pinned recommended) to device staging carved from
@@ -186,8 +283,11 @@ OFSPMM_API int ofspmm_version(void);
 /* Number of kernels the library has launched on this process so far (monotonic, relaxed atomic);
  * the benchmark reports the delta over its timed region as `gpu_launches`. */
 OFSPMM_API uint64_t ofspmm_launch_count(void);
-/* Name of the kernel variant ofspmm_fwd would pick for this shape (static string). */
+/* Name of the kernel variant ofspmm_fwd would pick for this shape (AUTO), or of an explicit
+ * variant code (thread-local string, valid until the next call on the same thread). */
 OFSPMM_API const char* ofspmm_fwd_variant(int64_t rows, int64_t nnz, int64_t n, int dense_dtype);
+OFSPMM_API const char* ofspmm_variant_name(int variant, int64_t rows, int64_t nnz, int64_t n,
+                                           int dense_dtype);
 
 #ifdef __cplusplus
 }

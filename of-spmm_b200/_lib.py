@@ -21,8 +21,15 @@ EXPORTS = (
     "ofspmm_sddmm_workspace_bytes", "ofspmm_sddmm", "ofspmm_partition", "ofspmm_partition_host",
     "ofspmm_row_hist", "ofspmm_csr_transpose_workspace_bytes", "ofspmm_csr_transpose",
     "ofspmm_fwd_host_workspace_bytes", "ofspmm_fwd_host", "ofspmm_strerror", "ofspmm_version",
-    "ofspmm_launch_count", "ofspmm_fwd_variant",
+    "ofspmm_launch_count", "ofspmm_fwd_variant", "ofspmm_variant_name",
+    "ofspmm_fwd_ex_workspace_bytes", "ofspmm_fwd_ex", "ofspmm_plan_bytes", "ofspmm_plan_build",
+    "ofspmm_choose_variant", "ofspmm_bwd_b_cached_workspace_bytes", "ofspmm_bwd_b_cached", "ofspmm_sddmm_ex",
+    "ofspmm_gather_rows", "ofspmm_scatter_add_rows",
 )
+
+# ofspmm_opts.flags / variant codes (include/ofspmm.h)
+FWD_ACCUMULATE, FWD_BIAS, FWD_RELU, ORDER_DYNAMIC, ORDER_STATIC = 1, 2, 4, 8, 16
+VARIANT_AUTO, VARIANT_ITEMS64, VARIANT_ROWPAR, VARIANT_UNROLL8, VARIANT_EXPLICIT = 0, 1, 2, 4, 0x100
 
 
 class OfspmmLibraryError(ImportError):
@@ -41,6 +48,13 @@ class CsrStruct(ctypes.Structure):
     _fields_ = [("rows", ctypes.c_int64), ("cols", ctypes.c_int64), ("nnz", ctypes.c_int64),
                 ("crow", ctypes.c_void_p), ("col", ctypes.c_void_p), ("val", ctypes.c_void_p),
                 ("idx_dtype", ctypes.c_int32), ("val_dtype", ctypes.c_int32)]
+
+
+class OptsStruct(ctypes.Structure):
+    """struct ofspmm_opts (include/ofspmm.h)."""
+    _fields_ = [("flags", ctypes.c_uint32), ("tasks_per_warp", ctypes.c_int32), ("variant", ctypes.c_int32),
+                ("reserved", ctypes.c_int32), ("plan", ctypes.c_void_p), ("plan_bytes", ctypes.c_size_t),
+                ("bias", ctypes.c_void_p)]
 
 
 _LIB = None
@@ -98,6 +112,29 @@ def lib() -> ctypes.CDLL:
     L.ofspmm_launch_count.restype = ctypes.c_uint64
     L.ofspmm_fwd_variant.argtypes = [i64, i64, i64, i32]
     L.ofspmm_fwd_variant.restype = ctypes.c_char_p
+    opts_p = ctypes.POINTER(OptsStruct)
+    L.ofspmm_variant_name.argtypes = [i32, i64, i64, i64, i32]
+    L.ofspmm_variant_name.restype = ctypes.c_char_p
+    L.ofspmm_fwd_ex_workspace_bytes.argtypes = [i64, i64, i64, i64, i32, i32]
+    L.ofspmm_fwd_ex_workspace_bytes.restype = sz
+    L.ofspmm_fwd_ex.argtypes = [csr_p, vp, i64, vp, i64, i64, i32, opts_p, vp, sz, vp]
+    L.ofspmm_fwd_ex.restype = i32
+    L.ofspmm_plan_bytes.argtypes = [i64, i64, i64, i32, i32]
+    L.ofspmm_plan_bytes.restype = sz
+    L.ofspmm_plan_build.argtypes = [vp, i32, i64, i64, i64, i32, i32, vp, sz, vp]
+    L.ofspmm_plan_build.restype = i32
+    L.ofspmm_choose_variant.argtypes = [ctypes.POINTER(ctypes.c_int64), i64, i64, i64, i32]
+    L.ofspmm_choose_variant.restype = i32
+    L.ofspmm_bwd_b_cached_workspace_bytes.argtypes = [i64, i64, i64, i64, i32, i32]
+    L.ofspmm_bwd_b_cached_workspace_bytes.restype = sz
+    L.ofspmm_bwd_b_cached.argtypes = [csr_p, vp, vp, vp, vp, vp, i64, i32, opts_p, vp, sz, vp]
+    L.ofspmm_bwd_b_cached.restype = i32
+    L.ofspmm_sddmm_ex.argtypes = [csr_p, vp, vp, vp, i64, i32, opts_p, vp, sz, vp]
+    L.ofspmm_sddmm_ex.restype = i32
+    L.ofspmm_gather_rows.argtypes = [vp, i64, vp, i64, vp, i32, i64, i64, i64, i32, i32, vp]
+    L.ofspmm_gather_rows.restype = i32
+    L.ofspmm_scatter_add_rows.argtypes = [vp, i64, vp, i64, vp, i32, i64, i64, i64, i32, i32, vp]
+    L.ofspmm_scatter_add_rows.restype = i32
     _LIB = L
     return L
 

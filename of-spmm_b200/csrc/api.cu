@@ -1,6 +1,7 @@
 // api.cu — the extern "C" boundary declared in include/ofspmm.h: argument validation, workspace
 // carving and dispatch to the per-op launchers.  Nothing here allocates device memory or
 // synchronises; every entry point is re-entrant.
+#include <stdio.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -22,11 +23,12 @@ int get_dev_info(DevInfo* out) {
   return OFSPMM_OK;
 }
 
-FwdWorkspace fwd_workspace_layout(int64_t rows, int64_t nnz, int64_t n, int dense_dtype) {
+FwdWorkspace fwd_workspace_layout(int64_t rows, int64_t nnz, int64_t n, int dense_dtype, int items) {
   FwdWorkspace L;
-  const size_t P = static_cast<size_t>(num_tasks(rows, nnz));
-  L.part_off = 0;
-  L.carry_off = align_up((P + 1) * sizeof(int2), 256);
+  const size_t P = static_cast<size_t>(num_tasks(rows, nnz, items));
+  L.counter_off = 0;  // task counter of the dynamic order (zeroed by a memset node before the launch)
+  L.part_off = 256;
+  L.carry_off = L.part_off + align_up((P + 1) * sizeof(int2), 256);
   const size_t rowbuf = align_up(P * static_cast<size_t>(n) * sizeof(float), 256);
   L.head_off = L.carry_off + rowbuf;
   L.total = L.head_off + (dense_dtype == OFSPMM_DTYPE_FLOAT ? 0 : rowbuf);
@@ -65,24 +67,62 @@ int check_ws(const void* ws, size_t have, size_t need) {
   return OFSPMM_OK;
 }
 
-// C = A·B through the merge-path kernels; shared by ofspmm_fwd and route (1) of ofspmm_bwd_b.
+// Forward workspace of a call that leaves the variant to the library (AUTO).
+size_t fwd_ws_auto(int64_t rows, int64_t nnz, int64_t n, int dense_dtype) {
+  return fwd_workspace_layout(rows, nnz, n, dense_dtype,
+                              resolve_variant(OFSPMM_VARIANT_AUTO, rows, nnz, n, dense_dtype).items).total;
+}
+
+size_t plan_bytes_for(int64_t rows, int64_t nnz, int items) {
+  return align_up((static_cast<size_t>(num_tasks(rows, nnz, items)) + 1) * sizeof(int2), 256);
+}
+
+// Options of one call -> launch description.  `opts` may be NULL (all defaults).
+FwdLaunch make_launch(const ofspmm_opts* opts, int64_t rows, int64_t nnz, int64_t n, int dense_dtype) {
+  FwdLaunch L;
+  L.variant = resolve_variant(opts ? opts->variant : OFSPMM_VARIANT_AUTO, rows, nnz, n, dense_dtype);
+  L.tasks_per_warp = opts && opts->tasks_per_warp > 0 ? opts->tasks_per_warp : 0;
+  const uint32_t fl = opts ? opts->flags : 0u;
+  // task order: dynamic (drawn from a counter) unless the caller pins the static interleave
+  L.dynamic = OFSPMM_DEFAULT_DYNAMIC_ORDER ? (fl & OFSPMM_ORDER_STATIC) == 0 : (fl & OFSPMM_ORDER_DYNAMIC) != 0;
+  L.flags = fl & (OFSPMM_FWD_ACCUMULATE | OFSPMM_FWD_BIAS | OFSPMM_FWD_RELU);
+  L.bias = opts ? opts->bias : nullptr;
+  return L;
+}
+
+// C = A·B through the merge-path kernels; shared by every forward-shaped entry point.
 int run_fwd(const ofspmm_csr* A, const void* B, int64_t ldb, void* C, int64_t ldc, int64_t n,
-            int dense_dtype, void* ws, size_t ws_bytes, cudaStream_t stream) {
+            int dense_dtype, const ofspmm_opts* opts, void* ws, size_t ws_bytes, cudaStream_t stream) {
   if (A->rows == 0 || n == 0) return OFSPMM_OK;
   if (ldb < n || ldc < n || ldb >= (int64_t{1} << 30)) return OFSPMM_ERR_INVALID_ARG;
+  FwdLaunch L = make_launch(opts, A->rows, A->nnz, n, dense_dtype);
+  if ((L.flags & OFSPMM_FWD_BIAS) && L.bias == nullptr) return OFSPMM_ERR_INVALID_ARG;
   if (A->nnz == 0 || A->cols == 0) {
-    OFSPMM_CUDA_OK(cudaMemset2DAsync(C, static_cast<size_t>(ldc) * dense_size(dense_dtype), 0,
-                                     static_cast<size_t>(n) * dense_size(dense_dtype),
-                                     static_cast<size_t>(A->rows), stream));
-    return OFSPMM_OK;
+    if (L.flags == OFSPMM_FWD_ACCUMULATE) return OFSPMM_OK;  // C += 0
+    if (L.flags == 0) {
+      OFSPMM_CUDA_OK(cudaMemset2DAsync(C, static_cast<size_t>(ldc) * dense_size(dense_dtype), 0,
+                                       static_cast<size_t>(n) * dense_size(dense_dtype),
+                                       static_cast<size_t>(A->rows), stream));
+      return OFSPMM_OK;
+    }
+    // bias / relu of an all-zero product: run the kernels on the (empty) rows; needs a valid crow
+    if (A->nnz != 0) return OFSPMM_ERR_INVALID_ARG;
   }
-  const FwdWorkspace L = fwd_workspace_layout(A->rows, A->nnz, n, dense_dtype);
-  if (int rc = check_ws(ws, ws_bytes, L.total)) return rc;
+  const FwdWorkspace W = fwd_workspace_layout(A->rows, A->nnz, n, dense_dtype, L.variant.items);
+  if (int rc = check_ws(ws, ws_bytes, W.total)) return rc;
   unsigned char* w = static_cast<unsigned char*>(ws);
-  const int64_t P = num_tasks(A->rows, A->nnz);
-  if (int rc = launch_task_partition(A->crow, A->idx_dtype, A->rows, A->nnz, P, w + L.part_off, stream)) return rc;
-  return launch_fwd(A, B, ldb, C, ldc, n, dense_dtype, w + L.part_off, reinterpret_cast<float*>(w + L.carry_off),
-                    reinterpret_cast<float*>(w + L.head_off), P, stream);
+  const int64_t P = num_tasks(A->rows, A->nnz, L.variant.items);
+  const void* part = w + W.part_off;
+  if (opts != nullptr && opts->plan != nullptr) {
+    // a plan built for another task size is a caller bug, not something to paper over
+    if (opts->plan_bytes != plan_bytes_for(A->rows, A->nnz, L.variant.items)) return OFSPMM_ERR_INVALID_ARG;
+    part = opts->plan;
+  } else if (int rc = launch_task_partition(A->crow, A->idx_dtype, A->rows, A->nnz, P, L.variant.items,
+                                            w + W.part_off, stream)) {
+    return rc;
+  }
+  return launch_fwd(A, B, ldb, C, ldc, n, dense_dtype, part, reinterpret_cast<float*>(w + W.carry_off),
+                    reinterpret_cast<float*>(w + W.head_off), w + W.counter_off, P, L, stream);
 }
 
 }  // namespace
@@ -93,9 +133,68 @@ using namespace ofspmm;
 extern "C" {
 
 size_t ofspmm_fwd_workspace_bytes(int64_t rows, int64_t cols, int64_t nnz, int64_t n, int dense_dtype) {
+  return ofspmm_fwd_ex_workspace_bytes(rows, cols, nnz, n, dense_dtype, OFSPMM_VARIANT_AUTO);
+}
+
+size_t ofspmm_fwd_ex_workspace_bytes(int64_t rows, int64_t cols, int64_t nnz, int64_t n, int dense_dtype,
+                                     int variant) {
   (void)cols;
   if (rows < 0 || nnz < 0 || n < 0) return 0;
-  return fwd_workspace_layout(rows, nnz, n, dense_dtype).total;
+  return fwd_workspace_layout(rows, nnz, n, dense_dtype, resolve_variant(variant, rows, nnz, n, dense_dtype).items).total;
+}
+
+int ofspmm_fwd_ex(const ofspmm_csr* A, const void* B, int64_t ldb, void* C, int64_t ldc, int64_t n,
+                  int dense_dtype, const ofspmm_opts* opts, void* workspace, size_t workspace_bytes,
+                  ofspmm_stream_t stream) {
+  if (int rc = check_csr(A, true)) return rc;
+  if (int rc = check_dtypes(A, dense_dtype)) return rc;
+  if (n < 0 || n >= (int64_t{1} << 31)) return OFSPMM_ERR_INVALID_ARG;
+  if (A->rows > 0 && n > 0 && (C == nullptr || (A->nnz > 0 && A->cols > 0 && B == nullptr))) return OFSPMM_ERR_INVALID_ARG;
+  return run_fwd(A, B, ldb, C, ldc, n, dense_dtype, opts, workspace, workspace_bytes, reinterpret_cast<cudaStream_t>(stream));
+}
+
+size_t ofspmm_plan_bytes(int64_t rows, int64_t nnz, int64_t n, int dense_dtype, int variant) {
+  if (rows < 0 || nnz < 0) return 0;
+  return plan_bytes_for(rows, nnz, resolve_variant(variant, rows, nnz, n, dense_dtype).items);
+}
+
+int ofspmm_plan_build(const void* crow, int idx_dtype, int64_t rows, int64_t nnz, int64_t n, int dense_dtype,
+                      int variant, void* plan, size_t plan_bytes, ofspmm_stream_t stream) {
+  if (crow == nullptr || plan == nullptr || rows < 0 || nnz < 0) return OFSPMM_ERR_INVALID_ARG;
+  if (!idx_ok(idx_dtype)) return OFSPMM_ERR_UNSUPPORTED_DTYPE;
+  if (rows >= (int64_t{1} << 31) - 1 || nnz >= (int64_t{1} << 31) - 1) return OFSPMM_ERR_TOO_LARGE;
+  const int items = resolve_variant(variant, rows, nnz, n, dense_dtype).items;
+  if (plan_bytes < plan_bytes_for(rows, nnz, items) || (reinterpret_cast<uintptr_t>(plan) & 15)) return OFSPMM_ERR_WORKSPACE;
+  return launch_task_partition(crow, idx_dtype, rows, nnz, num_tasks(rows, nnz, items), items, plan,
+                               reinterpret_cast<cudaStream_t>(stream));
+}
+
+int ofspmm_choose_variant(const int64_t* hist32_host, int64_t rows, int64_t nnz, int64_t n, int dense_dtype) {
+  FwdVariant v = resolve_variant(OFSPMM_VARIANT_AUTO, rows, nnz, n, dense_dtype);
+  if (hist32_host == nullptr || rows <= 0 || nnz <= 0 || v.items == kSmallTaskItems) return encode_variant(v);
+  // nnz-weighted view of the log2 histogram: bucket b holds rows of 2^(b-1) <= len < 2^b, which
+  // carry about count * 0.75 * 2^b non-zeros.
+  double w_total = 0, w_long = 0, w_short = 0;
+  const int64_t vecw = dense_dtype == OFSPMM_DTYPE_BFLOAT16 ? 8 : 4;
+  const int64_t lanes = n % vecw == 0 ? n / vecw : 32;       // lanes per dense row
+  const int64_t groups = lanes <= 8 ? 4 : (lanes <= 16 ? 2 : 1);  // non-zero groups per warp instruction
+  for (int b = 1; b < 32; ++b) {
+    const double w = static_cast<double>(hist32_host[b]) * 0.75 * static_cast<double>(int64_t{1} << b);
+    w_total += w;
+    if (b >= 8) w_long += w;                                  // rows of >= 128 non-zeros
+    if ((int64_t{1} << b) <= 4 * groups) w_short += w;        // rows that fit one 4-slot chunk per group
+  }
+  v.unroll8 = false;
+  v.row_parallel = false;
+  if (w_total > 0) {
+    // eight gathers in flight pay once most non-zeros sit in long rows (few edge chunks per row)
+    if (w_long >= 0.5 * w_total) v.unroll8 = true;
+    // row-parallel lanes pay when the groups of a narrow dense row would mostly idle: most
+    // non-zeros in rows too short to feed every group a full chunk
+    else if (groups > 1 && w_short >= 0.5 * w_total) v.row_parallel = true;
+  }
+  // resolve again so unsupported widths fall back exactly as the launch would
+  return encode_variant(resolve_variant(encode_variant(v), rows, nnz, n, dense_dtype));
 }
 
 int ofspmm_fwd(const ofspmm_csr* A, const void* B, void* C, int64_t n, int dense_dtype, void* workspace,
@@ -104,7 +203,7 @@ int ofspmm_fwd(const ofspmm_csr* A, const void* B, void* C, int64_t n, int dense
   if (int rc = check_dtypes(A, dense_dtype)) return rc;
   if (n < 0 || n >= (int64_t{1} << 31)) return OFSPMM_ERR_INVALID_ARG;
   if (A->rows > 0 && n > 0 && (C == nullptr || (A->nnz > 0 && A->cols > 0 && B == nullptr))) return OFSPMM_ERR_INVALID_ARG;
-  return run_fwd(A, B, n, C, n, n, dense_dtype, workspace, workspace_bytes, reinterpret_cast<cudaStream_t>(stream));
+  return run_fwd(A, B, n, C, n, n, dense_dtype, nullptr, workspace, workspace_bytes, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int ofspmm_fwd_strided(const ofspmm_csr* A, const void* B, int64_t ldb, void* C, int64_t ldc, int64_t n,
@@ -113,14 +212,14 @@ int ofspmm_fwd_strided(const ofspmm_csr* A, const void* B, int64_t ldb, void* C,
   if (int rc = check_dtypes(A, dense_dtype)) return rc;
   if (n < 0 || n >= (int64_t{1} << 31)) return OFSPMM_ERR_INVALID_ARG;
   if (A->rows > 0 && n > 0 && (C == nullptr || (A->nnz > 0 && A->cols > 0 && B == nullptr))) return OFSPMM_ERR_INVALID_ARG;
-  return run_fwd(A, B, ldb, C, ldc, n, dense_dtype, workspace, workspace_bytes, reinterpret_cast<cudaStream_t>(stream));
+  return run_fwd(A, B, ldb, C, ldc, n, dense_dtype, nullptr, workspace, workspace_bytes, reinterpret_cast<cudaStream_t>(stream));
 }
 
 size_t ofspmm_bwd_b_workspace_bytes(int64_t rows, int64_t cols, int64_t nnz, int64_t n, int dense_dtype,
                                     int have_transpose) {
   if (rows < 0 || cols < 0 || nnz < 0 || n < 0) return 0;
-  if (have_transpose) return fwd_workspace_layout(cols, nnz, n, dense_dtype).total;
-  size_t total = align_up((static_cast<size_t>(num_tasks(rows, nnz)) + 1) * sizeof(int2), 256);
+  if (have_transpose) return fwd_ws_auto(cols, nnz, n, dense_dtype);
+  size_t total = plan_bytes_for(rows, nnz, kTaskItems);
   if (dense_dtype != OFSPMM_DTYPE_FLOAT) total += align_up(static_cast<size_t>(cols) * n * sizeof(float), 256);
   return total;
 }
@@ -137,7 +236,7 @@ int ofspmm_bwd_b(const ofspmm_csr* A, const ofspmm_csr* At, const void* dY, void
     if (int rc = check_csr(At, true)) return rc;
     if (At->rows != A->cols || At->cols != A->rows || At->nnz != A->nnz) return OFSPMM_ERR_INVALID_ARG;
     if (int rc = check_dtypes(At, dense_dtype)) return rc;
-    return run_fwd(At, dY, n, dB, n, n, dense_dtype, workspace, workspace_bytes, stream);
+    return run_fwd(At, dY, n, dB, n, n, dense_dtype, nullptr, workspace, workspace_bytes, stream);
   }
   // route (2): vector-atomic scatter into an fp32 accumulator
   const size_t out_elems = static_cast<size_t>(A->cols) * static_cast<size_t>(n);
@@ -150,7 +249,7 @@ int ofspmm_bwd_b(const ofspmm_csr* A, const ofspmm_csr* At, const void* dY, void
   unsigned char* w = static_cast<unsigned char*>(workspace);
   const int64_t P = num_tasks(A->rows, A->nnz);
   const size_t part_bytes = align_up((static_cast<size_t>(P) + 1) * sizeof(int2), 256);
-  if (int rc = launch_task_partition(A->crow, A->idx_dtype, A->rows, A->nnz, P, w, stream)) return rc;
+  if (int rc = launch_task_partition(A->crow, A->idx_dtype, A->rows, A->nnz, P, kTaskItems, w, stream)) return rc;
   if (dense_dtype == OFSPMM_DTYPE_FLOAT)
     return launch_bwd_atomic(A, dY, static_cast<float*>(dB), nullptr, n, dense_dtype, w, P, stream);
   return launch_bwd_atomic(A, dY, reinterpret_cast<float*>(w + part_bytes), dB, n, dense_dtype, w, P, stream);
@@ -171,7 +270,7 @@ TransientLayout transient_layout(int64_t rows, int64_t cols, int64_t nnz, int64_
   L.t_val = off;  off += align_up(static_cast<size_t>(nnz > 0 ? nnz : 1) * vs, 256);
   L.tws = off;    L.tws_bytes = transpose_workspace_bytes(rows, cols, nnz, idx_dtype);
   off += align_up(L.tws_bytes, 256);
-  L.fws = off;    off += fwd_workspace_layout(cols, nnz, n, dense_dtype).total;
+  L.fws = off;    off += fwd_ws_auto(cols, nnz, n, dense_dtype);
   L.total = off;
   return L;
 }
@@ -205,17 +304,76 @@ int ofspmm_bwd_b_transient(const ofspmm_csr* A, const void* dY, void* dB, int64_
   At.crow = w + L.t_crow;
   At.col = w + L.t_col;
   At.val = w + L.t_val;
-  return run_fwd(&At, dY, n, dB, n, n, dense_dtype, w + L.fws, workspace_bytes - L.fws, stream);
+  return run_fwd(&At, dY, n, dB, n, n, dense_dtype, nullptr, w + L.fws, workspace_bytes - L.fws, stream);
+}
+
+size_t ofspmm_bwd_b_cached_workspace_bytes(int64_t rows, int64_t cols, int64_t nnz, int64_t n, int dense_dtype,
+                                          int val_dtype) {
+  if (rows < 0 || cols < 0 || nnz < 0 || n < 0) return 0;
+  const size_t vs = val_dtype == OFSPMM_DTYPE_FLOAT ? 4 : 2;
+  return align_up(static_cast<size_t>(nnz > 0 ? nnz : 1) * vs, 256) + fwd_ws_auto(cols, nnz, n, dense_dtype);
+}
+
+int ofspmm_bwd_b_cached(const ofspmm_csr* A, const void* t_crow, const void* t_col, const void* t_perm,
+                        const void* dY, void* dB, int64_t n, int dense_dtype, const ofspmm_opts* opts,
+                        void* workspace, size_t workspace_bytes, ofspmm_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (int rc = check_csr(A, true)) return rc;
+  if (int rc = check_dtypes(A, dense_dtype)) return rc;
+  if (n < 0 || n >= (int64_t{1} << 31)) return OFSPMM_ERR_INVALID_ARG;
+  if (A->cols == 0 || n == 0) return OFSPMM_OK;
+  if (dB == nullptr || t_crow == nullptr || (A->nnz > 0 && (dY == nullptr || t_col == nullptr || t_perm == nullptr)))
+    return OFSPMM_ERR_INVALID_ARG;
+  const size_t vs = A->val_dtype == OFSPMM_DTYPE_FLOAT ? 4 : 2;
+  const size_t tv_bytes = align_up(static_cast<size_t>(A->nnz > 0 ? A->nnz : 1) * vs, 256);
+  const size_t need = ofspmm_bwd_b_cached_workspace_bytes(A->rows, A->cols, A->nnz, n, dense_dtype, A->val_dtype);
+  if (int rc = check_ws(workspace, workspace_bytes, need)) return rc;
+  unsigned char* w = static_cast<unsigned char*>(workspace);
+  // the STRUCTURE of A^T is cached by the caller; the values are re-gathered from A on every call,
+  // so in-place updates of a_val (learnable edge weights) are always seen
+  if (int rc = launch_gather_vals(A->val, A->val_dtype, t_perm, A->idx_dtype, A->nnz, w, stream)) return rc;
+  ofspmm_csr At = *A;
+  At.rows = A->cols;
+  At.cols = A->rows;
+  At.crow = t_crow;
+  At.col = t_col;
+  At.val = w;
+  return run_fwd(&At, dY, n, dB, n, n, dense_dtype, opts, w + tv_bytes, workspace_bytes - tv_bytes, stream);
+}
+
+int ofspmm_gather_rows(void* dst, int64_t ld_dst, const void* src, int64_t ld_src, const void* list, int idx_dtype,
+                       int64_t idx_offset, int64_t count, int64_t n, int dense_dtype, int max_ctas,
+                       ofspmm_stream_t stream) {
+  if (count < 0 || n < 0 || ld_dst < n || ld_src < n) return OFSPMM_ERR_INVALID_ARG;
+  if (count > 0 && n > 0 && (dst == nullptr || src == nullptr)) return OFSPMM_ERR_INVALID_ARG;
+  if (list != nullptr && !idx_ok(idx_dtype)) return OFSPMM_ERR_UNSUPPORTED_DTYPE;
+  return launch_gather_rows(dst, ld_dst, src, ld_src, list, list ? idx_dtype : OFSPMM_DTYPE_INT32, idx_offset, count, n,
+                            dense_dtype, max_ctas, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int ofspmm_scatter_add_rows(void* dst, int64_t ld_dst, const void* src, int64_t ld_src, const void* list,
+                            int idx_dtype, int64_t idx_offset, int64_t count, int64_t n, int dense_dtype,
+                            int max_ctas, ofspmm_stream_t stream) {
+  if (count < 0 || n < 0 || ld_dst < n || ld_src < n) return OFSPMM_ERR_INVALID_ARG;
+  if (count > 0 && n > 0 && (dst == nullptr || src == nullptr)) return OFSPMM_ERR_INVALID_ARG;
+  if (list != nullptr && !idx_ok(idx_dtype)) return OFSPMM_ERR_UNSUPPORTED_DTYPE;
+  return launch_scatter_add_rows(dst, ld_dst, src, ld_src, list, list ? idx_dtype : OFSPMM_DTYPE_INT32, idx_offset, count,
+                                 n, dense_dtype, max_ctas, reinterpret_cast<cudaStream_t>(stream));
 }
 
 size_t ofspmm_sddmm_workspace_bytes(int64_t rows, int64_t cols, int64_t nnz, int64_t n, int dense_dtype) {
   (void)cols; (void)n; (void)dense_dtype;
   if (rows < 0 || nnz < 0) return 0;
-  return align_up((static_cast<size_t>(num_tasks(rows, nnz)) + 1) * sizeof(int2), 256);
+  return plan_bytes_for(rows, nnz, kTaskItems);
 }
 
 int ofspmm_sddmm(const ofspmm_csr* A, const void* dY, const void* B, void* dval, int64_t n, int dense_dtype,
                  void* workspace, size_t workspace_bytes, ofspmm_stream_t stream_) {
+  return ofspmm_sddmm_ex(A, dY, B, dval, n, dense_dtype, nullptr, workspace, workspace_bytes, stream_);
+}
+
+int ofspmm_sddmm_ex(const ofspmm_csr* A, const void* dY, const void* B, void* dval, int64_t n, int dense_dtype,
+                    const ofspmm_opts* opts, void* workspace, size_t workspace_bytes, ofspmm_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (int rc = check_csr(A, false)) return rc;
   if (int rc = check_dtypes(A, dense_dtype)) return rc;
@@ -228,10 +386,13 @@ int ofspmm_sddmm(const ofspmm_csr* A, const void* dY, const void* B, void* dval,
     return OFSPMM_OK;
   }
   if (dY == nullptr || B == nullptr) return OFSPMM_ERR_INVALID_ARG;
+  const int64_t P = num_tasks(A->rows, A->nnz);
+  // the SDDMM kernels use 256-item tasks: a plan of that task size is taken as is
+  if (opts != nullptr && opts->plan != nullptr && opts->plan_bytes == plan_bytes_for(A->rows, A->nnz, kTaskItems))
+    return launch_sddmm(A, dY, B, dval, n, dense_dtype, opts->plan, P, stream);
   const size_t need = ofspmm_sddmm_workspace_bytes(A->rows, A->cols, A->nnz, n, dense_dtype);
   if (int rc = check_ws(workspace, workspace_bytes, need)) return rc;
-  const int64_t P = num_tasks(A->rows, A->nnz);
-  if (int rc = launch_task_partition(A->crow, A->idx_dtype, A->rows, A->nnz, P, workspace, stream)) return rc;
+  if (int rc = launch_task_partition(A->crow, A->idx_dtype, A->rows, A->nnz, P, kTaskItems, workspace, stream)) return rc;
   return launch_sddmm(A, dY, B, dval, n, dense_dtype, workspace, P, stream);
 }
 
@@ -292,7 +453,7 @@ size_t ofspmm_fwd_host_workspace_bytes(int64_t rows, int64_t cols, int64_t nnz, 
   total += align_up(static_cast<size_t>(nnz) * vs, 256);
   total += align_up(static_cast<size_t>(cols) * n * dense_size(dense_dtype), 256);
   total += align_up(static_cast<size_t>(rows) * n * dense_size(dense_dtype), 256);
-  total += fwd_workspace_layout(rows, nnz, n, dense_dtype).total;
+  total += fwd_ws_auto(rows, nnz, n, dense_dtype);
   return total;
 }
 
@@ -328,7 +489,7 @@ int ofspmm_fwd_host(const ofspmm_csr* Ah, const void* B_host, void* C_host, int6
   Ad.crow = d_crow;
   Ad.col = d_col;
   Ad.val = d_val;
-  if (int rc = run_fwd(&Ad, d_B, n, d_C, n, n, dense_dtype, w + off, workspace_bytes - off, stream)) return rc;
+  if (int rc = run_fwd(&Ad, d_B, n, d_C, n, n, dense_dtype, nullptr, w + off, workspace_bytes - off, stream)) return rc;
   OFSPMM_CUDA_OK(cudaMemcpyAsync(C_host, d_C, static_cast<size_t>(Ah->rows) * n * ds, cudaMemcpyDeviceToHost, stream));
   return OFSPMM_OK;
 }
@@ -351,8 +512,19 @@ int ofspmm_version(void) { return 100; }
 uint64_t ofspmm_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 const char* ofspmm_fwd_variant(int64_t rows, int64_t nnz, int64_t n, int dense_dtype) {
-  (void)rows; (void)nnz;
-  return fwd_variant_name(n, dense_dtype, true);
+  return ofspmm_variant_name(OFSPMM_VARIANT_AUTO, rows, nnz, n, dense_dtype);
+}
+
+const char* ofspmm_variant_name(int variant, int64_t rows, int64_t nnz, int64_t n, int dense_dtype) {
+  // "<schedule family>/<lane layout>": family from the variant, layout from the dense width
+  static thread_local char buf[160];
+  const FwdVariant v = resolve_variant(variant, rows, nnz, n, dense_dtype);
+  const char* fam = v.items == kSmallTaskItems ? "merge_path(64-item tasks)"
+                    : v.row_parallel           ? "merge_path(256-item tasks, row-parallel groups)"
+                    : v.unroll8                ? "merge_path(256-item tasks, 8 gathers in flight)"
+                                               : "merge_path(256-item tasks)";
+  snprintf(buf, sizeof(buf), "%s/%s", fam, fwd_variant_name(n, dense_dtype, true));
+  return buf;
 }
 
 }  // extern "C"

@@ -1,0 +1,245 @@
+// exchange.cu — row-exchange kernels of the multi-GPU path and the value re-gather
+// of the cached-transpose backward.
+//
+// In the needed-rows exchange every rank keeps its shard of the dense operand in symmetric (peer
+// mapped) memory; a rank PULLS exactly the B rows its row block touches straight out of the
+// owners' HBM over NVLink / NVSwitch with ordinary 16-byte loads on the peer pointer
+// (gather_rows_kernel, `src` = peer address), and the dual for A^T·dY: the owner of a dB shard
+// pulls the peers' partial rows and adds them in rank order (scatter_add_rows_kernel; the rows of
+// one list are distinct, so no atomics and a fixed summation order).  The reference instead
+// materialises the whole operand on every rank with a blocking all-gather before the op is even
+// issued (oneflow/core/boxing/ccl_boxing_function.cpp:105-124,183-197).
+//
+// Peer loads see ~2 us of latency: each thread keeps UNROLL independent 16-byte units in flight,
+// and the grid is capped (`max_ctas`) so the copy shares the GPU with the SpMM kernel it overlaps.
+#include "common.cuh"
+#include "internal.h"
+
+namespace ofspmm {
+
+namespace {
+
+constexpr int kThreads = 512;
+constexpr int kUnroll = 4;
+
+__device__ __forceinline__ uint4 ld_peer16(const void* p) {
+  // plain (coherent) load: the source may live in a peer GPU's memory and is rewritten every step
+  uint4 v;
+  asm volatile("ld.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+
+template <typename IdxT>
+__device__ __forceinline__ long long list_at(const IdxT* list, long long i, long long off) {
+  return list == nullptr ? i : static_cast<long long>(list[i]) - off;
+}
+
+// dst[i, :] = src[list[i] - off, :]; rows are `units` 16-byte units wide.
+template <typename IdxT>
+__global__ void __launch_bounds__(kThreads) gather_rows_kernel(
+    char* __restrict__ dst, long long dst_stride, const char* __restrict__ src, long long src_stride,
+    const IdxT* __restrict__ list, long long off, long long count, int units) {
+  const long long total = count * units;
+  const long long stride = static_cast<long long>(gridDim.x) * kThreads;
+  long long u = static_cast<long long>(blockIdx.x) * kThreads + threadIdx.x;
+  for (; u + (kUnroll - 1) * stride < total; u += kUnroll * stride) {
+    uint4 v[kUnroll];
+    long long drow[kUnroll];
+    int c[kUnroll];
+#pragma unroll
+    for (int k = 0; k < kUnroll; ++k) {
+      const long long uu = u + k * stride;
+      drow[k] = uu / units;
+      c[k] = static_cast<int>(uu - drow[k] * units);
+      v[k] = ld_peer16(src + list_at(list, drow[k], off) * src_stride + c[k] * 16);
+    }
+#pragma unroll
+    for (int k = 0; k < kUnroll; ++k)
+      *reinterpret_cast<uint4*>(dst + drow[k] * dst_stride + c[k] * 16) = v[k];
+  }
+  for (; u < total; u += stride) {
+    const long long r = u / units;
+    const int c = static_cast<int>(u - r * units);
+    *reinterpret_cast<uint4*>(dst + r * dst_stride + c * 16) = ld_peer16(src + list_at(list, r, off) * src_stride + c * 16);
+  }
+}
+
+// element-wise fallback for rows that are not a whole number of aligned 16-byte units
+template <typename IdxT, typename DT>
+__global__ void gather_rows_scalar_kernel(DT* __restrict__ dst, long long ld_dst, const DT* __restrict__ src,
+                                          long long ld_src, const IdxT* __restrict__ list, long long off,
+                                          long long count, int n) {
+  const long long total = count * n;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long u = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; u < total; u += stride) {
+    const long long r = u / n;
+    const int c = static_cast<int>(u - r * n);
+    dst[r * ld_dst + c] = *static_cast<const volatile DT*>(src + list_at(list, r, off) * ld_src + c);
+  }
+}
+
+__device__ __forceinline__ uint4 add16(uint4 a, uint4 b, float) {
+  a.x = __float_as_uint(__uint_as_float(a.x) + __uint_as_float(b.x));
+  a.y = __float_as_uint(__uint_as_float(a.y) + __uint_as_float(b.y));
+  a.z = __float_as_uint(__uint_as_float(a.z) + __uint_as_float(b.z));
+  a.w = __float_as_uint(__uint_as_float(a.w) + __uint_as_float(b.w));
+  return a;
+}
+__device__ __forceinline__ uint32_t add_bf16x2(uint32_t a, uint32_t b) {
+  const float lo = __uint_as_float(a << 16) + __uint_as_float(b << 16);
+  const float hi = __uint_as_float(a & 0xffff0000u) + __uint_as_float(b & 0xffff0000u);
+  const __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+__device__ __forceinline__ uint4 add16(uint4 a, uint4 b, __nv_bfloat16) {
+  a.x = add_bf16x2(a.x, b.x);
+  a.y = add_bf16x2(a.y, b.y);
+  a.z = add_bf16x2(a.z, b.z);
+  a.w = add_bf16x2(a.w, b.w);
+  return a;
+}
+
+// dst[list[i] - off, :] += src[i, :]; the entries of `list` are distinct.
+template <typename IdxT, typename DT>
+__global__ void __launch_bounds__(kThreads) scatter_add_rows_kernel(
+    char* __restrict__ dst, long long dst_stride, const char* __restrict__ src, long long src_stride,
+    const IdxT* __restrict__ list, long long off, long long count, int units) {
+  const long long total = count * units;
+  const long long stride = static_cast<long long>(gridDim.x) * kThreads;
+  long long u = static_cast<long long>(blockIdx.x) * kThreads + threadIdx.x;
+  for (; u + (kUnroll - 1) * stride < total; u += kUnroll * stride) {
+    uint4 v[kUnroll];
+    char* d[kUnroll];
+#pragma unroll
+    for (int k = 0; k < kUnroll; ++k) {
+      const long long uu = u + k * stride;
+      const long long r = uu / units;
+      const int c = static_cast<int>(uu - r * units);
+      v[k] = ld_peer16(src + r * src_stride + c * 16);
+      d[k] = dst + list_at(list, r, off) * dst_stride + c * 16;
+    }
+#pragma unroll
+    for (int k = 0; k < kUnroll; ++k) {
+      uint4* dp = reinterpret_cast<uint4*>(d[k]);
+      *dp = add16(*dp, v[k], DT{});
+    }
+  }
+  for (; u < total; u += stride) {
+    const long long r = u / units;
+    const int c = static_cast<int>(u - r * units);
+    uint4* dp = reinterpret_cast<uint4*>(dst + list_at(list, r, off) * dst_stride + c * 16);
+    *dp = add16(*dp, ld_peer16(src + r * src_stride + c * 16), DT{});
+  }
+}
+
+template <typename IdxT, typename DT>
+__global__ void scatter_add_rows_scalar_kernel(DT* __restrict__ dst, long long ld_dst, const DT* __restrict__ src,
+                                               long long ld_src, const IdxT* __restrict__ list, long long off,
+                                               long long count, int n) {
+  const long long total = count * n;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long u = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; u < total; u += stride) {
+    const long long r = u / n;
+    const int c = static_cast<int>(u - r * n);
+    DT* dp = dst + list_at(list, r, off) * ld_dst + c;
+    *dp = from_float<DT>(to_float(*dp) + to_float(*static_cast<const volatile DT*>(src + r * ld_src + c)));
+  }
+}
+
+template <typename IdxT, typename ValT>
+__global__ void gather_vals_kernel(const ValT* __restrict__ val, const IdxT* __restrict__ perm, long long nnz,
+                                   ValT* __restrict__ out) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long q = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; q < nnz; q += stride)
+    out[q] = val[perm[q]];
+}
+
+int grid_for(long long work_items, int threads, int max_ctas, int sms) {
+  long long g = (work_items + threads - 1) / threads;
+  const long long cap = max_ctas > 0 ? max_ctas : static_cast<long long>(sms) * 4;
+  if (g > cap) g = cap;
+  return g < 1 ? 1 : static_cast<int>(g);
+}
+
+template <typename IdxT, typename DT>
+int rows_impl(bool add, void* dst, int64_t ld_dst, const void* src, int64_t ld_src, const void* list,
+              int64_t off, int64_t count, int64_t n, int max_ctas, cudaStream_t stream) {
+  DevInfo dev;
+  if (int rc = get_dev_info(&dev)) return rc;
+  const bool vec = (n * sizeof(DT)) % 16 == 0 && (ld_dst * sizeof(DT)) % 16 == 0 && (ld_src * sizeof(DT)) % 16 == 0 &&
+                   ((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src)) & 15) == 0;
+  const IdxT* l = static_cast<const IdxT*>(list);
+  if (vec) {
+    const int units = static_cast<int>(n * sizeof(DT) / 16);
+    const int grid = grid_for((count * units + kUnroll - 1) / kUnroll, kThreads, max_ctas, dev.sms);
+    if (add)
+      scatter_add_rows_kernel<IdxT, DT><<<grid, kThreads, 0, stream>>>(
+          static_cast<char*>(dst), ld_dst * sizeof(DT), static_cast<const char*>(src), ld_src * sizeof(DT), l, off, count, units);
+    else
+      gather_rows_kernel<IdxT><<<grid, kThreads, 0, stream>>>(
+          static_cast<char*>(dst), ld_dst * sizeof(DT), static_cast<const char*>(src), ld_src * sizeof(DT), l, off, count, units);
+  } else {
+    const int grid = grid_for(count * n, 256, max_ctas, dev.sms);
+    if (add)
+      scatter_add_rows_scalar_kernel<IdxT, DT><<<grid, 256, 0, stream>>>(
+          static_cast<DT*>(dst), ld_dst, static_cast<const DT*>(src), ld_src, l, off, count, static_cast<int>(n));
+    else
+      gather_rows_scalar_kernel<IdxT, DT><<<grid, 256, 0, stream>>>(
+          static_cast<DT*>(dst), ld_dst, static_cast<const DT*>(src), ld_src, l, off, count, static_cast<int>(n));
+  }
+  count_launch();
+  OFSPMM_CUDA_OK(cudaGetLastError());
+  return OFSPMM_OK;
+}
+
+int rows_dispatch(bool add, void* dst, int64_t ld_dst, const void* src, int64_t ld_src, const void* list,
+                  int idx_dtype, int64_t off, int64_t count, int64_t n, int dense_dtype, int max_ctas,
+                  cudaStream_t stream) {
+  if (count == 0 || n == 0) return OFSPMM_OK;
+  const bool f32 = dense_dtype == OFSPMM_DTYPE_FLOAT;
+  if (!f32 && dense_dtype != OFSPMM_DTYPE_BFLOAT16) return OFSPMM_ERR_UNSUPPORTED_DTYPE;
+  if (idx_dtype == OFSPMM_DTYPE_INT32)
+    return f32 ? rows_impl<int32_t, float>(add, dst, ld_dst, src, ld_src, list, off, count, n, max_ctas, stream)
+               : rows_impl<int32_t, __nv_bfloat16>(add, dst, ld_dst, src, ld_src, list, off, count, n, max_ctas, stream);
+  if (idx_dtype == OFSPMM_DTYPE_INT64)
+    return f32 ? rows_impl<int64_t, float>(add, dst, ld_dst, src, ld_src, list, off, count, n, max_ctas, stream)
+               : rows_impl<int64_t, __nv_bfloat16>(add, dst, ld_dst, src, ld_src, list, off, count, n, max_ctas, stream);
+  return OFSPMM_ERR_UNSUPPORTED_DTYPE;
+}
+
+}  // namespace
+
+int launch_gather_rows(void* dst, int64_t ld_dst, const void* src, int64_t ld_src, const void* list,
+                       int idx_dtype, int64_t idx_offset, int64_t count, int64_t n, int dense_dtype,
+                       int max_ctas, cudaStream_t stream) {
+  return rows_dispatch(false, dst, ld_dst, src, ld_src, list, idx_dtype, idx_offset, count, n, dense_dtype, max_ctas, stream);
+}
+
+int launch_scatter_add_rows(void* dst, int64_t ld_dst, const void* src, int64_t ld_src, const void* list,
+                            int idx_dtype, int64_t idx_offset, int64_t count, int64_t n, int dense_dtype,
+                            int max_ctas, cudaStream_t stream) {
+  return rows_dispatch(true, dst, ld_dst, src, ld_src, list, idx_dtype, idx_offset, count, n, dense_dtype, max_ctas, stream);
+}
+
+int launch_gather_vals(const void* val, int val_dtype, const void* perm, int idx_dtype, int64_t nnz,
+                       void* out, cudaStream_t stream) {
+  if (nnz == 0) return OFSPMM_OK;
+  DevInfo dev;
+  if (int rc = get_dev_info(&dev)) return rc;
+  const int grid = grid_for(nnz, 256, dev.sms * 8, dev.sms);
+  const bool i32 = idx_dtype == OFSPMM_DTYPE_INT32;
+  if (val_dtype == OFSPMM_DTYPE_FLOAT) {
+    if (i32) gather_vals_kernel<int32_t, float><<<grid, 256, 0, stream>>>(static_cast<const float*>(val), static_cast<const int32_t*>(perm), nnz, static_cast<float*>(out));
+    else gather_vals_kernel<int64_t, float><<<grid, 256, 0, stream>>>(static_cast<const float*>(val), static_cast<const int64_t*>(perm), nnz, static_cast<float*>(out));
+  } else if (val_dtype == OFSPMM_DTYPE_BFLOAT16) {
+    if (i32) gather_vals_kernel<int32_t, __nv_bfloat16><<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(val), static_cast<const int32_t*>(perm), nnz, static_cast<__nv_bfloat16*>(out));
+    else gather_vals_kernel<int64_t, __nv_bfloat16><<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(val), static_cast<const int64_t*>(perm), nnz, static_cast<__nv_bfloat16*>(out));
+  } else {
+    return OFSPMM_ERR_UNSUPPORTED_DTYPE;
+  }
+  count_launch();
+  OFSPMM_CUDA_OK(cudaGetLastError());
+  return OFSPMM_OK;
+}
+
+}  // namespace ofspmm

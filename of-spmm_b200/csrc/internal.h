@@ -22,10 +22,33 @@ constexpr int kWarpsPerCta = OFSPMM_WARPS;
 extern std::atomic<uint64_t> g_launches;
 inline void count_launch(uint64_t k = 1) { g_launches.fetch_add(k, std::memory_order_relaxed); }
 
-inline int64_t num_tasks(int64_t rows, int64_t nnz) {
+constexpr int kSmallTaskItems = 64;       // task size of the small-problem family
+// Below this many 256-item tasks the machine (148 SMs x 36 resident warps) is not filled by one
+// task per warp: AUTO switches to 64-item tasks so 4x more warps work in parallel.
+constexpr int64_t kSmallProblemTasks = 148 * 36;
+
+inline int64_t num_tasks(int64_t rows, int64_t nnz, int items = kTaskItems) {
   const int64_t total = rows + nnz;
-  return (total + kTaskItems - 1) / kTaskItems;
+  return (total + items - 1) / items;
 }
+
+// Resolved kernel family of a forward launch (public encoding: OFSPMM_VARIANT_*).
+struct FwdVariant {
+  int items;          // merge items per warp task: kTaskItems or kSmallTaskItems
+  bool row_parallel;  // sub-warp per row (short rows, narrow dense operand) instead of nnz-parallel
+  bool unroll8;       // two index chunks = eight gathers in flight per lane group (long rows)
+};
+FwdVariant resolve_variant(int variant, int64_t rows, int64_t nnz, int64_t n, int dense_dtype);
+int encode_variant(const FwdVariant& v);
+
+// Per-launch options the C ABI passes down (ofspmm_opts).
+struct FwdLaunch {
+  FwdVariant variant;
+  int tasks_per_warp;  // 0 = persistent grid
+  bool dynamic;        // tasks drawn from a global counter (persistent grid only)
+  unsigned flags;      // kFwd* epilogue bits
+  const void* bias;
+};
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 struct DevInfo {
@@ -36,16 +59,16 @@ int get_dev_info(DevInfo* out);  // OFSPMM_OK / OFSPMM_ERR_CUDA
 
 // Layout of the workspace shared by fwd / bwd(transpose) calls.
 struct FwdWorkspace {
-  size_t part_off, carry_off, head_off, total;
+  size_t counter_off, part_off, carry_off, head_off, total;
 };
-FwdWorkspace fwd_workspace_layout(int64_t rows, int64_t nnz, int64_t n, int dense_dtype);
+FwdWorkspace fwd_workspace_layout(int64_t rows, int64_t nnz, int64_t n, int dense_dtype, int items = kTaskItems);
 
 // Each returns an OFSPMM_* status; all launches go to `stream`.
 int launch_task_partition(const void* crow, int idx_dtype, int64_t rows, int64_t nnz, int64_t P,
-                          void* part, cudaStream_t stream);
+                          int items, void* part, cudaStream_t stream);
 int launch_fwd(const ofspmm_csr* A, const void* B, int64_t ldb, void* C, int64_t ldc, int64_t n,
-               int dense_dtype, const void* part, float* carry, float* head, int64_t P,
-               cudaStream_t stream);
+               int dense_dtype, const void* part, float* carry, float* head, void* counter, int64_t P,
+               const FwdLaunch& L, cudaStream_t stream);
 int launch_sddmm(const ofspmm_csr* A, const void* dY, const void* B, void* dval, int64_t n,
                  int dense_dtype, const void* part, int64_t P, cudaStream_t stream);
 int launch_bwd_atomic(const ofspmm_csr* A, const void* dY, float* acc, void* dB_cast_out,
@@ -58,6 +81,14 @@ size_t transpose_workspace_bytes(int64_t rows, int64_t cols, int64_t nnz, int id
 int launch_transpose(const ofspmm_csr* A, void* t_crow, void* t_col, void* t_val, void* t_perm,
                      void* ws, size_t ws_bytes, cudaStream_t stream);
 const char* fwd_variant_name(int64_t n, int dense_dtype, bool aligned);
+int launch_gather_vals(const void* val, int val_dtype, const void* perm, int idx_dtype, int64_t nnz,
+                       void* out, cudaStream_t stream);
+int launch_gather_rows(void* dst, int64_t ld_dst, const void* src, int64_t ld_src, const void* list,
+                       int idx_dtype, int64_t idx_offset, int64_t count, int64_t n, int dense_dtype,
+                       int max_ctas, cudaStream_t stream);
+int launch_scatter_add_rows(void* dst, int64_t ld_dst, const void* src, int64_t ld_src, const void* list,
+                            int idx_dtype, int64_t idx_offset, int64_t count, int64_t n, int dense_dtype,
+                            int max_ctas, cudaStream_t stream);
 
 #define OFSPMM_CUDA_OK(expr)                         \
   do {                                               \

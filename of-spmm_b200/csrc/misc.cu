@@ -42,19 +42,33 @@ __global__ void row_hist_kernel(const IdxT* __restrict__ crow, long long rows,
     atomicAdd(&hist[threadIdx.x], static_cast<unsigned long long>(sh[threadIdx.x]));
 }
 
+// Sort keys of the transpose: the column index, or the sentinel `cols` for an index outside
+// [0, cols) — such entries are skipped by every kernel of the library (include/ofspmm.h), so they
+// must not alias into a valid column bucket; they sort behind every valid key.  pos[p] = p.
 template <typename IdxT>
-__global__ void iota_kernel(IdxT* __restrict__ out, long long count) {
+__global__ void transpose_keys_kernel(const IdxT* __restrict__ col, long long cols, long long count,
+                                      IdxT* __restrict__ keys, IdxT* __restrict__ pos) {
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < count; i += stride)
-    out[i] = static_cast<IdxT>(i);
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < count; i += stride) {
+    const IdxT c = col[i];
+    const bool ok = static_cast<unsigned long long>(c) < static_cast<unsigned long long>(cols);
+    keys[i] = ok ? c : static_cast<IdxT>(cols);
+    pos[i] = static_cast<IdxT>(i);
+  }
 }
 
-// t_crow[c] = first position in the column-sorted key array whose key is >= c.
+// t_crow[c] = first position in the column-sorted key array whose key is >= c.  t_crow[cols] is
+// pinned to nnz (crow[rows] == nnz is what the merge-path kernels rely on): the skipped entries
+// therefore trail the last row of A^T, where the fill kernel marks them with column -1.
 template <typename IdxT>
 __global__ void transpose_offsets_kernel(const IdxT* __restrict__ sorted_cols, long long nnz,
                                          long long cols, IdxT* __restrict__ t_crow) {
   const long long c = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (c > cols) return;
+  if (c == cols) {
+    t_crow[c] = static_cast<IdxT>(cols > 0 ? nnz : 0);
+    return;
+  }
   long long lo = 0, hi = nnz;
   while (lo < hi) {
     const long long mid = (lo + hi) >> 1;
@@ -67,10 +81,16 @@ __global__ void transpose_offsets_kernel(const IdxT* __restrict__ sorted_cols, l
 template <typename IdxT, typename ValT>
 __global__ void transpose_fill_kernel(const IdxT* __restrict__ crow, long long rows,
                                       const ValT* __restrict__ val, const IdxT* __restrict__ perm,
+                                      const IdxT* __restrict__ sorted_keys, long long cols,
                                       long long nnz, IdxT* __restrict__ t_col, ValT* __restrict__ t_val) {
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
   for (long long q = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; q < nnz; q += stride) {
     const long long p = static_cast<long long>(perm[q]);
+    if (static_cast<long long>(sorted_keys[q]) >= cols) {  // skipped entry of A: stays skipped in A^T
+      t_col[q] = static_cast<IdxT>(-1);
+      if (t_val != nullptr) t_val[q] = ValT{};
+      continue;
+    }
     long long lo = 0, hi = rows;  // largest r with crow[r] <= p
     while (lo < hi) {
       const long long mid = (lo + hi + 1) >> 1;
@@ -97,18 +117,19 @@ size_t cub_sort_temp_bytes(int64_t nnz, int end_bit) {
 }
 
 struct TransposeLayout {
-  size_t keys_out, pos_in, pos_out, cub_tmp, cub_bytes, total;
+  size_t keys_in, keys_out, pos_in, pos_out, cub_tmp, cub_bytes, total;
 };
 
 template <typename IdxT>
 TransposeLayout transpose_layout(int64_t cols, int64_t nnz) {
   TransposeLayout L;
   const size_t arr = align_up(static_cast<size_t>(nnz > 0 ? nnz : 1) * sizeof(IdxT), 256);
-  L.keys_out = 0;
-  L.pos_in = arr;
-  L.pos_out = 2 * arr;
-  L.cub_tmp = 3 * arr;
-  L.cub_bytes = cub_sort_temp_bytes<IdxT>(nnz, bits_for(cols));
+  L.keys_in = 0;
+  L.keys_out = arr;
+  L.pos_in = 2 * arr;
+  L.pos_out = 3 * arr;
+  L.cub_tmp = 4 * arr;
+  L.cub_bytes = cub_sort_temp_bytes<IdxT>(nnz, bits_for(cols + 1));
   L.total = L.cub_tmp + align_up(L.cub_bytes, 256);
   return L;
 }
@@ -120,6 +141,7 @@ int transpose_impl(const ofspmm_csr* A, void* t_crow, void* t_col, void* t_val, 
   const TransposeLayout L = transpose_layout<IdxT>(cols, nnz);
   if (ws == nullptr || ws_bytes < L.total) return OFSPMM_ERR_WORKSPACE;
   unsigned char* w = static_cast<unsigned char*>(ws);
+  IdxT* keys_in = reinterpret_cast<IdxT*>(w + L.keys_in);
   IdxT* keys_out = reinterpret_cast<IdxT*>(w + L.keys_out);
   IdxT* pos_in = reinterpret_cast<IdxT*>(w + L.pos_in);
   IdxT* pos_out = t_perm != nullptr ? static_cast<IdxT*>(t_perm) : reinterpret_cast<IdxT*>(w + L.pos_out);
@@ -127,14 +149,14 @@ int transpose_impl(const ofspmm_csr* A, void* t_crow, void* t_col, void* t_val, 
   if (int rc = get_dev_info(&dev)) return rc;
   const int grid = dev.sms * 8;
   if (nnz > 0) {
-    iota_kernel<IdxT><<<grid, 256, 0, stream>>>(pos_in, nnz);
+    transpose_keys_kernel<IdxT><<<grid, 256, 0, stream>>>(static_cast<const IdxT*>(A->col), cols, nnz, keys_in, pos_in);
     count_launch();
     size_t cub_bytes = L.cub_bytes;
     // stable LSD radix sort by column: entries of one column keep ascending source position,
     // i.e. ascending row — the transposed CSR is deterministic and row-sorted.
-    OFSPMM_CUDA_OK(cub::DeviceRadixSort::SortPairs(w + L.cub_tmp, cub_bytes, static_cast<const IdxT*>(A->col),
+    OFSPMM_CUDA_OK(cub::DeviceRadixSort::SortPairs(w + L.cub_tmp, cub_bytes, static_cast<const IdxT*>(keys_in),
                                                    keys_out, static_cast<const IdxT*>(pos_in), pos_out,
-                                                   static_cast<long long>(nnz), 0, bits_for(cols), stream));
+                                                   static_cast<long long>(nnz), 0, bits_for(cols + 1), stream));
     count_launch(4);
   }
   transpose_offsets_kernel<IdxT><<<static_cast<unsigned>((cols + 1 + 255) / 256), 256, 0, stream>>>(
@@ -143,14 +165,14 @@ int transpose_impl(const ofspmm_csr* A, void* t_crow, void* t_col, void* t_val, 
   if (nnz > 0) {
     if (A->val == nullptr || t_val == nullptr) {
       transpose_fill_kernel<IdxT, float><<<grid, 256, 0, stream>>>(
-          static_cast<const IdxT*>(A->crow), rows, nullptr, pos_out, nnz, static_cast<IdxT*>(t_col), nullptr);
+          static_cast<const IdxT*>(A->crow), rows, nullptr, pos_out, keys_out, cols, nnz, static_cast<IdxT*>(t_col), nullptr);
     } else if (A->val_dtype == OFSPMM_DTYPE_FLOAT) {
       transpose_fill_kernel<IdxT, float><<<grid, 256, 0, stream>>>(
-          static_cast<const IdxT*>(A->crow), rows, static_cast<const float*>(A->val), pos_out, nnz,
+          static_cast<const IdxT*>(A->crow), rows, static_cast<const float*>(A->val), pos_out, keys_out, cols, nnz,
           static_cast<IdxT*>(t_col), static_cast<float*>(t_val));
     } else if (A->val_dtype == OFSPMM_DTYPE_BFLOAT16) {
       transpose_fill_kernel<IdxT, __nv_bfloat16><<<grid, 256, 0, stream>>>(
-          static_cast<const IdxT*>(A->crow), rows, static_cast<const __nv_bfloat16*>(A->val), pos_out, nnz,
+          static_cast<const IdxT*>(A->crow), rows, static_cast<const __nv_bfloat16*>(A->val), pos_out, keys_out, cols, nnz,
           static_cast<IdxT*>(t_col), static_cast<__nv_bfloat16*>(t_val));
     } else {
       return OFSPMM_ERR_UNSUPPORTED_DTYPE;

@@ -112,17 +112,19 @@ sddmm_merge_kernel(const SddmmParams p) {
 
       auto dot_one = [&](int elem) {  // full dot of one staged element, result in every group lane
         const IdxT c = tk.scol[elem];
-        const char* brow = Bl + row_offset(c, row_bytes);
         float d = 0.f;
+        if (static_cast<unsigned long long>(c) < static_cast<unsigned long long>(p.cols)) {  // group-uniform
+          const char* brow = Bl + row_offset(c, row_bytes);
 #pragma unroll
-        for (int ch = 0; ch < CH; ++ch)
-          d = RV::dot(y[ch], load_b<DT, VEC>(brow + (kFull ? ch * kChunkBytes : choff[ch]), 0), d);
+          for (int ch = 0; ch < CH; ++ch)
+            d = RV::dot(y[ch], load_b<DT, VEC>(brow + (kFull ? ch * kChunkBytes : choff[ch]), 0), d);
+        }
 #pragma unroll
         for (int off = LPR / 2; off > 0; off >>= 1) d += __shfl_xor_sync(gmask, d, off);
         if (lig == 0) sout[elem] = d;
       };
 
-      if constexpr (kVecIdx) {
+      if (kVecIdx && !tk.dirty) {
         // slots s = pre_c + e, read as 16-byte chunks of 4; chunk q of the row goes to group q % G.
         // First / last chunk: slots outside the row are masked (no gather, no result written).
         const int s0 = tk.pre_c + e, s1 = tk.pre_c + e_end;
@@ -249,9 +251,11 @@ __global__ void __launch_bounds__(WARPS * 32) sddmm_wide_kernel(const SddmmParam
       const int e_end = r < re ? static_cast<int>(tk.srow[r - rs + 1]) - ns : cnt_nz;
       const DT* yrow = dY + static_cast<size_t>(r) * n;
       for (int q = e; q < e_end; ++q) {
-        const DT* brow = B + static_cast<size_t>(tk.scol[q]) * n;
+        const IdxT cq = tk.scol[q];
+        const bool okq = static_cast<unsigned long long>(cq) < static_cast<unsigned long long>(p.cols);
+        const DT* brow = B + static_cast<size_t>(okq ? cq : 0) * n;
         float d = 0.f;
-        for (int c0 = lane * VEC; c0 < n; c0 += 32 * VEC) {
+        for (int c0 = lane * VEC; okq && c0 < n; c0 += 32 * VEC) {
           float yy[VEC];
           RV::load(yrow + c0, yy);
           d = RV::dot(yy, RV::load_raw(brow + c0), d);
@@ -339,7 +343,6 @@ __global__ void __launch_bounds__(WARPS * 32) bwd_atomic_kernel(const BwdAtomicP
     const int rs = ps.x, ns = ps.y, re = pe.x, ne = pe.y;
     const int cnt_nz = ne - ns;
     if (cnt_nz == 0) continue;
-    // sanitised staging: out-of-range entries become (col 0, val 0) and add nothing
     const StagedTask<IdxT, ValT> tk = stage_task<true>(st, bar, phase, crow, col, val, rs, ns, re - rs + 1,
                                                        cnt_nz, p.cols, lane, pol_stream);
     int e = 0;
@@ -352,6 +355,7 @@ __global__ void __launch_bounds__(WARPS * 32) bwd_atomic_kernel(const BwdAtomicP
         if (chmask & (1u << ch)) RowVec<DT, VEC>::load(dYl + static_cast<size_t>(r) * n + ch * LPR * VEC, y[ch]);
       for (int q = e + grp; q < e_end; q += G) {
         const IdxT c = tk.scol[q];
+        if (static_cast<unsigned long long>(c) >= static_cast<unsigned long long>(p.cols)) continue;  // skipped
         const float v = to_float(tk.sval[q]);
         float* dst = accl + static_cast<size_t>(c) * n;
 #pragma unroll

@@ -28,7 +28,7 @@
 #include "common.cuh"
 
 #ifndef OFSPMM_B_LOAD
-#define OFSPMM_B_LOAD 0  // 0: ld.global.nc   1: + L1::no_allocate   2: + L2 evict_last policy
+#define OFSPMM_B_LOAD 0  // 0: ld.global.nc   1: + L1::no_allocate   2: 1 + L2 evict_last   3: L1 allocate + L2 evict_last
 #endif
 
 namespace ofspmm {
@@ -36,11 +36,13 @@ namespace ofspmm {
 // Resident CTAs per SM the kernels are compiled for (4 warps per CTA): sets the register cap.
 // Measured on B200 (tools/sweep_fwd.py, profiles/r1_tuning_sweeps.md): fp32 rows run best at 36
 // warps/SM with 54 registers, bf16 rows (8 accumulators + unpacking) at 32 warps/SM with 60.
-template <typename DT, int CH>
+// UNR == 2 (eight gathers in flight per lane group, long-row graphs): 7 CTAs/SM = 72 registers.
+template <typename DT, int CH, int UNR = 1>
 constexpr int min_ctas_per_sm() {
 #ifdef OFSPMM_MIN_CTAS
   return CH == 1 ? OFSPMM_MIN_CTAS : (CH == 2 ? 6 : 4);
 #else
+  if (UNR == 2) return CH == 1 ? 7 : 4;
   return CH == 1 ? (sizeof(DT) == 4 ? 9 : 8) : (CH == 2 ? 6 : 4);
 #endif
 }
@@ -62,7 +64,39 @@ struct FwdParams {
   int panels;        // column panels of LPR*VEC*CH columns each
   long long ldb;     // row stride of B in elements (>= n)
   long long ldc;     // row stride of C in elements (>= n)
+  const void* bias;  // n elements of the dense dtype (kFwdBias)
+  unsigned long long* counter;  // dynamic task order: zeroed before the launch; nullptr = static
+  unsigned flags;    // kFwd* epilogue bits
 };
+
+// Epilogue bits (= OFSPMM_FWD_* of include/ofspmm.h).  A row's epilogue runs exactly once, where
+// its complete fp32 sum is known: in the merge kernel for rows that live inside one task, in the
+// fix-up kernel for rows stitched from several tasks.
+constexpr unsigned kFwdAccumulate = 1u;  // C += A·B instead of C = A·B
+constexpr unsigned kFwdBias = 2u;        // + bias[j]
+constexpr unsigned kFwdRelu = 4u;        // max(., 0)
+
+// acc (+ old C) (+ bias) (relu) for VEC consecutive columns starting at column `c0` of row `crow_ptr`.
+template <typename DT, int VEC>
+__device__ __forceinline__ void row_epilogue(float (&acc)[VEC], const DT* c_old, const void* bias, int c0,
+                                             unsigned flags, bool add_old) {
+  if (add_old) {
+    float o[VEC];
+    RowVec<DT, VEC>::load(c_old, o);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) acc[i] += o[i];
+  }
+  if (flags & kFwdBias) {
+    float b[VEC];
+    RowVec<DT, VEC>::load(static_cast<const DT*>(bias) + c0, b);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) acc[i] += b[i];
+  }
+  if (flags & kFwdRelu) {
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) acc[i] = fmaxf(acc[i], 0.f);
+  }
+}
 
 template <typename IdxT, typename ValT, int ITEMS>
 struct alignas(16) TaskStage {
@@ -104,11 +138,16 @@ struct StagedTask {
   int pre_c, pre_v;  // slot of element 0 inside st.col / st.val (address alignment phase)
   // lane i holds the bit mask of out-of-range elements 32*i .. 32*i+31 of the task
   unsigned badmask;
+  // some column index of the task lies outside [0, cols): the task takes the per-element checked
+  // path (the staged copy is left untouched, nothing is gathered for such an element)
+  bool dirty;
 };
 
 // Stages crow[rs..re], col[ns..ne) and (optionally) val[ns..ne) of a task: TMA bulk copies for
 // the 16-byte aligned bodies, lanes for the ragged edges, then waits for the bytes to land and
-// neutralises out-of-range column indices (col := 0, val := 0) in the staged copy.
+// scans the column indices once: a task whose indices are all inside [0, cols) runs the check-free
+// vector loop; a task with an out-of-range index is flagged `dirty` and runs a per-element checked
+// loop that issues no load for such an element (so NaN / Inf in unrelated B rows cannot leak in).
 template <bool kWithVal, typename IdxT, typename ValT, int ITEMS>
 __device__ __forceinline__ StagedTask<IdxT, ValT> stage_task(
     TaskStage<IdxT, ValT, ITEMS>& st, uint64_t* bar, uint32_t& phase, const IdxT* __restrict__ crow,
@@ -121,13 +160,11 @@ __device__ __forceinline__ StagedTask<IdxT, ValT> stage_task(
   const uint32_t tx = static_cast<uint32_t>(body_c * sizeof(IdxT) + body_v * sizeof(ValT) +
                                             body_r * sizeof(IdxT));
   __syncwarp();  // every lane is done reading the previous task's stage
-#ifdef OFSPMM_PROXY_FENCE
-  // formal-model nicety (off by default, see ROUND_NOTES.md): order this warp's earlier generic-proxy
-  // shared-memory stores (sanitise pass, ragged edges, SDDMM staging) before the async-proxy writes
-  // of the next bulk copies into the same bytes
-  if (lane == 0) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-#endif
   if (lane == 0 && tx != 0) {
+    // order this warp's earlier generic-proxy shared-memory stores (ragged edges, SDDMM result
+    // staging; made visible to lane 0 by the __syncwarp above) before the async-proxy writes of the
+    // bulk copies into the same bytes
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     mbar_arrive_expect_tx(bar, tx);
     if (body_c) tma_bulk_g2s(st.col + pre_c + head_c, col + ns + head_c, body_c * sizeof(IdxT), bar, pol_stream);
     if (kWithVal && body_v) tma_bulk_g2s(st.val + pre_v + head_v, val + ns + head_v, body_v * sizeof(ValT), bar, pol_stream);
@@ -141,25 +178,23 @@ __device__ __forceinline__ StagedTask<IdxT, ValT> stage_task(
     phase ^= 1;
   }
   __syncwarp();
-  // sanitise: indices outside [0, cols) contribute nothing (reference: segment-sum skips them)
+  // indices outside [0, cols) contribute nothing (reference: segment-sum skips them)
   unsigned badmask = 0;
+  bool dirty = false;
   for (int e0 = 0; e0 < cnt_nz; e0 += 32) {
     const int e = e0 + lane;
     bool bad = false;
     if (e < cnt_nz) {
       const IdxT c = st.col[pre_c + e];
       bad = static_cast<unsigned long long>(c) >= static_cast<unsigned long long>(cols);
-      if (bad) {
-        st.col[pre_c + e] = 0;
-        if constexpr (kWithVal) st.val[pre_v + e] = from_float<ValT>(0.f);
-      }
     }
     const unsigned m = __ballot_sync(0xffffffffu, bad);
     if (lane == (e0 >> 5)) badmask = m;
+    dirty |= m != 0;
   }
-  __syncwarp();
   StagedTask<IdxT, ValT> t;
   t.badmask = badmask;
+  t.dirty = dirty;
   t.scol = st.col + pre_c;
   t.sval = st.val + pre_v;
   t.srow = st.crow + pre_r;
@@ -182,6 +217,9 @@ __device__ __forceinline__ typename RowVec<DT, VEC>::Raw load_b(const char* p, u
     (void)pol;
     asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
                  : "=r"(w.x), "=r"(w.y), "=r"(w.z), "=r"(w.w) : "l"(p));
+#elif OFSPMM_B_LOAD == 3
+    asm volatile("ld.global.nc.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=r"(w.x), "=r"(w.y), "=r"(w.z), "=r"(w.w) : "l"(p), "l"(pol));
 #else
     asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
                  : "=r"(w.x), "=r"(w.y), "=r"(w.z), "=r"(w.w) : "l"(p), "l"(pol));
@@ -218,8 +256,8 @@ __device__ __forceinline__ uint2 lds64(uint32_t addr) {
 // kFull: n is a whole number of LPR*VEC*CH-column tiles, so no lane is ever masked and the chunk
 // offsets are immediates.  Otherwise masked chunks are pointed at column 0 (a valid address:
 // their loads are harmless duplicates) and only the stores are predicated.
-template <typename DT, typename ValT, typename IdxT, int VEC, int LPR, int CH, bool kFull, bool kRowPar, int ITEMS, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32, min_ctas_per_sm<DT, CH>())
+template <typename DT, typename ValT, typename IdxT, int VEC, int LPR, int CH, bool kFull, bool kRowPar, int ITEMS, int WARPS, int UNR>
+__global__ void __launch_bounds__(WARPS * 32, min_ctas_per_sm<DT, CH, UNR>())
 spmm_merge_kernel(const FwdParams p) {
   constexpr int G = 32 / LPR;  // groups of lanes working on different non-zeros
   constexpr bool kF32Out = sizeof(DT) == 4;
@@ -246,7 +284,7 @@ spmm_merge_kernel(const FwdParams p) {
   __syncwarp();
 
   const uint64_t pol_stream = l2_policy_evict_first();
-#if OFSPMM_B_LOAD == 2
+#if OFSPMM_B_LOAD >= 2
   const uint64_t pol_b = l2_policy_evict_last();
 #else
   const uint64_t pol_b = 0;
@@ -261,7 +299,18 @@ spmm_merge_kernel(const FwdParams p) {
   const int total_warps = gridDim.x * WARPS;
   uint32_t phase = 0;
 
-  for (long long t = blockIdx.x * WARPS + warp; t < total_tasks; t += total_warps) {
+  // Task order.  Static: warp w runs tasks w, w + W, w + 2W, ...  Dynamic (p.counter != nullptr):
+  // the first task is still w, every later one is drawn from a global counter in launch order, so
+  // the rows in flight chip-wide always form ONE contiguous window of the matrix however unevenly
+  // the warps progress (keeps the B rows of that window L2-resident, and evens out the tail).
+  // The draw is issued at the top of a task and consumed at its end: its latency is hidden.
+  for (long long t = blockIdx.x * WARPS + warp; t < total_tasks;) {
+    long long t_next = t + total_warps;
+    if (p.counter != nullptr) {
+      unsigned long long drawn = 0;
+      if (lane == 0) drawn = atomicAdd(p.counter, 1ull);
+      t_next = static_cast<long long>(__shfl_sync(0xffffffffu, drawn, 0)) + total_warps;
+    }
     // panel-major: all tasks of column panel 0, then panel 1, ... (keeps the B panel in L2)
     const int panel = static_cast<int>(t / p.P);
     const int k = static_cast<int>(t - static_cast<long long>(panel) * p.P);
@@ -288,7 +337,7 @@ spmm_merge_kernel(const FwdParams p) {
     const StagedTask<IdxT, ValT> tk = stage_task<true>(st, bar, phase, crow, col, val, rs, ns, re - rs + 1,
                                                        cnt_nz, p.cols, lane, pol_stream);
     // 16-byte LDS path: index chunk and value chunk must share their alignment phase
-    const bool vec_ok = kVecIdx && (((tk.pre_v - tk.pre_c) & 3) == 0);
+    const bool vec_ok = kVecIdx && !tk.dirty && (((tk.pre_v - tk.pre_c) & 3) == 0);
     // value byte address of the slot that pairs with index slot 0
     const uint32_t val_s0 = val_sa + static_cast<uint32_t>((tk.pre_v - tk.pre_c) * static_cast<int>(sizeof(ValT)));
     const bool started_earlier = static_cast<int>(tk.srow[0]) < ns;
@@ -364,10 +413,10 @@ spmm_merge_kernel(const FwdParams p) {
           const int q0 = chunk_first == 0 ? kChunkStride : chunk_first;
           uint32_t ca = col_sa + static_cast<uint32_t>(cbase + 4 * q0) * 4u;
           const uint32_t cend = col_sa + static_cast<uint32_t>(cbase + 4 * (nchunks - 1)) * 4u;
-#if defined(OFSPMM_CHUNKS_PER_ITER) && OFSPMM_CHUNKS_PER_ITER == 2
-          // tuning experiment (off by default): two index chunks = eight gathers in flight per
-          // iteration; the single-chunk loop below then only handles an odd leftover chunk
-          while (ca + 16u * kChunkStride < cend) {
+          // UNR == 2 (picked for long-row graphs by the row-length histogram): two index chunks =
+          // eight gathers in flight per iteration; the single-chunk loop below then only handles
+          // an odd leftover chunk
+          if constexpr (UNR == 2) while (ca + 16u * kChunkStride < cend) {
             const uint4 ca4 = lds128(ca), cb4 = lds128(ca + 16u * kChunkStride);
             const uint32_t c8[8] = {ca4.x, ca4.y, ca4.z, ca4.w, cb4.x, cb4.y, cb4.z, cb4.w};
             typename RV::Raw x8[8][CH];
@@ -399,7 +448,6 @@ spmm_merge_kernel(const FwdParams p) {
 #pragma unroll
               for (int ch = 0; ch < CH; ++ch) RV::fma(acc[ch], v8[u], x8[u][ch]);
           }
-#endif
           if (ca < cend) {
             uint4 cn = lds128(ca);
             do {
@@ -437,6 +485,7 @@ spmm_merge_kernel(const FwdParams p) {
       } else {
         for (int el = e0 + chunk_first; el < e1; el += kChunkStride) {
           const IdxT c = tk.scol[el];
+          if (static_cast<unsigned long long>(c) >= static_cast<unsigned long long>(p.cols)) continue;
           const float v = to_float(tk.sval[el]);
           const char* brow = Bl + row_offset(c, row_bytes);
 #pragma unroll
@@ -464,12 +513,25 @@ spmm_merge_kernel(const FwdParams p) {
             if (chmask & (1u << ch)) store_f32<VEC>(dst + ch * LPR * VEC, acc[ch]);
         } else {
           DT* dst = static_cast<DT*>(p.C) + static_cast<size_t>(r) * p.ldc + col0;
+          if (p.flags != 0) {
+            // complete row: whole epilogue here.  Final segment of a stitched row (fp32 output
+            // only — bf16 went to head[] above): fold the old C in now, the fix-up kernel adds
+            // the carries and applies bias / relu.
+            const bool partial = r == rs && started_earlier;
+            const unsigned fl = partial ? 0u : p.flags;
+#pragma unroll
+            for (int ch = 0; ch < CH; ++ch)
+              if (chmask & (1u << ch))
+                row_epilogue<DT, VEC>(acc[ch], dst + ch * LPR * VEC, p.bias, col0 + ch * LPR * VEC, fl,
+                                      (p.flags & kFwdAccumulate) != 0);
+          }
 #pragma unroll
           for (int ch = 0; ch < CH; ++ch)
             if (chmask & (1u << ch)) RV::store_stream(dst + ch * LPR * VEC, acc[ch]);
         }
       }
     }
+    t = t_next;
   }
 }
 
@@ -528,12 +590,14 @@ __global__ void __launch_bounds__(WARPS * 32) spmm_fixup_kernel(const FwdParams 
       }
       float h[VEC];
       if constexpr (kF32Out) {
-        load_f32<VEC>(reinterpret_cast<const float*>(crow_out) + c0, h);
+        load_f32<VEC>(reinterpret_cast<const float*>(crow_out) + c0, h);  // already holds old C when accumulating
       } else {
         load_f32<VEC>(p.head + static_cast<size_t>(kk) * n + c0, h);
       }
 #pragma unroll
       for (int i = 0; i < VEC; ++i) sum[i] += h[i];
+      if (p.flags != 0)
+        row_epilogue<DT, VEC>(sum, crow_out + c0, p.bias, c0, p.flags, !kF32Out && (p.flags & kFwdAccumulate) != 0);
       RowVec<DT, VEC>::store_stream(crow_out + c0, sum);
     }
   }

@@ -22,36 +22,33 @@ from . import ops
 
 class SpmmOpKernelState:
     """Per-op persistent data — the role OpKernelState plays in the reference
-    (oneflow/user/kernels/stateful_opkernel.cpp:919-928): a CSR of A^T built once on the device and
-    keyed by the identity of the CSR arrays, so `spmm_csr_grad_b` runs the deterministic,
-    atomic-free route."""
+    (oneflow/user/kernels/stateful_opkernel.cpp:919-928): one ``ops.SpmmPlan`` per CSR *structure*
+    (histogram-chosen kernel variants, cached task partitions, and the structure of A^T with its
+    value permutation).  Values are never cached — the backward re-gathers ``a_val`` through
+    ``t_perm`` on every call — so in-place updates of learnable edge weights are always seen.  The
+    key holds the index tensors' data pointers, shapes and autograd versions, and the plan keeps
+    the index tensors alive, so a recycled address cannot alias a different graph."""
 
-    def __init__(self) -> None:
-        self._cache: Dict[Tuple[int, int, int, int, int, int], Tuple[torch.Tensor, ...]] = {}
-        self._keep = {}
+    def __init__(self, transpose: bool = True) -> None:
+        self._plan: Optional[ops.SpmmPlan] = None
+        self._transpose = transpose
 
-    @staticmethod
-    def _key(a_crow, a_col, a_val, a_rows, a_cols):
-        return (a_crow.data_ptr(), a_col.data_ptr(), a_val.data_ptr(), a_val._version, a_rows, a_cols)
-
-    def transposed(self, a_crow, a_col, a_val, a_rows: int, a_cols: int):
-        k = self._key(a_crow, a_col, a_val, a_rows, a_cols)
-        hit = self._cache.get(k)
-        if hit is None:
-            hit = ops.csr_transpose(a_crow, a_col, a_val.detach(), a_rows, a_cols)
-            self._cache = {k: hit}                      # one entry: the op sees one graph at a time
-            self._keep = (a_crow, a_col, a_val)         # pin the key tensors so pointers stay unique
-        return hit
+    def plan(self, a_crow, a_col, a_rows: int, a_cols: int, n: int, dtype) -> "ops.SpmmPlan":
+        p = self._plan
+        if p is None or not p.matches(a_crow, a_col, a_rows, a_cols, n, dtype):
+            p = ops.SpmmPlan(a_crow, a_col, a_rows, a_cols, n, dtype, transpose=self._transpose)
+            self._plan = p                               # one entry: the op sees one graph at a time
+        return p
 
     def clear(self) -> None:
-        self._cache.clear()
-        self._keep = {}
+        self._plan = None
 
 
 class _SpmmCsrFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, a_crow, a_col, a_val, b, a_rows, a_cols, state):
-        out = ops.spmm_csr_compute(a_crow, a_col, a_val.detach(), b.detach(), a_rows, a_cols)
+        plan = state.plan(a_crow, a_col, a_rows, a_cols, b.shape[1], b.dtype) if state is not None else None
+        out = ops.spmm_csr_compute(a_crow, a_col, a_val.detach(), b.detach(), a_rows, a_cols, plan=plan)
         # Capture (matmul.cpp:48-73): save only what Apply will read
         ctx.val_requires_grad = a_val.requires_grad
         ctx.b_requires_grad = b.requires_grad
@@ -65,13 +62,15 @@ class _SpmmCsrFn(torch.autograd.Function):
         a_crow, a_col, a_val, b = ctx.saved_tensors
         dy = dy.contiguous()
         d_val = d_b = None
+        plan = None
+        if ctx.state is not None:
+            plan = ctx.state.plan(a_crow, a_col, ctx.a_rows, ctx.a_cols, dy.shape[1], dy.dtype)
         if ctx.val_requires_grad:
-            d_val = ops.sddmm_csr_compute(a_crow, a_col, dy, b, ctx.a_rows, ctx.a_cols, a_val.dtype)
+            d_val = ops.sddmm_csr_compute(a_crow, a_col, dy, b, ctx.a_rows, ctx.a_cols, a_val.dtype, plan=plan)
         if ctx.b_requires_grad:
-            tr = None
-            if ctx.state is not None:
-                tr = ctx.state.transposed(a_crow, a_col, a_val, ctx.a_rows, ctx.a_cols)
-            d_b = ops.spmm_csr_grad_b_compute(a_crow, a_col, a_val.detach(), dy, ctx.a_rows, ctx.a_cols, tr)
+            # cached structure of A^T when the op has a state, transient transpose otherwise — both
+            # deterministic; the atomic scatter is opt-in (ops.spmm_csr_grad_b_compute(atomic=True))
+            d_b = ops.spmm_csr_grad_b_compute(a_crow, a_col, a_val.detach(), dy, ctx.a_rows, ctx.a_cols, plan=plan)
         return None, None, d_val, d_b, None, None, None
 
 
@@ -79,18 +78,21 @@ def spmm_csr(a_crow: torch.Tensor, a_col: torch.Tensor, a_val: torch.Tensor, b: 
              a_rows: int, a_cols: int, state: Optional[SpmmOpKernelState] = None) -> torch.Tensor:
     """out[a_rows, n] = CSR(a_crow, a_col, a_val; a_rows x a_cols) @ b[a_cols, n].
 
-    Differentiable wrt ``a_val`` (SDDMM) and ``b`` (A^T·dy).  ``state`` (optional) caches the device
-    transpose for the deterministic backward; without it the backward uses the atomic route."""
+    Differentiable wrt ``a_val`` (SDDMM) and ``b`` (A^T·dy).  ``state`` (optional) keeps the plan of
+    the CSR structure (variant, task partition, structure of A^T); without it the partition is
+    recomputed per call and the backward builds A^T transiently — still deterministic."""
     if not (torch.is_grad_enabled() and (a_val.requires_grad or b.requires_grad)):
-        return ops.spmm_csr_compute(a_crow, a_col, a_val, b, a_rows, a_cols)
+        plan = state.plan(a_crow, a_col, a_rows, a_cols, b.shape[1], b.dtype) if state is not None else None
+        return ops.spmm_csr_compute(a_crow, a_col, a_val, b, a_rows, a_cols, plan=plan)
     ops._check_device(a_crow, a_col, a_val, b)
     ops.infer_spmm_csr(a_crow, a_col, a_val, b, a_rows, a_cols)
     return _SpmmCsrFn.apply(a_crow, a_col, a_val, b, a_rows, a_cols, state)
 
 
-def spmm_csr_grad_b(a_crow, a_col, a_val, dy, a_rows: int, a_cols: int, transposed=None) -> torch.Tensor:
+def spmm_csr_grad_b(a_crow, a_col, a_val, dy, a_rows: int, a_cols: int, transposed=None, plan=None,
+                    atomic: bool = False) -> torch.Tensor:
     """db[a_cols, n] = A^T @ dy (the op the grad function dispatches for ``b``)."""
-    return ops.spmm_csr_grad_b_compute(a_crow, a_col, a_val, dy, a_rows, a_cols, transposed)
+    return ops.spmm_csr_grad_b_compute(a_crow, a_col, a_val, dy, a_rows, a_cols, transposed, plan=plan, atomic=atomic)
 
 
 def sddmm_csr(a_crow, a_col, dy, b, a_rows: int, a_cols: int, val_dtype=torch.float32) -> torch.Tensor:

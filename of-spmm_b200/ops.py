@@ -23,7 +23,7 @@ from typing import Optional, Tuple
 import torch
 
 from . import _lib
-from ._lib import CsrStruct, check
+from ._lib import CsrStruct, OptsStruct, check
 
 _DENSE = {torch.float32: _lib.DTYPE_FLOAT, torch.bfloat16: _lib.DTYPE_BFLOAT16}
 _INDEX = {torch.int32: _lib.DTYPE_INT32, torch.int64: _lib.DTYPE_INT64}
@@ -89,51 +89,166 @@ def _check_device(*tensors) -> None:
         _chk(t.device == dev, "all tensors must live on one device")
 
 
+def _check_packed(*tensors) -> None:
+    """Operands of the entry points that take no leading dimension (dy / b / out of
+    `spmm_csr_grad_b` and `sddmm_csr`) must be packed row-major: a column-slice view would be read
+    with the wrong row stride."""
+    for t in tensors:
+        if t is not None:
+            _chk(t.is_contiguous(), "spmm_csr_grad_b / sddmm_csr take packed (contiguous) dense operands; "
+                                    "call .contiguous() on column-slice views")
+
+
 def _csr_struct(a_crow, a_col, a_val, rows: int, cols: int, val_dtype=None) -> CsrStruct:
     vd = _DENSE[a_val.dtype] if a_val is not None else _DENSE[val_dtype or torch.float32]
     return CsrStruct(rows, cols, int(a_col.numel()), _ptr(a_crow), _ptr(a_col), _ptr(a_val),
                      _INDEX[a_crow.dtype], vd)
 
 
+class SpmmPlan:
+    """What the op keeps per CSR *structure* — the OpKernelState role
+    (oneflow/user/kernels/stateful_opkernel.cpp:919-928), built once, outside any captured call:
+
+      * the kernel variant chosen from the row-length histogram (``ofspmm_row_hist`` → host →
+        ``ofspmm_choose_variant``) for this (structure, n, dtype);
+      * the merge-path task partition of that variant (``ofspmm_plan_build``), so products skip
+        the partition kernel;
+      * optionally (``transpose=True``) the structure of A^T — ``t_crow, t_col, t_perm`` — with its
+        own variant and partition, for the deterministic backward.  Values are never cached:
+        ``spmm_csr_grad_b`` re-gathers them through ``t_perm`` on every call.
+
+    The plan is read-only to the products and holds references to ``a_crow`` / ``a_col`` so their
+    storage cannot be recycled under it."""
+
+    def __init__(self, a_crow: torch.Tensor, a_col: torch.Tensor, a_rows: int, a_cols: int, n: int,
+                 dtype: torch.dtype = torch.float32, transpose: bool = False, variant: Optional[int] = None):
+        _check_device(a_crow, a_col)
+        _chk(a_crow.dtype in _INDEX and a_col.dtype == a_crow.dtype, "a_crow / a_col must share an index dtype")
+        _chk(a_crow.numel() == a_rows + 1, "a_crow must have a_rows+1 entries")
+        _chk(dtype in _DENSE, f"dense dtype {dtype} unsupported")
+        self.a_crow, self.a_col = a_crow, a_col
+        self.rows, self.cols, self.n, self.dtype = a_rows, a_cols, int(n), dtype
+        self.nnz = int(a_col.numel())
+        self.key = (a_crow.data_ptr(), a_col.data_ptr(), a_crow._version, a_col._version, a_rows, a_cols, self.nnz)
+        self.hist = None
+        self.variant, self.part = self._build(a_crow, a_rows, self.nnz, variant)
+        self.t_crow = self.t_col = self.t_perm = self.t_part = None
+        self.t_variant = _lib.VARIANT_AUTO
+        if transpose:
+            self.t_crow, self.t_col, _, self.t_perm = csr_transpose(a_crow, a_col, None, a_rows, a_cols, want_perm=True)
+            self.t_variant, self.t_part = self._build(self.t_crow, a_cols, self.nnz, None)
+
+    def _build(self, crow, rows, nnz, variant):
+        L = _lib.lib()
+        dd = _DENSE[self.dtype]
+        with torch.cuda.device(crow.device):
+            if variant is None:
+                hist = row_hist(crow).cpu()                     # one D2H read, at plan time only
+                if self.hist is None:
+                    self.hist = hist
+                arr = (ctypes.c_int64 * 32)(*hist.tolist())
+                variant = L.ofspmm_choose_variant(arr, rows, nnz, self.n, dd)
+            nbytes = L.ofspmm_plan_bytes(rows, nnz, self.n, dd, variant)
+            part = torch.empty(nbytes, dtype=torch.uint8, device=crow.device)
+            check(L.ofspmm_plan_build(_ptr(crow), _INDEX[crow.dtype], rows, nnz, self.n, dd, variant,
+                                      part.data_ptr(), nbytes, _stream_ptr(crow)), "plan_build")
+        return variant, part
+
+    def matches(self, a_crow, a_col, a_rows, a_cols, n, dtype) -> bool:
+        return (self.key == (a_crow.data_ptr(), a_col.data_ptr(), a_crow._version, a_col._version, a_rows, a_cols,
+                             int(a_col.numel())) and self.n == int(n) and self.dtype == dtype)
+
+    def variant_name(self, transposed: bool = False) -> str:
+        v = self.t_variant if transposed else self.variant
+        r, c = (self.cols, self.rows) if transposed else (self.rows, self.cols)
+        return _lib.lib().ofspmm_variant_name(v, r, self.nnz, self.n, _DENSE[self.dtype]).decode()
+
+
+def _opts(flags: int = 0, tasks_per_warp: int = 0, variant: int = 0, part: Optional[torch.Tensor] = None,
+          bias: Optional[torch.Tensor] = None) -> OptsStruct:
+    return OptsStruct(flags, tasks_per_warp, variant, 0, part.data_ptr() if part is not None else None,
+                      part.numel() if part is not None else 0, bias.data_ptr() if bias is not None else None)
+
+
 def spmm_csr_compute(a_crow, a_col, a_val, b, a_rows: int, a_cols: int,
-                     out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """SpmmCsrKernel::Compute — out[a_rows, n] = A · b."""
-    _check_device(a_crow, a_col, a_val, b)
+                     out: Optional[torch.Tensor] = None, *, plan: Optional[SpmmPlan] = None,
+                     accumulate: bool = False, bias: Optional[torch.Tensor] = None, relu: bool = False,
+                     tasks_per_warp: int = 0, variant: Optional[int] = None, order: Optional[str] = None) -> torch.Tensor:
+    """SpmmCsrKernel::Compute — out[a_rows, n] = A · b  (``accumulate``: out += A · b; ``bias`` /
+    ``relu``: epilogue fused into the store, applied to the complete row sum).
+
+    ``plan`` supplies the histogram-chosen variant and the cached task partition; ``tasks_per_warp``
+    > 0 launches short-lived CTAs (multi-GPU overlap); ``order`` in {None, "dynamic", "static"}."""
+    _check_device(a_crow, a_col, a_val, b, bias)
     (m, n), dt = infer_spmm_csr(a_crow, a_col, a_val, b, a_rows, a_cols)
     if out is None:
+        _chk(not accumulate, "accumulate needs an `out` tensor to add to")
         out = torch.empty((m, n), dtype=dt, device=b.device)
     else:
         _chk(out.shape == (m, n) and out.dtype == dt and out.device == b.device,
              "out has the wrong shape / dtype / device")
         _check_device(out)
+    if bias is not None:
+        _chk(bias.dim() == 1 and bias.numel() == n and bias.dtype == dt and bias.is_contiguous(),
+             "bias must be a contiguous vector of n elements of the dense dtype")
+    if plan is not None:
+        _chk(plan.matches(a_crow, a_col, a_rows, a_cols, n, dt), "plan was built for another CSR structure / n / dtype")
     L = _lib.lib()
+    flags = (_lib.FWD_ACCUMULATE if accumulate else 0) | (_lib.FWD_BIAS if bias is not None else 0) | \
+            (_lib.FWD_RELU if relu else 0) | {None: 0, "dynamic": _lib.ORDER_DYNAMIC, "static": _lib.ORDER_STATIC}[order]
+    v = variant if variant is not None else (plan.variant if plan is not None else _lib.VARIANT_AUTO)
+    part = plan.part if (plan is not None and v == plan.variant) else None
     with torch.cuda.device(b.device):
         A = _csr_struct(a_crow, a_col, a_val, a_rows, a_cols)
-        nbytes = L.ofspmm_fwd_workspace_bytes(a_rows, a_cols, A.nnz, n, _DENSE[dt])
+        nbytes = L.ofspmm_fwd_ex_workspace_bytes(a_rows, a_cols, A.nnz, n, _DENSE[dt], v)
         ws, wsp = _workspace(nbytes, b.device)
         ldb = b.stride(0) if b.shape[0] > 1 else max(n, 1)
         ldc = out.stride(0) if out.shape[0] > 1 else max(n, 1)
-        if ldb == n and ldc == n:
-            rc = L.ofspmm_fwd(ctypes.byref(A), _ptr(b), _ptr(out), n, _DENSE[dt], wsp, nbytes, _stream_ptr(b))
-        else:
-            rc = L.ofspmm_fwd_strided(ctypes.byref(A), _ptr(b), ldb, _ptr(out), ldc, n, _DENSE[dt], wsp, nbytes,
-                                      _stream_ptr(b))
+        o = _opts(flags, tasks_per_warp, v, part, bias)
+        rc = L.ofspmm_fwd_ex(ctypes.byref(A), _ptr(b), ldb, _ptr(out), ldc, n, _DENSE[dt], ctypes.byref(o), wsp, nbytes,
+                             _stream_ptr(b))
         check(rc, "spmm_csr")
     return out
 
 
 def spmm_csr_grad_b_compute(a_crow, a_col, a_val, dy, a_rows: int, a_cols: int,
                             transposed: Optional[Tuple[torch.Tensor, torch.Tensor, torch.Tensor]] = None,
-                            out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """SpmmCsrGradBKernel::Compute — db[a_cols, n] = A^T · dy.  ``transposed`` = (t_crow, t_col,
-    t_val) from csr_transpose (kept in the op state) selects the deterministic route."""
+                            out: Optional[torch.Tensor] = None, *, plan: Optional[SpmmPlan] = None,
+                            atomic: bool = False, tasks_per_warp: int = 0) -> torch.Tensor:
+    """SpmmCsrGradBKernel::Compute — db[a_cols, n] = A^T · dy.  Routes, in order of preference:
+
+      * ``plan`` with a transposed structure → ``ofspmm_bwd_b_cached`` (values re-gathered through
+        ``t_perm`` each call; deterministic);
+      * ``transposed`` = (t_crow, t_col, t_val) from csr_transpose → forward kernel on that CSR;
+      * default → ``ofspmm_bwd_b_transient`` (A^T built inside the workspace; deterministic and
+        2-9x faster than the scatter on the BASELINE graphs);
+      * ``atomic=True`` → the reference-style vector-atomic scatter (order-nondeterministic)."""
     _check_device(a_crow, a_col, a_val, dy)
     _chk(dy.dim() == 2 and dy.shape[0] == a_rows, f"dy must be (a_rows={a_rows}) x n")
+    _check_packed(dy, out)
     infer_spmm_csr(a_crow, a_col, a_val, dy.new_empty((a_cols, dy.shape[1])), a_rows, a_cols)
     n, dt = int(dy.shape[1]), dy.dtype
     if out is None:
         out = torch.empty((a_cols, n), dtype=dt, device=dy.device)
+    else:
+        _chk(out.shape == (a_cols, n) and out.dtype == dt and out.device == dy.device, "out has the wrong shape / dtype / device")
     L = _lib.lib()
+    if plan is not None and plan.t_crow is not None and not atomic:
+        _chk(plan.matches(a_crow, a_col, a_rows, a_cols, n, dt), "plan was built for another CSR structure / n / dtype")
+        with torch.cuda.device(dy.device):
+            A = _csr_struct(a_crow, a_col, a_val, a_rows, a_cols)
+            vs = 4 if A.val_dtype == _lib.DTYPE_FLOAT else 2
+            nbytes = ((max(A.nnz, 1) * vs + 255) // 256) * 256 + \
+                L.ofspmm_fwd_ex_workspace_bytes(a_cols, a_rows, A.nnz, n, _DENSE[dt], plan.t_variant)
+            nbytes = max(nbytes, L.ofspmm_bwd_b_cached_workspace_bytes(a_rows, a_cols, A.nnz, n, _DENSE[dt], A.val_dtype))
+            ws, wsp = _workspace(nbytes, dy.device)
+            o = _opts(0, tasks_per_warp, plan.t_variant, plan.t_part)
+            check(L.ofspmm_bwd_b_cached(ctypes.byref(A), _ptr(plan.t_crow), _ptr(plan.t_col), _ptr(plan.t_perm),
+                                        _ptr(dy), _ptr(out), n, _DENSE[dt], ctypes.byref(o), wsp, nbytes,
+                                        _stream_ptr(dy)), "spmm_csr_grad_b(cached structure)")
+        return out
+    if transposed is None and not atomic:
+        return spmm_csr_grad_b_transient_compute(a_crow, a_col, a_val, dy, a_rows, a_cols, out=out)
     with torch.cuda.device(dy.device):
         A = _csr_struct(a_crow, a_col, a_val, a_rows, a_cols)
         At_ref = None
@@ -151,9 +266,10 @@ def spmm_csr_grad_b_compute(a_crow, a_col, a_val, dy, a_rows: int, a_cols: int,
 
 def sddmm_csr_compute(a_crow, a_col, dy, b, a_rows: int, a_cols: int,
                       val_dtype: torch.dtype = torch.float32,
-                      out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                      out: Optional[torch.Tensor] = None, *, plan: Optional[SpmmPlan] = None) -> torch.Tensor:
     """SddmmCsrKernel::Compute — dval[p] = <dy[i,:], b[col[p],:]>."""
     _check_device(a_crow, a_col, dy, b)
+    _check_packed(dy, b, out)
     infer_spmm_csr(a_crow, a_col, None, b, a_rows, a_cols)
     _chk(dy.dim() == 2 and dy.shape[0] == a_rows and dy.shape[1] == b.shape[1] and dy.dtype == b.dtype,
          "dy must be (a_rows x n) with b's dtype")
@@ -167,8 +283,9 @@ def sddmm_csr_compute(a_crow, a_col, dy, b, a_rows: int, a_cols: int,
         A = _csr_struct(a_crow, a_col, None, a_rows, a_cols, val_dtype)
         nbytes = L.ofspmm_sddmm_workspace_bytes(a_rows, a_cols, nnz, n, _DENSE[dt])
         ws, wsp = _workspace(nbytes, b.device)
-        check(L.ofspmm_sddmm(ctypes.byref(A), _ptr(dy), _ptr(b), _ptr(out), n, _DENSE[dt], wsp, nbytes,
-                             _stream_ptr(b)), "sddmm_csr")
+        o = _opts(0, 0, 0, plan.part if plan is not None else None)
+        check(L.ofspmm_sddmm_ex(ctypes.byref(A), _ptr(dy), _ptr(b), _ptr(out), n, _DENSE[dt], ctypes.byref(o), wsp, nbytes,
+                                _stream_ptr(b)), "sddmm_csr")
     return out
 
 
@@ -242,8 +359,7 @@ def spmm_csr_grad_b_transient_compute(a_crow, a_col, a_val, dy, a_rows: int, a_c
                                       out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """db = A^T · dy through route (3) of the C ABI (``ofspmm_bwd_b_transient``): A^T is built
     inside the workspace for this call only, then the forward kernel runs on it — deterministic,
-    for callers that hold no op state.  NOTE (round 1): compiled and exported, not yet exercised on
-    a GPU (the round's GPU budget was spent); ``spmm_csr_grad_b_compute`` remains the default."""
+    for callers that hold no op state (the default route of ``spmm_csr_grad_b_compute``)."""
     _check_device(a_crow, a_col, a_val, dy)
     _chk(dy.dim() == 2 and dy.shape[0] == a_rows and dy.is_contiguous(), f"dy must be contiguous (a_rows={a_rows}) x n")
     infer_spmm_csr(a_crow, a_col, a_val, dy.new_empty((a_cols, dy.shape[1])), a_rows, a_cols)
@@ -258,3 +374,38 @@ def spmm_csr_grad_b_transient_compute(a_crow, a_col, a_val, dy, a_rows: int, a_c
         check(L.ofspmm_bwd_b_transient(ctypes.byref(A), _ptr(dy), _ptr(out), n, _DENSE[dt], wsp, nbytes,
                                        _stream_ptr(dy)), "spmm_csr_grad_b(transient)")
     return out
+
+
+def gather_rows(dst: torch.Tensor, src: torch.Tensor, index: Optional[torch.Tensor] = None, index_offset: int = 0,
+                count: Optional[int] = None, max_ctas: int = 0) -> torch.Tensor:
+    """dst[i, :] = src[index[i] - index_offset, :] (index None: rows 0..count-1).  ``src`` may be a
+    peer-mapped tensor of another GPU (symmetric memory): the rows then travel over NVLink."""
+    _check_device(dst, index)
+    _chk(dst.dim() == 2 and src.dim() == 2 and dst.shape[1] == src.shape[1] and dst.dtype == src.dtype
+         and dst.dtype in _DENSE and dst.stride(1) == 1 and src.stride(1) == 1, "gather_rows: 2-D operands of one dense dtype")
+    count = int(index.numel() if index is not None else (dst.shape[0] if count is None else count))
+    _chk(count <= dst.shape[0], "gather_rows: dst has fewer rows than indices")
+    n = int(dst.shape[1])
+    with torch.cuda.device(dst.device):
+        check(_lib.lib().ofspmm_gather_rows(_ptr(dst), dst.stride(0) if dst.shape[0] > 1 else n, _ptr(src),
+                                            src.stride(0) if src.shape[0] > 1 else n, _ptr(index),
+                                            _INDEX[index.dtype] if index is not None else _lib.DTYPE_INT32, index_offset,
+                                            count, n, _DENSE[dst.dtype], max_ctas, _stream_ptr(dst)), "gather_rows")
+    return dst
+
+
+def scatter_add_rows(dst: torch.Tensor, src: torch.Tensor, index: Optional[torch.Tensor] = None, index_offset: int = 0,
+                     count: Optional[int] = None, max_ctas: int = 0) -> torch.Tensor:
+    """dst[index[i] - index_offset, :] += src[i, :] for distinct indices (no atomics; deterministic)."""
+    _check_device(dst, index)
+    _chk(dst.dim() == 2 and src.dim() == 2 and dst.shape[1] == src.shape[1] and dst.dtype == src.dtype
+         and dst.dtype in _DENSE and dst.stride(1) == 1 and src.stride(1) == 1, "scatter_add_rows: 2-D operands of one dense dtype")
+    count = int(index.numel() if index is not None else (src.shape[0] if count is None else count))
+    n = int(dst.shape[1])
+    with torch.cuda.device(dst.device):
+        check(_lib.lib().ofspmm_scatter_add_rows(_ptr(dst), dst.stride(0) if dst.shape[0] > 1 else n, _ptr(src),
+                                                 src.stride(0) if src.shape[0] > 1 else n, _ptr(index),
+                                                 _INDEX[index.dtype] if index is not None else _lib.DTYPE_INT32,
+                                                 index_offset, count, n, _DENSE[dst.dtype], max_ctas, _stream_ptr(dst)),
+              "scatter_add_rows")
+    return dst

@@ -415,20 +415,31 @@ void oracle_row_hist(const void* crow, int idx64, int64_t M, int64_t* hist32) {
 void oracle_csr_transpose(int64_t M, int64_t K, const void* crow, const void* col, const float* val,
                           int idx64, int64_t* t_crow, int64_t* t_col, float* t_val,
                           int64_t* t_perm) {
+  /* Entries whose column lies outside [0, K) are skipped by every product (segment-sum idiom,
+   * oneflow/user/kernels/unsorted_segment_sum_kernel_util.cpp:35-39).  In the transpose they keep
+   * their source order behind the last row of A^T, marked with column -1 and value 0, and
+   * t_crow[K] stays nnz so that t_crow[rows] == nnz holds for the transposed CSR too. */
   const int64_t nnz = IDX(crow, M, idx64);
   for (int64_t c = 0; c <= K; ++c) t_crow[c] = 0;
-  for (int64_t p = 0; p < nnz; ++p) t_crow[IDX(col, p, idx64) + 1] += 1;
+  for (int64_t p = 0; p < nnz; ++p) {
+    const int64_t c = IDX(col, p, idx64);
+    if (c >= 0 && c < K) t_crow[c + 1] += 1;
+  }
   for (int64_t c = 0; c < K; ++c) t_crow[c + 1] += t_crow[c];
   int64_t* cursor = (int64_t*)malloc(sizeof(int64_t) * (size_t)(K > 0 ? K : 1));
   for (int64_t c = 0; c < K; ++c) cursor[c] = t_crow[c];
+  int64_t tail = t_crow[K];
   for (int64_t i = 0; i < M; ++i) {
     const int64_t pe = IDX(crow, i + 1, idx64);
     for (int64_t p = IDX(crow, i, idx64); p < pe; ++p) {
-      const int64_t q = cursor[IDX(col, p, idx64)]++;
-      t_col[q] = i;
-      if (t_val) t_val[q] = val[p];
+      const int64_t c = IDX(col, p, idx64);
+      const int ok = c >= 0 && c < K;
+      const int64_t q = ok ? cursor[c]++ : tail++;
+      t_col[q] = ok ? i : -1;
+      if (t_val) t_val[q] = ok ? val[p] : 0.0f;
       if (t_perm) t_perm[q] = p;
     }
   }
+  if (K > 0) t_crow[K] = nnz;
   free(cursor);
 }

@@ -18,6 +18,8 @@ from oracle import oracle as O
 
 pytestmark = pytest.mark.gpu
 graphs = ofs.graphs
+ops = __import__("importlib").import_module("of-spmm_b200.ops")
+_lib = ofs._lib
 DEV = "cuda:0"
 
 
@@ -61,8 +63,10 @@ def test_golden_forward_backward_sddmm(golden):
     C = ofs.spmm_csr(crow, col, val, B, M, K)
     _assert_fp32(_np(C), g["C"], O.spmm_absmax(g["crow"], g["col"], g["val"], g["B"], K), lens, "golden fwd")
     amax_t, cnt = O.spmm_t_absmax(g["crow"], g["col"], g["val"], g["dY"], K)
-    dB_atomic = ofs.spmm_csr_grad_b(crow, col, val, dY, M, K)
+    dB_atomic = ofs.spmm_csr_grad_b(crow, col, val, dY, M, K, atomic=True)
     _assert_fp32(_np(dB_atomic), g["dB"], amax_t, cnt, "golden bwd atomic")
+    dB_default = ofs.spmm_csr_grad_b(crow, col, val, dY, M, K)            # default = transient transpose
+    _assert_fp32(_np(dB_default), g["dB"], amax_t, cnt, "golden bwd transient")
     tr = ofs.csr_transpose(crow, col, val, M, K)
     assert np.array_equal(_np(tr[0]), g["t_crow"]) and np.array_equal(_np(tr[1]), g["t_col"])
     assert np.array_equal(_np(tr[2]), g["t_val"])
@@ -180,7 +184,7 @@ def test_forward_bf16(N, bf16_vals):
 # ------------------------------------------------------------------ backward wrt B, SDDMM
 
 @pytest.mark.parametrize("N", [4, 64, 128, 130])
-@pytest.mark.parametrize("route", ["atomic", "transpose"])
+@pytest.mark.parametrize("route", ["atomic", "transpose", "transient", "plan"])
 def test_backward_b_fp32(N, route):
     A = graphs.rmat_csr(12, 16, seed=4)
     dY = graphs.upstream_grad(A.rows, N, 6)
@@ -189,13 +193,15 @@ def test_backward_b_fp32(N, route):
     amax, cnt = O.spmm_t_absmax(crow, col, val, dY.numpy(), A.cols)
     Ad = A.to(DEV)
     tr = ofs.csr_transpose(Ad.crow, Ad.col, Ad.val, A.rows, A.cols) if route == "transpose" else None
-    got = ofs.spmm_csr_grad_b(Ad.crow, Ad.col, Ad.val, dY.to(DEV), A.rows, A.cols, transposed=tr)
+    plan = ops.SpmmPlan(Ad.crow, Ad.col, A.rows, A.cols, N, torch.float32, transpose=True) if route == "plan" else None
+    kw = dict(transposed=tr, plan=plan, atomic=route == "atomic")
+    got = ofs.spmm_csr_grad_b(Ad.crow, Ad.col, Ad.val, dY.to(DEV), A.rows, A.cols, **kw)
     _assert_fp32(_np(got), dB64, amax, cnt, f"bwd_b {route} N={N}")
-    if route == "transpose":   # deterministic route: bitwise repeatable
-        assert torch.equal(got, ofs.spmm_csr_grad_b(Ad.crow, Ad.col, Ad.val, dY.to(DEV), A.rows, A.cols, transposed=tr))
+    if route != "atomic":   # deterministic routes: bitwise repeatable
+        assert torch.equal(got, ofs.spmm_csr_grad_b(Ad.crow, Ad.col, Ad.val, dY.to(DEV), A.rows, A.cols, **kw))
 
 
-@pytest.mark.parametrize("route", ["atomic", "transpose"])
+@pytest.mark.parametrize("route", ["atomic", "transpose", "transient", "plan"])
 def test_backward_b_bf16(route):
     A = graphs.products_like(512, seed=3)
     N = 256
@@ -205,7 +211,9 @@ def test_backward_b_bf16(route):
     amax, _ = O.spmm_t_absmax(crow, col, val, dY.float().numpy(), A.cols)
     Ad = A.to(DEV)
     tr = ofs.csr_transpose(Ad.crow, Ad.col, Ad.val, A.rows, A.cols) if route == "transpose" else None
-    got = ofs.spmm_csr_grad_b(Ad.crow, Ad.col, Ad.val, dY.to(DEV), A.rows, A.cols, transposed=tr)
+    plan = ops.SpmmPlan(Ad.crow, Ad.col, A.rows, A.cols, N, torch.bfloat16, transpose=True) if route == "plan" else None
+    got = ofs.spmm_csr_grad_b(Ad.crow, Ad.col, Ad.val, dY.to(DEV), A.rows, A.cols, transposed=tr, plan=plan,
+                              atomic=route == "atomic")
     _assert_bf16(got, dB64, amax, f"bwd_b bf16 {route}")
 
 
@@ -363,9 +371,11 @@ def test_full_size_reddit_properties():
     # adjoint identity
     dY = graphs.upstream_grad(A.rows, N, 23, DEV)
     lhs = (dY.double() * Ca.double()).sum()
-    dB_atomic = ofs.spmm_csr_grad_b(A.crow, A.col, A.val, dY, A.rows, A.cols)
+    dB_atomic = ofs.spmm_csr_grad_b(A.crow, A.col, A.val, dY, A.rows, A.cols, atomic=True)
     tr = ofs.csr_transpose(A.crow, A.col, A.val, A.rows, A.cols)
     dB_t = ofs.spmm_csr_grad_b(A.crow, A.col, A.val, dY, A.rows, A.cols, transposed=tr)
+    dB_tr = ofs.spmm_csr_grad_b(A.crow, A.col, A.val, dY, A.rows, A.cols)          # transient route
+    assert torch.equal(dB_t, dB_tr)
     for dB in (dB_atomic, dB_t):
         rhs = (dB.double() * B1.double()).sum()
         assert abs(float(lhs - rhs)) <= 1e-6 * float((dY.double() * Ca.double()).abs().sum())
