@@ -4,16 +4,19 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
 
 A *step* is one pass of the hot path over the workload: SpMM forward C = A·B plus the A^T·dY
-backward (BASELINE.json configs[1]: "forward + A^T·dY backward").  Workload at N=1 = configs[1]
-(Reddit-shaped synthetic graph, 232 965 nodes, ~114.6 M nnz, dense N=128 fp32).  For N>1 the same
-graph is partitioned into nnz-balanced row blocks (one per rank), B / dY row-sharded and
-all-gathered with NCCL overlapped with local compute (strong scaling: total work fixed).
+backward (BASELINE.json configs[1]: "forward + A^T·dY backward").  Default workload = configs[1]
+(Reddit-shaped synthetic graph, 232 965 nodes, ~114.6 M nnz, dense N=128 fp32); configs[2] / [3] /
+[4] are selectable with --workload.  For N>1 the same graph is partitioned into nnz-balanced row
+blocks (one per rank), B / dB row-sharded, and every rank pulls only the B rows its block touches
+out of the owners' HBM over NVLink while its local columns already compute (dist.ShardedSpmm;
+strong scaling: total work fixed).
 
 Prints ONE JSON line (rank 0).  `value` = GFLOP/s = flops of the whole job / max-over-ranks device
 time, inputs resident in HBM.  `e2e` = the same metric through the public op API with pinned HOST
-buffers, host↔device copies inside the timed region.  `roofline` is for the dominant kernel
-(spmm_merge_kernel, forward) under the gather model M2 of SURVEY.md §8d; `cpu_baseline` is the
-oracle's OneFlow-style CPU loop timed on a bounded row sample on this box's host cores.
+buffers, host<->device copies inside the timed region (max over ranks).  `roofline` is for the
+dominant kernel (spmm_merge_kernel, forward) under the gather model M2 of SURVEY.md §8d, with the
+ncu-measured DRAM and L2 bytes beside it; `cpu_baseline` is the oracle's OneFlow-style CPU loop on
+this box's host cores; `verified` says that sampled rows of the timed outputs matched the oracle.
 """
 from __future__ import annotations
 
@@ -33,14 +36,22 @@ if ROOT not in sys.path:
 
 METRIC = "SpMM GFLOP/s (2*nnz*N/t), fwd + A^T*dY"
 UNIT = "GFLOP/s"
+STEP_DESC = "forward C=A*B + backward dB=A^T*dY"
+L2_NOTE = ("inputs larger than L2 (CSR stream ~1 GB/step >> 126 MB); no flush between steps; cold-L2 forward "
+           "reported as fwd_ms_cold_l2")
+# L2 -> SM peak used for the second roofline entry: 184 L2 slices x 2 sectors/clk x 32 B x 1.964 GHz
+# (ncu: lts__lts2xbar_cycles_active peak_sustained = 2 per slice, 184 slices active, profiles/r2_ncu_*.md)
+L2_PEAK_GBS = 184 * 2 * 32 * 1.964
 
 WORKLOADS = {
-    # name: (generator kwargs, dense width, dtype)
     "cfg2_reddit_n128_fp32": dict(kind="reddit", scale_div=1, n=128, dtype="fp32"),
     "cfg3_products_n256_bf16": dict(kind="products", scale_div=1, n=256, dtype="bf16"),
     "cfg4_rmat24_n128_fp32": dict(kind="rmat", scale=24, n=128, dtype="fp32"),
     "cfg1_uniform4096_n64_fp32": dict(kind="uniform", n=64, dtype="fp32"),
+    "cfg5_gcn_reddit_h256": dict(kind="reddit", scale_div=1, n=256, dtype="fp32", gcn=True),
     "twin_reddit16_n128_fp32": dict(kind="reddit", scale_div=16, n=128, dtype="fp32"),
+    "twin_rmat18_n128_fp32": dict(kind="rmat", scale=18, n=128, dtype="fp32"),
+    "twin_gcn_reddit16_h256": dict(kind="reddit", scale_div=16, n=256, dtype="fp32", gcn=True),
 }
 
 
@@ -62,6 +73,11 @@ def _make_graph(spec, device):
     if spec["kind"] == "rmat":
         return g.rmat_csr(spec["scale"], 16, seed=4, device=device)
     return g.uniform_csr(4096, 4096, 0.01, seed=1, device=device)
+
+
+def _config(workload, A, n):
+    """Identical in both arms (ours / reference) so the driver's same_config check holds."""
+    return {"workload": workload, "rows": A.rows, "cols": A.cols, "nnz": A.nnz, "n": n, "step": STEP_DESC, "l2": L2_NOTE}
 
 
 class ClockSampler:
@@ -116,60 +132,65 @@ class ClockSampler:
         return out
 
 
-def _cpu_baseline(A, B, dY, n, seconds_target=12.0):
-    """Oracle (kind "port": the reference has no CPU SpMM kernel to compile) timed on
-    a bounded row sample of the same workload: forward with rows split equally over all host cores
-    (MultiThreadLoop + BalancedSplitter idiom) + A^T·dY with per-thread accumulators."""
-    import numpy as np
-    from oracle import oracle as O
-    try:
-        O.lib(native=True)
-        native = True
-    except Exception:
-        native = False
-    cores = os.cpu_count() or 1
-    crow_all = A.crow.cpu().numpy()
-    M = A.rows
-    Bh = B.float().cpu().numpy()
-    # probe a small sample to size the timed one
-    def run(rows):
-        p1 = int(crow_all[rows])
-        crow = crow_all[:rows + 1]
-        col = A.col[:p1].cpu().numpy()
-        val = A.val[:p1].float().cpu().numpy()
-        dYh = dY[:rows].float().cpu().numpy()
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port (kind "port": the reference has no CPU SpMM kernel to compile,
+# SURVEY.md §0.1) on all host cores
+
+class CpuArm:
+    """OneFlow-CPU-kernel-style loops (oracle/) on the FULL workload — no row-prefix extrapolation.
+    Forward: rows split equally over the host threads (MultiThreadLoop + BalancedSplitter idiom,
+    oneflow/core/thread/thread_manager.h:53-73).  A^T·dY: the same row-split loop on a CSR of A^T
+    built once outside the timed region — the CPU twin of the cached transpose our op state holds,
+    and unlike per-thread K x N accumulators it keeps scaling with the core count."""
+
+    def __init__(self, A, B, dY, n):
+        import numpy as np
+        from oracle import oracle as O
+        self.O, self.np = O, np
+        try:
+            O.lib(native=True)
+            self.native = True
+        except Exception:
+            self.native = False
+        self.cores = os.cpu_count() or 1
+        self.crow, self.col, self.val = A.crow.cpu().numpy(), A.col.cpu().numpy(), A.val.float().cpu().numpy()
+        self.B, self.dY = B.float().cpu().numpy(), dY.float().cpu().numpy()
+        self.rows, self.cols, self.nnz, self.n = A.rows, A.cols, A.nnz, n
         t0 = time.perf_counter()
-        O.spmm_f32(crow, col, val, Bh, A.cols, threads=cores, native=native)
-        O.spmm_t_f32(crow, col, val, dYh, A.cols, threads=cores, native=native)
-        return time.perf_counter() - t0, p1
-    probe_rows = max(1, min(M, M // 64))
-    t_probe, nnz_probe = run(probe_rows)
-    rate = nnz_probe / max(t_probe, 1e-6)
-    want_nnz = min(int(crow_all[-1]), int(rate * seconds_target))
-    rows = int(np.searchsorted(crow_all, want_nnz, side="right")) - 1
-    rows = max(probe_rows, min(M, rows))
-    t, nnz_s = run(rows)
-    flops = 2.0 * 2.0 * nnz_s * n
-    # the reference's default CPU_THREADING_RUNTIME is SEQ (CMakeLists.txt:54): also time the plain
-    # single-thread loop, on a 1/16 sample so the whole baseline stays within seconds
-    rows1 = max(1, rows // 16)
-    p1 = int(crow_all[rows1])
-    t0 = time.perf_counter()
-    O.spmm_f32(crow_all[:rows1 + 1], A.col[:p1].cpu().numpy(), A.val[:p1].float().cpu().numpy(), Bh, A.cols,
-               threads=1, native=native)
-    O.spmm_t_f32(crow_all[:rows1 + 1], A.col[:p1].cpu().numpy(), A.val[:p1].float().cpu().numpy(),
-                 dY[:rows1].float().cpu().numpy(), A.cols, threads=1, native=native)
-    t1 = max(time.perf_counter() - t0, 1e-9)
-    return {"value": flops / t / 1e9, "unit": UNIT, "cores": cores, "kind": "port",
-            "single_thread_value": 2.0 * 2.0 * p1 * n / t1 / 1e9,
-            "sample": f"first {rows} of {M} rows ({nnz_s} nnz), fwd (rows split over {cores} threads) + A^T*dY "
-                      f"(per-thread accumulators), {t:.2f} s, oracle built {'-march=native' if native else 'x86-64-v3'}"}
+        tc, tcol, tv, _ = O.csr_transpose(self.crow, self.col, self.val, A.cols)
+        self.t = (tc, tcol, tv)
+        self.transpose_s = time.perf_counter() - t0
+
+    def step(self, threads=None):
+        th = threads or self.cores
+        t0 = time.perf_counter()
+        self.O.spmm_f32(self.crow, self.col, self.val, self.B, self.cols, threads=th, native=self.native)
+        self.O.spmm_f32(self.t[0], self.t[1], self.t[2], self.dY, self.rows, threads=th, native=self.native)
+        return time.perf_counter() - t0
+
+    def single_thread_sample(self, frac=16):
+        """The reference's default CPU_THREADING_RUNTIME is SEQ (CMakeLists.txt:54): the plain
+        single-thread loops (forward + sequential scatter) on the first 1/frac of the rows."""
+        rows1 = max(1, self.rows // frac)
+        p1 = int(self.crow[rows1])
+        t0 = time.perf_counter()
+        self.O.spmm_f32(self.crow[:rows1 + 1], self.col[:p1], self.val[:p1], self.B, self.cols, threads=1, native=self.native)
+        self.O.spmm_t_f32(self.crow[:rows1 + 1], self.col[:p1], self.val[:p1], self.dY[:rows1], self.cols, threads=1,
+                          native=self.native)
+        return 2.0 * 2.0 * p1 * self.n / max(time.perf_counter() - t0, 1e-9) / 1e9
+
+    def describe(self, value, secs, reps):
+        return {"value": value, "unit": UNIT, "cores": self.cores, "kind": "port",
+                "sample": f"the full workload ({self.rows} rows, {self.nnz} nnz) x {reps} timed passes of {secs:.2f} s: fwd (rows "
+                          f"split over {self.cores} threads) + A^T*dY (same loop on a CSR of A^T built once outside the timed "
+                          f"region in {self.transpose_s:.1f} s, like the GPU arm's cached transpose); oracle built "
+                          f"{'-march=native' if self.native else 'x86-64-v3'}"}
 
 
 def run_reference(args):
     """--impl reference: the reference's own CPU implementation of the path.  /root/reference has
     no SpMM kernel and cannot be built offline, so this arm times the oracle
-    port (OneFlow CPU-kernel idiom) on all host cores, each step a bounded sample of the workload."""
+    port (OneFlow CPU-kernel idiom) on all host cores, every step the full workload."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -181,34 +202,98 @@ def run_reference(args):
     A = _make_graph(spec, dev)
     B = ofs.graphs.dense_operand(A.cols, n, 11, dev)
     dY = ofs.graphs.upstream_grad(A.rows, n, 12, dev)
-    per_step = max(2.0, min(12.0, 120.0 / max(1, args.steps + args.warmup)))
-    vals = []
-    base = None
-    for i in range(args.warmup + args.steps):
-        base = _cpu_baseline(A, B, dY, n, seconds_target=per_step)
-        if i >= args.warmup:
-            vals.append(base["value"])
-    v = statistics.mean(vals)
-    base["value"] = v
-    nnz = A.nnz
-    ms = 2.0 * 2.0 * nnz * n / (v * 1e9) * 1e3
+    arm = CpuArm(A, B, dY, n)
+    # bound the whole run to a few minutes whatever K and W the driver passes
+    budget, times = 150.0, []
+    t_first = arm.step()
+    warm = max(0, min(args.warmup, int(budget * 0.2 / max(t_first, 1e-3))) - 1)
+    for _ in range(warm):
+        arm.step()
+    steps = max(1, min(args.steps, int(budget * 0.8 / max(t_first, 1e-3))))
+    for _ in range(steps):
+        times.append(arm.step())
+    secs = statistics.mean(times)
+    flops = 2.0 * 2.0 * A.nnz * n
+    v = flops / secs / 1e9
+    base = arm.describe(v, secs, steps)
+    base["single_thread_value"] = arm.single_thread_sample()
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+        "warmup": args.warmup, "ms_per_step": secs * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "rows": A.rows, "cols": A.cols, "nnz": nnz, "n": n,
-                   "step": "forward C=A*B + backward dB=A^T*dY", "parallelism": f"{base['cores']} host threads",
-                   "note": "ms_per_step extrapolated from the sampled rate to the full workload"},
+        "config": _config(args.workload, A, n),
+        "impl_detail": {"parallelism": f"{arm.cores} host threads", "timed_passes": steps,
+                        "note": "every timed step is the full workload; K is clipped so the run stays within minutes"},
         "cpu_baseline": base,
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
 
+# ------------------------------------------------------------------------------------------------
+# verification of the timed outputs against the oracle (sampled rows, any size)
+
+def verify_sample(A, B_full, dY_full, C_blk, r0, r1, dB_shard, s0, s1, dtype, nsample=256, seed=7):
+    """>= nsample rows of C and of dB taken from the buffers the timed loop wrote, against the fp64
+    oracle on exactly those rows (SURVEY.md §8c tolerances).  A / B_full / dY_full are the whole
+    operands on this rank's device; C_blk = rows [r0, r1) of C, dB_shard = rows [s0, s1) of dB."""
+    import numpy as np
+    import torch
+    from oracle import oracle as O
+    g = torch.Generator().manual_seed(seed)
+    f32 = dtype == torch.float32
+    res = {}
+    # ---- C rows
+    rows = torch.unique(torch.randint(r0, r1, (nsample,), generator=g)).to(A.crow.device)
+    starts, ends = A.crow[rows].long(), A.crow[rows + 1].long()
+    lens = ends - starts
+    pos = torch.repeat_interleave(starts - torch.cumsum(lens, 0) + lens, lens) + torch.arange(int(lens.sum()), device=rows.device)
+    col = A.col[pos].long()
+    ok = (col >= 0) & (col < A.cols)
+    ucol, inv = torch.unique(col[ok], return_inverse=True)
+    mini_col = torch.full_like(col, -1)
+    mini_col[ok] = inv
+    crow = np.zeros(rows.numel() + 1, dtype=np.int64)
+    crow[1:] = np.cumsum(lens.cpu().numpy())
+    Bh = B_full[ucol].float().cpu().numpy() if ucol.numel() else np.zeros((1, B_full.shape[1]), np.float32)
+    val = A.val[pos].float().cpu().numpy()
+    want = O.spmm_f64(crow, mini_col.cpu().numpy(), val, Bh, max(1, ucol.numel()))
+    amax = O.spmm_absmax(crow, mini_col.cpu().numpy(), val, Bh, max(1, ucol.numel()))
+    got = C_blk[(rows - r0)].float().cpu().numpy().astype(np.float64)
+    tol = (O.fp32_tolerance(want, amax, np.diff(crow)) + 2.0 ** -21 * np.abs(want)) if f32 else (1e-2 * np.abs(want) + 2.0 ** -6 * amax)
+    res["C_rows"] = int(rows.numel())
+    res["C_ok"] = bool((np.abs(got - want) <= tol + 1e-30).all())
+    # ---- dB rows (= columns of A): every non-zero of the sampled columns, over the whole matrix
+    cols_s = torch.unique(torch.randint(s0, max(s0 + 1, s1), (nsample,), generator=g)).to(A.crow.device)
+    hit = torch.isin(A.col, cols_s.to(A.col.dtype))
+    p = torch.nonzero(hit).flatten()
+    r_of = torch.searchsorted(A.crow.long(), p, right=True) - 1
+    c_of = torch.searchsorted(cols_s, A.col[p].long())
+    order = torch.argsort(c_of * (A.rows + 1) + r_of)
+    p, r_of, c_of = p[order], r_of[order], c_of[order]
+    urow, inv = torch.unique(r_of, return_inverse=True)
+    tcrow = np.zeros(cols_s.numel() + 1, dtype=np.int64)
+    tcrow[1:] = np.cumsum(torch.bincount(c_of, minlength=cols_s.numel()).cpu().numpy())
+    dYh = dY_full[urow].float().cpu().numpy() if urow.numel() else np.zeros((1, dY_full.shape[1]), np.float32)
+    tval = A.val[p].float().cpu().numpy()
+    want = O.spmm_f64(tcrow, inv.cpu().numpy(), tval, dYh, max(1, urow.numel()))
+    amax = O.spmm_absmax(tcrow, inv.cpu().numpy(), tval, dYh, max(1, urow.numel()))
+    got = dB_shard[(cols_s - s0)].float().cpu().numpy().astype(np.float64)
+    tol = (O.fp32_tolerance(want, amax, np.diff(tcrow)) + 2.0 ** -20 * np.abs(want)) if f32 else (1e-2 * np.abs(want) + 2.0 ** -5 * amax)
+    res["dB_rows"] = int(cols_s.numel())
+    res["dB_ok"] = bool((np.abs(got - want) <= tol + 1e-30).all())
+    res["ok"] = res["C_ok"] and res["dB_ok"]
+    return res
+
+
+# ------------------------------------------------------------------------------------------------
+# e2e: host buffers in, host buffers out, copies inside the timed region
+
 def _e2e_pipelined(args, ofs, ops, A, B, dY, n, dtype, dev, flops_step, blocks=8):
-    """EXPERIMENTAL (--e2e-mode pipelined; not yet validated on a GPU in round 1): stream the CSR to
-    the device in nnz-balanced row blocks so the H2D copy of block i+1 overlaps the forward of block
-    i and the D2H of block i-1; A^T·dY runs once the whole CSR and dY have arrived (transient
-    transpose route).  Same bytes per step as the simple mode."""
+    """The CSR is streamed to the device in nnz-balanced row blocks (host twin of the partitioner);
+    as soon as block i has landed, its forward rows C[r0:r1] = A_i·B and its contribution
+    dB += A_i^T·dY_i (device transpose of the block, then the forward kernel in accumulate mode)
+    run while block i+1 is still on the PCIe bus, and C blocks / dB go back on a third stream.
+    Fresh inputs every step: nothing about the graph is cached across steps."""
     import torch
     host = {k: v.cpu().pin_memory() for k, v in dict(crow=A.crow, col=A.col, val=A.val, B=B, dY=dY).items()}
     C_h = torch.empty((A.rows, n), dtype=dtype).pin_memory()
@@ -229,6 +314,7 @@ def _e2e_pipelined(args, ofs, ops, A, B, dY, n, dtype, dev, flops_step, blocks=8
         ev_in, ev_c = [], []
         with torch.cuda.stream(s_in):
             d["B"].copy_(host["B"], non_blocking=True)
+            d["dY"].copy_(host["dY"], non_blocking=True)
             for i in range(blocks):
                 r0, r1, p0, p1 = bounds[i], bounds[i + 1], offs[i], offs[i + 1]
                 d["crow"][r0:r1 + 1].copy_(host["crow"][r0:r1 + 1], non_blocking=True)
@@ -237,26 +323,25 @@ def _e2e_pipelined(args, ofs, ops, A, B, dY, n, dtype, dev, flops_step, blocks=8
                 e = torch.cuda.Event()
                 e.record(s_in)
                 ev_in.append(e)
-            d["dY"].copy_(host["dY"], non_blocking=True)
-            ev_dy = torch.cuda.Event()
-            ev_dy.record(s_in)
+        first = True
         for i in range(blocks):
             r0, r1, p0, p1 = bounds[i], bounds[i + 1], offs[i], offs[i + 1]
             cur.wait_event(ev_in[i])
             if r1 > r0:
                 crow_blk = d["crow"][r0:r1 + 1] - d["crow"][r0:r0 + 1]
-                ops.spmm_csr_compute(crow_blk, d["col"][p0:p1], d["val"][p0:p1], d["B"], r1 - r0, A.cols, out=C_d[r0:r1])
-            e = torch.cuda.Event()
-            e.record(cur)
-            ev_c.append(e)
-        cur.wait_event(ev_dy)
-        ops.spmm_csr_grad_b_transient_compute(d["crow"], d["col"], d["val"], d["dY"], A.rows, A.cols, out=dB_d)
+                col_blk, val_blk = d["col"][p0:p1], d["val"][p0:p1]
+                ops.spmm_csr_compute(crow_blk, col_blk, val_blk, d["B"], r1 - r0, A.cols, out=C_d[r0:r1])
+                e = torch.cuda.Event()
+                e.record(cur)
+                ev_c.append((e, r0, r1))
+                t = ops.csr_transpose(crow_blk, col_blk, val_blk, r1 - r0, A.cols)
+                ops.spmm_csr_compute(t[0], t[1], t[2], d["dY"][r0:r1], A.cols, r1 - r0, out=dB_d, accumulate=not first)
+                first = False
         ev_b = torch.cuda.Event()
         ev_b.record(cur)
         with torch.cuda.stream(s_out):
-            for i in range(blocks):
-                r0, r1 = bounds[i], bounds[i + 1]
-                s_out.wait_event(ev_c[i])
+            for e, r0, r1 in ev_c:
+                s_out.wait_event(e)
                 C_h[r0:r1].copy_(C_d[r0:r1], non_blocking=True)
             s_out.wait_event(ev_b)
             dB_h.copy_(dB_d, non_blocking=True)
@@ -273,15 +358,50 @@ def _e2e_pipelined(args, ofs, ops, A, B, dY, n, dtype, dev, flops_step, blocks=8
     b.record()
     torch.cuda.synchronize()
     e2e_ms = a.elapsed_time(b) / k
-    return {"value": flops_step / (e2e_ms * 1e-3) / 1e9, "unit": UNIT, "h2d_bytes_per_step": h2d,
-            "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms,
-            "path": f"pinned host -> device in {blocks} nnz-balanced row blocks on a copy stream, forward per block as "
-                    "it lands, A^T*dY via transient transpose, C blocks / dB -> pinned host on a third stream"}
+    return ({"value": flops_step / (e2e_ms * 1e-3) / 1e9, "unit": UNIT, "h2d_bytes_per_step": h2d,
+             "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms,
+             "path": f"pinned host -> device in {blocks} nnz-balanced row blocks on a copy stream; per block, as it lands: "
+                     "ofs spmm_csr (C rows) and csr_transpose + spmm_csr(accumulate) (dB += A_i^T*dY_i); C blocks / dB -> "
+                     "pinned host on a third stream; nothing cached across steps"}, C_h, dB_h)
+
+
+def _e2e_plugin_fwd(args, ofs, A, B, n, dtype, dev):
+    """Forward only, through the C-ABI entry a host-tensor caller binds: ofspmm_fwd_host (host
+    pointers in, host pointers out, staging carved from a caller-owned device workspace)."""
+    import ctypes
+    import torch
+    L = ofs._lib.lib()
+    crow, col, val, Bp = (t.cpu().pin_memory() for t in (A.crow, A.col, A.val, B))
+    C_h = torch.empty((A.rows, n), dtype=dtype).pin_memory()
+    dd = 2 if dtype == torch.float32 else 11
+    cs = ofs._lib.CsrStruct(A.rows, A.cols, A.nnz, crow.data_ptr(), col.data_ptr(), val.data_ptr(), 5, 2)
+    nbytes = L.ofspmm_fwd_host_workspace_bytes(A.rows, A.cols, A.nnz, n, dd, 5, 2)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def run():
+        rc = L.ofspmm_fwd_host(ctypes.byref(cs), Bp.data_ptr(), C_h.data_ptr(), n, dd, ws.data_ptr(), nbytes, stream)
+        assert rc == 0, rc
+    for _ in range(2):
+        run()
+    torch.cuda.synchronize()
+    k = 5
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(k):
+        run()
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / k
+    h2d = sum(t.numel() * t.element_size() for t in (crow, col, val, Bp))
+    return {"value": 2.0 * A.nnz * n / (ms * 1e-3) / 1e9, "unit": "GFLOP/s (forward only)", "ms_per_call": ms,
+            "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": C_h.numel() * C_h.element_size(),
+            "path": "ofspmm_fwd_host (C ABI): pinned host CSR + B -> device staging in the workspace, ofspmm_fwd, C -> pinned host"}
 
 
 def _teardown(world):
     """Leave the process group without ever hanging the launcher: a watchdog force-exits if NCCL
-    teardown does not return (seen after CUDA-graph capture of collectives)."""
+    teardown does not return."""
     if world <= 1:
         return
     import torch.distributed as dist
@@ -308,21 +428,19 @@ def main():
     ap.add_argument("--workload", default="cfg2_reddit_n128_fp32", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--bwd", default="transpose", choices=["transpose", "atomic"])
-    ap.add_argument("--e2e-mode", default="simple", choices=["simple", "pipelined"],
-                    help="pipelined = experimental row-block streaming of the CSR (see _e2e_pipelined)")
-    ap.add_argument("--graph", action="store_true",
-                    help="N>1: replay the sharded step from a CUDA graph (experimental: measured no faster than eager "
-                         "on 8 B200s, and NCCL teardown after capture can hang — off by default)")
-    ap.add_argument("--comm", default="nccl", choices=["nccl", "peer"],
-                    help="N>1: NCCL all-gather / reduce-scatter kernels, or copy-engine pulls over symmetric (peer) memory")
-    ap.add_argument("--panels", type=int, default=1,
-                    help="N>1: column panels used to pipeline a collective with its own product (1 = whole width; the "
-                         "collectives then overlap with the other product of the step)")
+    ap.add_argument("--no-verify", action="store_true")
+    ap.add_argument("--scheme", default="pull", choices=["pull", "allgather"],
+                    help="N>1: needed-rows pull over peer memory (default) or round 1's all-gather / reduce-scatter")
+    ap.add_argument("--buckets", type=int, default=1, help="N>1, pull: remote column buckets (accumulate passes)")
+    ap.add_argument("--tasks-per-warp", type=int, default=4, help="N>1: CTAs of the overlapped products retire after k tasks")
+    ap.add_argument("--pull-ctas", type=int, default=32, help="N>1, pull: grid cap of the peer-pull kernels")
     args = ap.parse_args()
     args.warmup = max(3, args.warmup)
     if args.impl == "reference":
         return run_reference(args)
+    if WORKLOADS[args.workload].get("gcn"):
+        import bench_gcn
+        return bench_gcn.main(args)
 
     import torch
     import ofspmm_b200 as ofs
@@ -339,7 +457,6 @@ def main():
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         # a multi-rank run that stops making progress must not hold the box: hard exit after 5 min
-        # (a healthy run takes well under one)
         wd = threading.Timer(300.0, lambda: os._exit(2))
         wd.daemon = True
         wd.start()
@@ -354,38 +471,49 @@ def main():
     s_dense = 4 if dtype == torch.float32 else 2
     alg = ofs.graphs.expected_alg_bytes(A.rows, A.cols, A.nnz, n, s_dense)
     flops_step = 2.0 * alg["flop"]      # forward + A^T·dY
+    detail = {}
 
     if world > 1:
         dmod = __import__("importlib").import_module("of-spmm_b200.dist")
-        runner = dmod.ShardedSpmm(A, n, dtype, rank, world, dev, bwd=args.bwd, panels=args.panels, comm=args.comm)
+        if args.scheme == "pull":
+            runner = dmod.ShardedSpmm(A, n, dtype, rank, world, dev, buckets=args.buckets,
+                                      tasks_per_warp=args.tasks_per_warp, pull_ctas=args.pull_ctas)
+            xb = runner.exchange_bytes()
+            detail["exchange"] = {"pulled_bytes_per_product_rank0": xb["pulled"], "all_gather_bytes_per_product": xb["all_gather"],
+                                  "local_nnz_fraction_rank0": round(xb["local_nnz_fraction"], 4)}
+            parallelism = (f"row-block x{world} (nnz-balanced whole rows), B/dB row-sharded; needed-rows exchange over peer "
+                           f"memory (comm={runner.comm}): local columns compute while {args.buckets} remote bucket(s) are pulled "
+                           f"with ofspmm_gather_rows, then accumulate passes; dB partials pulled + added in rank order")
+        else:
+            runner = dmod.AllGatherSpmm(A, n, dtype, rank, world, dev, tasks_per_warp=args.tasks_per_warp or 2)
+            parallelism = (f"row-block x{world}, round-1 scheme: ncclAllGather(B) overlapped with A^T*dY, ncclReduceScatter(dB) "
+                           f"overlapped with A*B (comm={runner.comm})")
         B_in, dY_in = runner.shard_rows(B), runner.shard_rows_out(dY)
-        step_eager = lambda: runner.step(B_in, dY_in)
-        l0 = ofs.launch_count()
-        step_eager()
-        graph_launches_per_step = ofs.launch_count() - l0
-        if not args.graph:
-            step, fwd_only = step_eager, (lambda: runner.forward(B_in))
-        else:  # one CUDA graph per step: kernels + copies + NCCL collectives, no host launch gaps
-            step = runner.capture(step_eager)
-            fwd_only = runner.capture(lambda: runner.forward(B_in))
-        parallelism = (f"row-block x{world} (nnz-balanced whole rows), B/dB row-sharded, comm={runner.comm}, "
-                       f"{runner.panels} column panel(s), all-gather(B) overlapped with A^T*dY and reduce-scatter(dB) "
-                       f"overlapped with A*B, " + ("CUDA-graph replay" if args.graph else "eager launches"))
+        step = lambda: runner.step(B_in, dY_in)
+        fwd_only = lambda: runner.forward(B_in)
+        plan_ms = None
+        r0, r1, s0, s1 = runner.r0, runner.r1, runner.lo, runner.hi
+        outputs = lambda: (runner._c, runner._db)
     else:
         t0 = time.perf_counter()
-        tr = ops.csr_transpose(A.crow, A.col, A.val, A.rows, A.cols) if args.bwd == "transpose" else None
+        plan = ops.SpmmPlan(A.crow, A.col, A.rows, A.cols, n, dtype, transpose=True)   # op state: built once
         torch.cuda.synchronize()
         plan_ms = (time.perf_counter() - t0) * 1e3
         C = torch.empty((A.rows, n), dtype=dtype, device=dev)
         dB = torch.empty((A.cols, n), dtype=dtype, device=dev)
 
         def fwd_only():
-            ops.spmm_csr_compute(A.crow, A.col, A.val, B, A.rows, A.cols, out=C)
+            ops.spmm_csr_compute(A.crow, A.col, A.val, B, A.rows, A.cols, out=C, plan=plan)
 
         def step():
-            ops.spmm_csr_compute(A.crow, A.col, A.val, B, A.rows, A.cols, out=C)
-            ops.spmm_csr_grad_b_compute(A.crow, A.col, A.val, dY, A.rows, A.cols, transposed=tr, out=dB)
+            ops.spmm_csr_compute(A.crow, A.col, A.val, B, A.rows, A.cols, out=C, plan=plan)
+            ops.spmm_csr_grad_b_compute(A.crow, A.col, A.val, dY, A.rows, A.cols, out=dB, plan=plan)
         parallelism = "single GPU"
+        detail["variant"] = {"forward": plan.variant_name(), "backward (forward kernel on A^T)": plan.variant_name(True),
+                             "chosen_from": "row-length histogram (ofspmm_row_hist -> ofspmm_choose_variant), plan built once",
+                             "row_hist_log2": [int(x) for x in plan.hist.tolist()[:24]]}
+        r0, r1, s0, s1 = 0, A.rows, 0, A.cols
+        outputs = lambda: (C, dB)
 
     def barrier():
         if world > 1:
@@ -411,8 +539,11 @@ def main():
     barrier()
     total_ms = ev[0].elapsed_time(ev[1])
     launches = ofs.launch_count() - launches0
-    if world > 1 and args.graph and launches == 0:
-        launches = graph_launches_per_step * args.steps   # replayed from the captured graph
+    # ---- the timed outputs are what gets verified (sampled rows vs the fp64 oracle)
+    verified = None
+    if not args.no_verify:
+        c_out, db_out = outputs()
+        verified = verify_sample(A, B, dY, c_out, r0, r1, db_out, s0, s1, dtype)
     # dominant kernel (forward): its own CUDA-event loop right after, same residency / clocks
     for i in range(args.steps):
         fwd_ev[i][0].record()
@@ -422,11 +553,12 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     fwd_ms = statistics.mean(a.elapsed_time(b) for a, b in fwd_ev)
 
-    t = torch.tensor([total_ms, fwd_ms], dtype=torch.float64, device=dev)
+    ok_flag = 1.0 if (verified is None or verified["ok"]) else 0.0
+    t = torch.tensor([total_ms, fwd_ms, -ok_flag], dtype=torch.float64, device=dev)
     if world > 1:
         import torch.distributed as dist
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms, fwd_ms = float(t[0]), float(t[1])
+    total_ms, fwd_ms, all_ok = float(t[0]), float(t[1]), float(t[2]) == -1.0
     ms_per_step = total_ms / args.steps
     value = flops_step / (ms_per_step * 1e-3) / 1e9
 
@@ -440,44 +572,24 @@ def main():
         torch.cuda.synchronize()
         cold.append(a.elapsed_time(b))
     del flush
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
 
-    # ---- e2e through the public op API with pinned host buffers (N=1 path; per rank for N>1)
-    e2e = None
-    if not args.no_e2e and world == 1 and args.e2e_mode == "pipelined":
-        e2e = _e2e_pipelined(args, ofs, ops, A, B, dY, n, dtype, dev, flops_step)
-    elif not args.no_e2e and world == 1:
-        host = {k: v.cpu().pin_memory() for k, v in dict(crow=A.crow, col=A.col, val=A.val, B=B, dY=dY).items()}
-        C_h = torch.empty((A.rows, n), dtype=dtype).pin_memory()
-        dB_h = torch.empty((A.cols, n), dtype=dtype).pin_memory()
-        h2d = sum(v.numel() * v.element_size() for v in host.values())
-        d2h = C_h.numel() * C_h.element_size() + dB_h.numel() * dB_h.element_size()
-
-        def e2e_step():
-            d = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
-            c = ofs.spmm_csr(d["crow"], d["col"], d["val"], d["B"], A.rows, A.cols)
-            g = ofs.spmm_csr_grad_b(d["crow"], d["col"], d["val"], d["dY"], A.rows, A.cols)
-            C_h.copy_(c, non_blocking=True)
-            dB_h.copy_(g, non_blocking=True)
-        for _ in range(3):
-            e2e_step()
-        torch.cuda.synchronize()
-        k = max(3, min(args.steps, 10))
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        for _ in range(k):
-            e2e_step()
-        b.record()
-        torch.cuda.synchronize()
-        e2e_ms = a.elapsed_time(b) / k
-        e2e = {"value": flops_step / (e2e_ms * 1e-3) / 1e9, "unit": UNIT, "h2d_bytes_per_step": h2d,
-               "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms,
-               "path": "pinned host -> device copies, ofs.spmm_csr + ofs.spmm_csr_grad_b (atomic route: no cached "
-                       "transpose for fresh inputs), device -> pinned host"}
-
+    # ---- e2e: pinned host buffers in and out, copies inside the timed region
+    e2e, e2e_plugin = None, None
+    if not args.no_e2e and world == 1:
+        e2e, C_h, dB_h = _e2e_pipelined(args, ofs, ops, A, B, dY, n, dtype, dev, flops_step)
+        if not args.no_verify:   # what came back to the host is checked too
+            ve = verify_sample(A, B, dY, C_h.to(dev), 0, A.rows, dB_h.to(dev), 0, A.cols, dtype, seed=9)
+            e2e["verified"] = ve["ok"]
+        del C_h, dB_h
+        if dtype == torch.float32:
+            e2e_plugin = _e2e_plugin_fwd(args, ofs, A, B, n, dtype, dev)
     if not args.no_e2e and world > 1:
-        # per-rank e2e: this rank's CSR block, B shard and dY block come from pinned host memory every
-        # step and its C block / dB shard go back; the sharded step itself is the one timed above.
-        # Never let a failure here cost the scaling numbers.
+        # per rank: its CSR row block, B shard and dY block come from pinned host memory every step and
+        # its C block / dB shard go back; time = max over ranks, bytes = sum over ranks.  Never let a
+        # failure here cost the scaling numbers.
         try:
             import torch.distributed as dist
             blk = runner.A_blk
@@ -491,29 +603,33 @@ def main():
             def e2e_step():
                 for key, src in host.items():
                     dst[key].copy_(src, non_blocking=True)
+                if hasattr(runner, "update_values"):
+                    runner.update_values(blk.val)          # the freshly copied values reach every sub-CSR
                 c, g = runner.step(B_in, dY_in)
                 C_h.copy_(c, non_blocking=True)
                 dB_h.copy_(g, non_blocking=True)
-            # no extra collectives in this section (only the ones inside runner.step, issued the
-            # same number of times by every rank): a rank-local failure can then never deadlock.
             for _ in range(3):
                 e2e_step()
             torch.cuda.synchronize()
             k = max(3, min(args.steps, 10))
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            dist.barrier()
+            torch.cuda.synchronize()
             a.record()
             for _ in range(k):
                 e2e_step()
             b.record()
             torch.cuda.synchronize()
-            e2e_ms = a.elapsed_time(b) / k
-            tt = [e2e_ms, float(h2d) * world, float(d2h) * world]
+            tt = torch.tensor([a.elapsed_time(b) / k, float(h2d), float(d2h)], dtype=torch.float64, device=dev)
+            mx = tt.clone()
+            dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+            dist.all_reduce(tt, op=dist.ReduceOp.SUM)
+            e2e_ms = float(mx[0])
             e2e = {"value": flops_step / (e2e_ms * 1e-3) / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(tt[1]),
                    "d2h_bytes_per_step": int(tt[2]), "ms_per_step": e2e_ms,
-                   "path": "per rank: pinned host -> device copies of its CSR row block, B shard and dY block, "
-                           "ShardedSpmm.step (cached transpose of the block: the graph is static across steps), "
-                           "C block and dB shard -> pinned host; time = rank 0's device time of the collective step (the "
-                           "collectives inside it synchronise the ranks), bytes = rank 0's x world (nnz-balanced blocks)"}
+                   "path": "per rank: pinned host -> device copies of its CSR row block (values re-split into the sub-CSRs), "
+                           "B shard and dY block, the sharded step (structure plans cached: the graph is static across "
+                           "steps), C block and dB shard -> pinned host; time = max over ranks, bytes = sum over ranks"}
         except Exception as exc:  # pragma: no cover
             e2e = {"value": None, "unit": UNIT, "h2d_bytes_per_step": None, "d2h_bytes_per_step": None,
                    "error": repr(exc)[:200]}
@@ -525,43 +641,61 @@ def main():
     peak, peak_src = _peaks()
     fwd_bytes = alg["m2"] if world == 1 else alg["m2"] / world
     achieved = fwd_bytes / (fwd_ms * 1e-3) / 1e9
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")   # written by hand from the ncu --set full capture
-    if os.path.exists(tpath):
+    traffic, l2_entry = None, None
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")   # written by tools/ncu_summary.py from ncu --set full reports
+    if world == 1 and os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get(args.workload)
+            rec = json.load(open(tpath)).get(args.workload, {}).get("fwd")
+            if rec:
+                traffic = rec["dram_bytes"]
+                l2_gbs = rec["l2_bytes"] / (fwd_ms * 1e-3) / 1e9
+                l2_entry = {"bound": "l2", "achieved": l2_gbs, "peak": L2_PEAK_GBS, "unit": "GB/s", "frac": l2_gbs / L2_PEAK_GBS,
+                            "traffic": rec["l2_bytes"], "kernel": rec["kernel"],
+                            "peak_source": "ncu: 184 L2 slices x 2 sectors/clk x 32 B x 1.964 GHz (lts__lts2xbar peak_sustained)",
+                            "dram_frac_of_measured_peak": rec["dram_bytes"] / (fwd_ms * 1e-3) / 1e9 / peak,
+                            "l2_hit_pct": rec.get("l2_hit_pct"), "ncu_capture": rec.get("tag")}
         except Exception:
             traffic = None
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32" if dtype == torch.float32 else "bf16", "data": "synthetic",
-        "config": {"workload": args.workload, "rows": A.rows, "cols": A.cols, "nnz": A.nnz, "n": n,
-                   "step": "forward C=A*B + backward dB=A^T*dY (" + args.bwd + " route)", "parallelism": parallelism,
-                   "l2": "inputs larger than L2 (CSR stream 0.9 GB/step >> 126 MB); no flush between steps; "
-                         "cold-L2 forward reported as fwd_ms_cold_l2",
-                   "variant": ofs._lib.lib().ofspmm_fwd_variant(A.rows, A.nnz, n, 2 if dtype == torch.float32 else 11).decode()},
+        "config": _config(args.workload, A, n),
+        "impl_detail": dict(parallelism=parallelism, **detail),
         "fwd_ms": fwd_ms, "fwd_ms_cold_l2": statistics.mean(cold) if cold else None,
         "fwd_gflops": alg["flop"] / (fwd_ms * 1e-3) / 1e9,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "kernel": "spmm_merge_kernel (forward)", "peak_source": peak_src,
                      "model": "M2 gather model: nnz*(idx+val) + (M+1)*idx + nnz*N*s + M*N*s bytes per launch "
                               "(SURVEY.md 8d); B-row gathers are mostly L2 hits, so achieved may exceed the HBM copy "
-                              "peak - see traffic (ncu dram bytes) and DESIGN.md",
+                              "peak - `traffic` is the DRAM bytes ncu measured for one launch, roofline_l2 the resource "
+                              "that binds when frac > 1",
                      "frac_of_nominal_8tbs": achieved / 8000.0,
                      "alg_bytes": fwd_bytes, "m1_compulsory_bytes": alg["m1"],
                      "m1_gbs": alg["m1"] / (fwd_ms * 1e-3) / 1e9 / max(1, world)},
         "gpu_launches": int(launches),
         "clocks": clocks,
+        "verified": bool(all_ok) if verified is not None else None,
+        "verified_detail": verified,
         "reference_cuda_path": "n/a: the reference snapshot has no SpMM kernel and OneFlow does not build offline "
                                "(SURVEY.md 0.1-0.2); the CPU arm is `bench.py --impl reference`",
     }
-    if world == 1:
+    if l2_entry is not None:
+        out["roofline_l2"] = l2_entry
+    if plan_ms is not None:
         out["plan_ms_one_off"] = plan_ms
     if e2e is not None:
         out["e2e"] = e2e
+    if e2e_plugin is not None:
+        out["e2e_plugin_fwd"] = e2e_plugin
     if not args.no_cpu_baseline and world == 1:
-        out["cpu_baseline"] = _cpu_baseline(A, B, dY, n)
+        arm = CpuArm(A, B, dY, n)
+        arm.step()
+        ts = [arm.step() for _ in range(3)]
+        secs = statistics.mean(ts)
+        base = arm.describe(flops_step / secs / 1e9, secs, len(ts))
+        base["single_thread_value"] = arm.single_thread_sample()
+        out["cpu_baseline"] = base
     print(json.dumps(out), flush=True)
     _teardown(world)
 

@@ -108,7 +108,6 @@ enum {
   OFSPMM_VARIANT_ITEMS64 = 1,  /* 64 merge items per warp task (small problems: 4x more warps)      */
   OFSPMM_VARIANT_ROWPAR = 2,   /* sub-warp per row instead of nnz-parallel groups (short rows x
                                   narrow dense operand)                                              */
-  OFSPMM_VARIANT_UNROLL8 = 4,  /* eight B-row gathers in flight per lane group (long rows, fp32)     */
   OFSPMM_VARIANT_EXPLICIT = 0x100
 };
 
@@ -205,6 +204,12 @@ OFSPMM_API int ofspmm_bwd_b_cached(const ofspmm_csr* A, const void* t_crow, cons
                                    const void* t_perm, const void* dY, void* dB, int64_t n,
                                    int dense_dtype, const ofspmm_opts* opts, void* workspace,
                                    size_t workspace_bytes, ofspmm_stream_t stream);
+
+/* out[q] = val[perm[q]]: the values of A^T from the values of A (perm = t_perm of
+ * ofspmm_csr_transpose).  What ofspmm_bwd_b_cached runs internally; exported for callers that can
+ * prove the values unchanged between calls (e.g. a tensor version counter) and keep t_val. */
+OFSPMM_API int ofspmm_permute_values(const void* val, int val_dtype, const void* perm, int idx_dtype,
+                                     int64_t nnz, void* out, ofspmm_stream_t stream);
 
 /* ---- SDDMM value gradient: dval[p] = <dY[i,:], B[col[p],:]> for every stored entry p of row i
  * (replaces `sddmm_csr`; no reference analogue).  dval has `val_dtype` of A

@@ -24,12 +24,12 @@ EXPORTS = (
     "ofspmm_launch_count", "ofspmm_fwd_variant", "ofspmm_variant_name",
     "ofspmm_fwd_ex_workspace_bytes", "ofspmm_fwd_ex", "ofspmm_plan_bytes", "ofspmm_plan_build",
     "ofspmm_choose_variant", "ofspmm_bwd_b_cached_workspace_bytes", "ofspmm_bwd_b_cached", "ofspmm_sddmm_ex",
-    "ofspmm_gather_rows", "ofspmm_scatter_add_rows",
+    "ofspmm_gather_rows", "ofspmm_scatter_add_rows", "ofspmm_permute_values",
 )
 
 # ofspmm_opts.flags / variant codes (include/ofspmm.h)
 FWD_ACCUMULATE, FWD_BIAS, FWD_RELU, ORDER_DYNAMIC, ORDER_STATIC = 1, 2, 4, 8, 16
-VARIANT_AUTO, VARIANT_ITEMS64, VARIANT_ROWPAR, VARIANT_UNROLL8, VARIANT_EXPLICIT = 0, 1, 2, 4, 0x100
+VARIANT_AUTO, VARIANT_ITEMS64, VARIANT_ROWPAR, VARIANT_EXPLICIT = 0, 1, 2, 0x100
 
 
 class OfspmmLibraryError(ImportError):
@@ -131,6 +131,8 @@ def lib() -> ctypes.CDLL:
     L.ofspmm_bwd_b_cached.restype = i32
     L.ofspmm_sddmm_ex.argtypes = [csr_p, vp, vp, vp, i64, i32, opts_p, vp, sz, vp]
     L.ofspmm_sddmm_ex.restype = i32
+    L.ofspmm_permute_values.argtypes = [vp, i32, vp, i32, i64, vp, vp]
+    L.ofspmm_permute_values.restype = i32
     L.ofspmm_gather_rows.argtypes = [vp, i64, vp, i64, vp, i32, i64, i64, i64, i32, i32, vp]
     L.ofspmm_gather_rows.restype = i32
     L.ofspmm_scatter_add_rows.argtypes = [vp, i64, vp, i64, vp, i32, i64, i64, i64, i32, i32, vp]

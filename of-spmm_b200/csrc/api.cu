@@ -14,12 +14,20 @@ std::atomic<uint64_t> g_launches{0};
 int get_dev_info(DevInfo* out) {
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return OFSPMM_ERR_NO_DEVICE;
-  int sms = 0, major = 0;
-  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return OFSPMM_ERR_CUDA;
-  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return OFSPMM_ERR_CUDA;
-  if (major != 10) return OFSPMM_ERR_NO_DEVICE;  // the library carries sm_100a code only
-  out->sms = sms;
-  out->cc_major = major;
+  // SM count / compute capability per device ordinal: immutable, memoised (sms << 8 | major)
+  static std::atomic<int> memo[KernelLaunchCache::kMaxDevices];
+  int packed = dev >= 0 && dev < KernelLaunchCache::kMaxDevices ? memo[dev].load(std::memory_order_relaxed) : 0;
+  if (packed == 0) {
+    int sms = 0, major = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return OFSPMM_ERR_CUDA;
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return OFSPMM_ERR_CUDA;
+    packed = (sms << 8) | (major & 0xff);
+    if (dev >= 0 && dev < KernelLaunchCache::kMaxDevices) memo[dev].store(packed, std::memory_order_relaxed);
+  }
+  if ((packed & 0xff) != 10) return OFSPMM_ERR_NO_DEVICE;  // the library carries sm_100a code only
+  out->sms = packed >> 8;
+  out->cc_major = packed & 0xff;
+  out->ordinal = dev;
   return OFSPMM_OK;
 }
 
@@ -172,27 +180,18 @@ int ofspmm_plan_build(const void* crow, int idx_dtype, int64_t rows, int64_t nnz
 int ofspmm_choose_variant(const int64_t* hist32_host, int64_t rows, int64_t nnz, int64_t n, int dense_dtype) {
   FwdVariant v = resolve_variant(OFSPMM_VARIANT_AUTO, rows, nnz, n, dense_dtype);
   if (hist32_host == nullptr || rows <= 0 || nnz <= 0 || v.items == kSmallTaskItems) return encode_variant(v);
-  // nnz-weighted view of the log2 histogram: bucket b holds rows of 2^(b-1) <= len < 2^b, which
-  // carry about count * 0.75 * 2^b non-zeros.
-  double w_total = 0, w_long = 0, w_short = 0;
+  // Row-parallel groups (each 8 / 16-lane group owns whole rows, 4 / 2 rows in flight per warp)
+  // against nnz-parallel groups (every group works on every row): measured on B200 at N = 32 / 64
+  // fp32, the row-parallel layout wins 10-20 % on R-MAT (median row length 0-1, 90 % of the rows
+  // under 16 non-zeros) and loses 5 % on products-shaped (median 32-63) and 60 % on Reddit-shaped
+  // rows (median 256-511), where one long row piece leaves three of four groups idle
+  // (profiles/r2_variant_sweeps.md).  Criterion: the MEDIAN row, empty rows included, has fewer
+  // than 16 non-zeros, i.e. the per-row work dominates the per-non-zero work.
   const int64_t vecw = dense_dtype == OFSPMM_DTYPE_BFLOAT16 ? 8 : 4;
-  const int64_t lanes = n % vecw == 0 ? n / vecw : 32;       // lanes per dense row
-  const int64_t groups = lanes <= 8 ? 4 : (lanes <= 16 ? 2 : 1);  // non-zero groups per warp instruction
-  for (int b = 1; b < 32; ++b) {
-    const double w = static_cast<double>(hist32_host[b]) * 0.75 * static_cast<double>(int64_t{1} << b);
-    w_total += w;
-    if (b >= 8) w_long += w;                                  // rows of >= 128 non-zeros
-    if ((int64_t{1} << b) <= 4 * groups) w_short += w;        // rows that fit one 4-slot chunk per group
-  }
-  v.unroll8 = false;
-  v.row_parallel = false;
-  if (w_total > 0) {
-    // eight gathers in flight pay once most non-zeros sit in long rows (few edge chunks per row)
-    if (w_long >= 0.5 * w_total) v.unroll8 = true;
-    // row-parallel lanes pay when the groups of a narrow dense row would mostly idle: most
-    // non-zeros in rows too short to feed every group a full chunk
-    else if (groups > 1 && w_short >= 0.5 * w_total) v.row_parallel = true;
-  }
+  const bool sub_warp_rows = n % vecw == 0 && n / vecw <= 16;
+  int64_t below16 = 0;
+  for (int b = 0; b <= 4; ++b) below16 += hist32_host[b];  // buckets 0..4 = lengths 0..15
+  v.row_parallel = sub_warp_rows && 2 * below16 > rows;
   // resolve again so unsupported widths fall back exactly as the launch would
   return encode_variant(resolve_variant(encode_variant(v), rows, nnz, n, dense_dtype));
 }
@@ -341,6 +340,14 @@ int ofspmm_bwd_b_cached(const ofspmm_csr* A, const void* t_crow, const void* t_c
   return run_fwd(&At, dY, n, dB, n, n, dense_dtype, opts, w + tv_bytes, workspace_bytes - tv_bytes, stream);
 }
 
+int ofspmm_permute_values(const void* val, int val_dtype, const void* perm, int idx_dtype, int64_t nnz, void* out,
+                          ofspmm_stream_t stream) {
+  if (nnz < 0) return OFSPMM_ERR_INVALID_ARG;
+  if (nnz > 0 && (val == nullptr || perm == nullptr || out == nullptr)) return OFSPMM_ERR_INVALID_ARG;
+  if (!idx_ok(idx_dtype)) return OFSPMM_ERR_UNSUPPORTED_DTYPE;
+  return launch_gather_vals(val, val_dtype, perm, idx_dtype, nnz, out, reinterpret_cast<cudaStream_t>(stream));
+}
+
 int ofspmm_gather_rows(void* dst, int64_t ld_dst, const void* src, int64_t ld_src, const void* list, int idx_dtype,
                        int64_t idx_offset, int64_t count, int64_t n, int dense_dtype, int max_ctas,
                        ofspmm_stream_t stream) {
@@ -364,7 +371,7 @@ int ofspmm_scatter_add_rows(void* dst, int64_t ld_dst, const void* src, int64_t 
 size_t ofspmm_sddmm_workspace_bytes(int64_t rows, int64_t cols, int64_t nnz, int64_t n, int dense_dtype) {
   (void)cols; (void)n; (void)dense_dtype;
   if (rows < 0 || nnz < 0) return 0;
-  return plan_bytes_for(rows, nnz, kTaskItems);
+  return 256 + plan_bytes_for(rows, nnz, kTaskItems);  // [task counter | task partition]
 }
 
 int ofspmm_sddmm(const ofspmm_csr* A, const void* dY, const void* B, void* dval, int64_t n, int dense_dtype,
@@ -387,13 +394,17 @@ int ofspmm_sddmm_ex(const ofspmm_csr* A, const void* dY, const void* B, void* dv
   }
   if (dY == nullptr || B == nullptr) return OFSPMM_ERR_INVALID_ARG;
   const int64_t P = num_tasks(A->rows, A->nnz);
-  // the SDDMM kernels use 256-item tasks: a plan of that task size is taken as is
-  if (opts != nullptr && opts->plan != nullptr && opts->plan_bytes == plan_bytes_for(A->rows, A->nnz, kTaskItems))
-    return launch_sddmm(A, dY, B, dval, n, dense_dtype, opts->plan, P, stream);
   const size_t need = ofspmm_sddmm_workspace_bytes(A->rows, A->cols, A->nnz, n, dense_dtype);
   if (int rc = check_ws(workspace, workspace_bytes, need)) return rc;
-  if (int rc = launch_task_partition(A->crow, A->idx_dtype, A->rows, A->nnz, P, kTaskItems, workspace, stream)) return rc;
-  return launch_sddmm(A, dY, B, dval, n, dense_dtype, workspace, P, stream);
+  unsigned char* w = static_cast<unsigned char*>(workspace);
+  const uint32_t fl = opts ? opts->flags : 0u;
+  const bool dynamic = OFSPMM_DEFAULT_DYNAMIC_ORDER ? (fl & OFSPMM_ORDER_STATIC) == 0 : (fl & OFSPMM_ORDER_DYNAMIC) != 0;
+  void* counter = dynamic ? w : nullptr;
+  // the SDDMM kernels use 256-item tasks: a plan of that task size is taken as is
+  if (opts != nullptr && opts->plan != nullptr && opts->plan_bytes == plan_bytes_for(A->rows, A->nnz, kTaskItems))
+    return launch_sddmm(A, dY, B, dval, n, dense_dtype, opts->plan, counter, P, stream);
+  if (int rc = launch_task_partition(A->crow, A->idx_dtype, A->rows, A->nnz, P, kTaskItems, w + 256, stream)) return rc;
+  return launch_sddmm(A, dY, B, dval, n, dense_dtype, w + 256, counter, P, stream);
 }
 
 int ofspmm_partition(const void* crow, int idx_dtype, int64_t rows, int64_t nnz, int64_t parts,
@@ -521,7 +532,6 @@ const char* ofspmm_variant_name(int variant, int64_t rows, int64_t nnz, int64_t 
   const FwdVariant v = resolve_variant(variant, rows, nnz, n, dense_dtype);
   const char* fam = v.items == kSmallTaskItems ? "merge_path(64-item tasks)"
                     : v.row_parallel           ? "merge_path(256-item tasks, row-parallel groups)"
-                    : v.unroll8                ? "merge_path(256-item tasks, 8 gathers in flight)"
                                                : "merge_path(256-item tasks)";
   snprintf(buf, sizeof(buf), "%s/%s", fam, fwd_variant_name(n, dense_dtype, true));
   return buf;

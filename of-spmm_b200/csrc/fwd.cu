@@ -7,18 +7,14 @@ namespace ofspmm {
 
 int launch_family_base(const FwdParams&, int, int, int, bool, const FwdLaunch&, cudaStream_t);
 int launch_family_small(const FwdParams&, int, int, int, bool, const FwdLaunch&, cudaStream_t);
-int launch_family_unroll8(const FwdParams&, int, int, int, bool, const FwdLaunch&, cudaStream_t);
 int launch_family_rowpar(const FwdParams&, int, int, int, bool, const FwdLaunch&, cudaStream_t);
 
 namespace {
 
 int64_t vec_width(int dense_dtype) { return dense_dtype == OFSPMM_DTYPE_BFLOAT16 ? 8 : 4; }
 
-// Which dense widths a family has kernels for (16-byte aligned rows assumed; fwd falls back to the
-// base family otherwise).
-bool unroll8_supported(int64_t n, int dense_dtype) {
-  return dense_dtype == OFSPMM_DTYPE_FLOAT && n % 4 == 0 && n / 4 <= 32;
-}
+// Which dense widths the row-parallel family has kernels for (16-byte aligned rows assumed; fwd
+// falls back to the base family otherwise): the sub-warp layouts, 8 or 16 lanes per dense row.
 bool rowpar_supported(int64_t n, int dense_dtype) {
   const int64_t v = vec_width(dense_dtype);
   return n % v == 0 && n / v <= 16;
@@ -26,25 +22,17 @@ bool rowpar_supported(int64_t n, int dense_dtype) {
 
 }  // namespace
 
-// AUTO (no histogram available): decided from the host-known sizes only.
-//   * fewer 256-item tasks than resident warps  -> 64-item tasks;
-//   * fp32 rows of one register tile and >= 128 non-zeros per row on average -> eight gathers in
-//     flight (measured on B200: Reddit-shaped avg 492: -4.6 %; products-shaped avg 50: +4.6 %).
-// With a histogram, ofspmm_choose_variant() makes the same decisions from the nnz-weighted row
-// lengths and may also pick the row-parallel layout.
+// AUTO (no histogram available): decided from the host-known sizes only — fewer 256-item tasks
+// than resident warps -> 64-item tasks.  With the row-length histogram on the host,
+// ofspmm_choose_variant() may also pick the row-parallel layout (api.cu).
 FwdVariant resolve_variant(int variant, int64_t rows, int64_t nnz, int64_t n, int dense_dtype) {
-  FwdVariant v{kTaskItems, false, false};
+  FwdVariant v{kTaskItems, false};
   if (variant & OFSPMM_VARIANT_EXPLICIT) {
     if (variant & OFSPMM_VARIANT_ITEMS64) v.items = kSmallTaskItems;
     else if ((variant & OFSPMM_VARIANT_ROWPAR) && rowpar_supported(n, dense_dtype)) v.row_parallel = true;
-    else if ((variant & OFSPMM_VARIANT_UNROLL8) && unroll8_supported(n, dense_dtype)) v.unroll8 = true;
     return v;
   }
-  if (num_tasks(rows, nnz, kTaskItems) < kSmallProblemTasks) {
-    v.items = kSmallTaskItems;
-  } else if (rows > 0 && nnz / rows >= 128 && unroll8_supported(n, dense_dtype)) {
-    v.unroll8 = true;
-  }
+  if (num_tasks(rows, nnz, kTaskItems) < kSmallProblemTasks) v.items = kSmallTaskItems;
   return v;
 }
 
@@ -52,7 +40,6 @@ int encode_variant(const FwdVariant& v) {
   int code = OFSPMM_VARIANT_EXPLICIT;
   if (v.items == kSmallTaskItems) code |= OFSPMM_VARIANT_ITEMS64;
   if (v.row_parallel) code |= OFSPMM_VARIANT_ROWPAR;
-  if (v.unroll8) code |= OFSPMM_VARIANT_UNROLL8;
   return code;
 }
 
@@ -105,8 +92,6 @@ int launch_fwd(const ofspmm_csr* A, const void* B, int64_t ldb, void* C, int64_t
     return launch_family_small(p, A->idx_dtype, dense_dtype, A->val_dtype, aligned, L, stream);
   if (L.variant.row_parallel && vec_rows && rowpar_supported(n, dense_dtype))
     return launch_family_rowpar(p, A->idx_dtype, dense_dtype, A->val_dtype, aligned, L, stream);
-  if (L.variant.unroll8 && vec_rows && unroll8_supported(n, dense_dtype) && A->val_dtype == OFSPMM_DTYPE_FLOAT)
-    return launch_family_unroll8(p, A->idx_dtype, dense_dtype, A->val_dtype, aligned, L, stream);
   return launch_family_base(p, A->idx_dtype, dense_dtype, A->val_dtype, aligned, L, stream);
 }
 

@@ -5,6 +5,6 @@
 namespace ofspmm {
 int launch_family_small(const FwdParams& p, int idx_dtype, int dense_dtype, int val_dtype, bool aligned,
                         const FwdLaunch& L, cudaStream_t stream) {
-  return launch_family<false, kSmallTaskItems, 1>(p, idx_dtype, dense_dtype, val_dtype, aligned, L, stream);
+  return launch_family<false, kSmallTaskItems>(p, idx_dtype, dense_dtype, val_dtype, aligned, L, stream);
 }
 }  // namespace ofspmm

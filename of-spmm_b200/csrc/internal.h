@@ -36,7 +36,6 @@ inline int64_t num_tasks(int64_t rows, int64_t nnz, int items = kTaskItems) {
 struct FwdVariant {
   int items;          // merge items per warp task: kTaskItems or kSmallTaskItems
   bool row_parallel;  // sub-warp per row (short rows, narrow dense operand) instead of nnz-parallel
-  bool unroll8;       // two index chunks = eight gathers in flight per lane group (long rows)
 };
 FwdVariant resolve_variant(int variant, int64_t rows, int64_t nnz, int64_t n, int dense_dtype);
 int encode_variant(const FwdVariant& v);
@@ -54,6 +53,17 @@ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 struct DevInfo {
   int sms;
   int cc_major;
+  int ordinal;
+};
+
+// Launch constants of one kernel instantiation per device ordinal (0 = not queried yet); values
+// are immutable once written, relaxed atomics make concurrent first calls benign.
+struct KernelLaunchCache {
+  static constexpr int kMaxDevices = 64;
+  std::atomic<int> occ[kMaxDevices];
+  KernelLaunchCache() { for (auto& o : occ) o.store(0, std::memory_order_relaxed); }
+  int get(int dev) const { return dev >= 0 && dev < kMaxDevices ? occ[dev].load(std::memory_order_relaxed) : 0; }
+  void set(int dev, int v) { if (dev >= 0 && dev < kMaxDevices) occ[dev].store(v, std::memory_order_relaxed); }
 };
 int get_dev_info(DevInfo* out);  // OFSPMM_OK / OFSPMM_ERR_CUDA
 
@@ -70,7 +80,7 @@ int launch_fwd(const ofspmm_csr* A, const void* B, int64_t ldb, void* C, int64_t
                int dense_dtype, const void* part, float* carry, float* head, void* counter, int64_t P,
                const FwdLaunch& L, cudaStream_t stream);
 int launch_sddmm(const ofspmm_csr* A, const void* dY, const void* B, void* dval, int64_t n,
-                 int dense_dtype, const void* part, int64_t P, cudaStream_t stream);
+                 int dense_dtype, const void* part, void* counter, int64_t P, cudaStream_t stream);
 int launch_bwd_atomic(const ofspmm_csr* A, const void* dY, float* acc, void* dB_cast_out,
                       int64_t n, int dense_dtype, const void* part, int64_t P, cudaStream_t stream);
 int launch_partition_public(const void* crow, int idx_dtype, int64_t rows, int64_t nnz,

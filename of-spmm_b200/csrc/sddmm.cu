@@ -7,17 +7,22 @@ namespace ofspmm {
 namespace {
 
 template <typename Kern>
-int launch_persistent(Kern kern, const SddmmParams& p, size_t smem, cudaStream_t stream) {
+int launch_persistent(Kern kern, SddmmParams p, size_t smem, bool dynamic_ok, KernelLaunchCache& cache, cudaStream_t stream) {
   constexpr int WARPS = kWarpsPerCta;
-  OFSPMM_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   DevInfo dev;
   if (int rc = get_dev_info(&dev)) return rc;
-  int occ = 0;
-  OFSPMM_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, WARPS * 32, smem));
-  if (occ < 1) return OFSPMM_ERR_CUDA;
+  int occ = cache.get(dev.ordinal);  // per (kernel, device) launch constants, queried once
+  if (occ == 0) {
+    OFSPMM_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    OFSPMM_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, WARPS * 32, smem));
+    if (occ < 1) return OFSPMM_ERR_CUDA;
+    cache.set(dev.ordinal, occ);
+  }
   const int64_t ctas_needed = (static_cast<int64_t>(p.P) + WARPS - 1) / WARPS;
   const int64_t resident = static_cast<int64_t>(dev.sms) * occ;
   const int gx = static_cast<int>(ctas_needed < resident ? ctas_needed : resident);
+  if (!dynamic_ok || gx == ctas_needed) p.counter = nullptr;
+  if (p.counter != nullptr) OFSPMM_CUDA_OK(cudaMemsetAsync(p.counter, 0, sizeof(unsigned long long), stream));
   kern<<<gx, WARPS * 32, smem, stream>>>(p);
   count_launch();
   OFSPMM_CUDA_OK(cudaGetLastError());
@@ -29,9 +34,10 @@ int launch_one(const SddmmParams& p, cudaStream_t stream) {
   constexpr int ITEMS = kTaskItems;
   constexpr int WARPS = kWarpsPerCta;
   const size_t smem = sizeof(TaskStage<IdxT, float, ITEMS>) * WARPS + sizeof(uint64_t) * WARPS;
+  static KernelLaunchCache cache_full, cache_masked;
   if (p.n % (LPR * VEC * CH) == 0)
-    return launch_persistent(sddmm_merge_kernel<DT, ValT, IdxT, VEC, LPR, CH, true, ITEMS, WARPS>, p, smem, stream);
-  return launch_persistent(sddmm_merge_kernel<DT, ValT, IdxT, VEC, LPR, CH, false, ITEMS, WARPS>, p, smem, stream);
+    return launch_persistent(sddmm_merge_kernel<DT, ValT, IdxT, VEC, LPR, CH, true, ITEMS, WARPS>, p, smem, true, cache_full, stream);
+  return launch_persistent(sddmm_merge_kernel<DT, ValT, IdxT, VEC, LPR, CH, false, ITEMS, WARPS>, p, smem, true, cache_masked, stream);
 }
 
 template <typename DT, typename ValT, typename IdxT, int VEC>
@@ -39,7 +45,8 @@ int launch_wide(const SddmmParams& p, cudaStream_t stream) {
   constexpr int ITEMS = kTaskItems;
   constexpr int WARPS = kWarpsPerCta;
   const size_t smem = sizeof(TaskStage<IdxT, float, ITEMS>) * WARPS + sizeof(uint64_t) * WARPS;
-  return launch_persistent(sddmm_wide_kernel<DT, ValT, IdxT, VEC, ITEMS, WARPS>, p, smem, stream);
+  static KernelLaunchCache cache;
+  return launch_persistent(sddmm_wide_kernel<DT, ValT, IdxT, VEC, ITEMS, WARPS>, p, smem, false, cache, stream);
 }
 
 template <typename DT, typename ValT, typename IdxT>
@@ -74,8 +81,9 @@ int launch_idx(const SddmmParams& p, int dense_dtype, int val_dtype, bool aligne
 }  // namespace
 
 int launch_sddmm(const ofspmm_csr* A, const void* dY, const void* B, void* dval, int64_t n,
-                 int dense_dtype, const void* part, int64_t P, cudaStream_t stream) {
+                 int dense_dtype, const void* part, void* counter, int64_t P, cudaStream_t stream) {
   SddmmParams p;
+  p.counter = static_cast<unsigned long long*>(counter);
   p.crow = A->crow;
   p.col = A->col;
   p.dY = dY;

@@ -12,6 +12,7 @@ struct SddmmParams {
   const void* B;    // cols x n
   void* dval;       // nnz
   const int2* part;
+  unsigned long long* counter;  // dynamic task order (see spmm_merge_kernel); nullptr = static
   long long cols;
   int rows;
   int nnz;
@@ -83,7 +84,15 @@ sddmm_merge_kernel(const SddmmParams p) {
   const int total_warps = gridDim.x * WARPS;
   uint32_t phase = 0;
 
-  for (int k = blockIdx.x * WARPS + warp; k < p.P; k += total_warps) {
+  // task order: static interleave, or drawn from a counter in launch order (spmm_merge_kernel)
+  for (long long kk = blockIdx.x * WARPS + warp; kk < p.P;) {
+    const int k = static_cast<int>(kk);
+    kk += total_warps;
+    if (p.counter != nullptr) {
+      unsigned long long drawn = 0;
+      if (lane == 0) drawn = atomicAdd(p.counter, 1ull);
+      kk = static_cast<long long>(__shfl_sync(0xffffffffu, drawn, 0)) + total_warps;
+    }
     const int2 ps = __ldg(&p.part[k]);
     const int2 pe = __ldg(&p.part[k + 1]);
     const int rs = ps.x, ns = ps.y, re = pe.x, ne = pe.y;

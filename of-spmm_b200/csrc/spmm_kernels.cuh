@@ -36,13 +36,11 @@ namespace ofspmm {
 // Resident CTAs per SM the kernels are compiled for (4 warps per CTA): sets the register cap.
 // Measured on B200 (tools/sweep_fwd.py, profiles/r1_tuning_sweeps.md): fp32 rows run best at 36
 // warps/SM with 54 registers, bf16 rows (8 accumulators + unpacking) at 32 warps/SM with 60.
-// UNR == 2 (eight gathers in flight per lane group, long-row graphs): 7 CTAs/SM = 72 registers.
-template <typename DT, int CH, int UNR = 1>
+template <typename DT, int CH>
 constexpr int min_ctas_per_sm() {
 #ifdef OFSPMM_MIN_CTAS
   return CH == 1 ? OFSPMM_MIN_CTAS : (CH == 2 ? 6 : 4);
 #else
-  if (UNR == 2) return CH == 1 ? 7 : 4;
   return CH == 1 ? (sizeof(DT) == 4 ? 9 : 8) : (CH == 2 ? 6 : 4);
 #endif
 }
@@ -67,6 +65,7 @@ struct FwdParams {
   const void* bias;  // n elements of the dense dtype (kFwdBias)
   unsigned long long* counter;  // dynamic task order: zeroed before the launch; nullptr = static
   unsigned flags;    // kFwd* epilogue bits
+  int max_tasks;     // tasks a warp runs before its CTA may retire (0: until the list is empty)
 };
 
 // Epilogue bits (= OFSPMM_FWD_* of include/ofspmm.h).  A row's epilogue runs exactly once, where
@@ -256,8 +255,8 @@ __device__ __forceinline__ uint2 lds64(uint32_t addr) {
 // kFull: n is a whole number of LPR*VEC*CH-column tiles, so no lane is ever masked and the chunk
 // offsets are immediates.  Otherwise masked chunks are pointed at column 0 (a valid address:
 // their loads are harmless duplicates) and only the stores are predicated.
-template <typename DT, typename ValT, typename IdxT, int VEC, int LPR, int CH, bool kFull, bool kRowPar, int ITEMS, int WARPS, int UNR>
-__global__ void __launch_bounds__(WARPS * 32, min_ctas_per_sm<DT, CH, UNR>())
+template <typename DT, typename ValT, typename IdxT, int VEC, int LPR, int CH, bool kFull, bool kRowPar, int ITEMS, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, min_ctas_per_sm<DT, CH>())
 spmm_merge_kernel(const FwdParams p) {
   constexpr int G = 32 / LPR;  // groups of lanes working on different non-zeros
   constexpr bool kF32Out = sizeof(DT) == 4;
@@ -300,17 +299,23 @@ spmm_merge_kernel(const FwdParams p) {
   uint32_t phase = 0;
 
   // Task order.  Static: warp w runs tasks w, w + W, w + 2W, ...  Dynamic (p.counter != nullptr):
-  // the first task is still w, every later one is drawn from a global counter in launch order, so
+  // every task is drawn from a global counter, i.e. handed out in the order warps ask for work, so
   // the rows in flight chip-wide always form ONE contiguous window of the matrix however unevenly
-  // the warps progress (keeps the B rows of that window L2-resident, and evens out the tail).
-  // The draw is issued at the top of a task and consumed at its end: its latency is hidden.
-  for (long long t = blockIdx.x * WARPS + warp; t < total_tasks;) {
+  // the warps progress (keeps the B rows of that window L2-resident — measured -13 % on the
+  // Reddit-shaped, -26 % on the products-shaped graph — and evens out the tail).  The next draw is
+  // issued at the top of a task and consumed at its end: its latency is hidden.  A warp stops
+  // after p.max_tasks tasks (short-lived CTAs for the multi-GPU overlap); it never draws a task it
+  // will not run.
+  const int max_tasks = p.max_tasks > 0 ? p.max_tasks : 0x7fffffff;
+  auto draw = [&]() -> long long {
+    unsigned long long drawn = 0;
+    if (lane == 0) drawn = atomicAdd(p.counter, 1ull);
+    return static_cast<long long>(__shfl_sync(0xffffffffu, drawn, 0));
+  };
+  long long t = p.counter != nullptr ? draw() : static_cast<long long>(blockIdx.x) * WARPS + warp;
+  for (int done = 0; t < total_tasks && done < max_tasks; ++done) {
     long long t_next = t + total_warps;
-    if (p.counter != nullptr) {
-      unsigned long long drawn = 0;
-      if (lane == 0) drawn = atomicAdd(p.counter, 1ull);
-      t_next = static_cast<long long>(__shfl_sync(0xffffffffu, drawn, 0)) + total_warps;
-    }
+    if (p.counter != nullptr) t_next = done + 1 < max_tasks ? draw() : total_tasks;
     // panel-major: all tasks of column panel 0, then panel 1, ... (keeps the B panel in L2)
     const int panel = static_cast<int>(t / p.P);
     const int k = static_cast<int>(t - static_cast<long long>(panel) * p.P);
@@ -413,41 +418,6 @@ spmm_merge_kernel(const FwdParams p) {
           const int q0 = chunk_first == 0 ? kChunkStride : chunk_first;
           uint32_t ca = col_sa + static_cast<uint32_t>(cbase + 4 * q0) * 4u;
           const uint32_t cend = col_sa + static_cast<uint32_t>(cbase + 4 * (nchunks - 1)) * 4u;
-          // UNR == 2 (picked for long-row graphs by the row-length histogram): two index chunks =
-          // eight gathers in flight per iteration; the single-chunk loop below then only handles
-          // an odd leftover chunk
-          if constexpr (UNR == 2) while (ca + 16u * kChunkStride < cend) {
-            const uint4 ca4 = lds128(ca), cb4 = lds128(ca + 16u * kChunkStride);
-            const uint32_t c8[8] = {ca4.x, ca4.y, ca4.z, ca4.w, cb4.x, cb4.y, cb4.z, cb4.w};
-            typename RV::Raw x8[8][CH];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-              const char* brow = Bl + static_cast<unsigned long long>(c8[u]) * row_bytes;
-#pragma unroll
-              for (int ch = 0; ch < CH; ++ch)
-                x8[u][ch] = load_b<DT, VEC>(brow + (kFull ? ch * kChunkBytes : choff[ch]), pol_b);
-            }
-            float v8[8];
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              const uint32_t cah = ca + h * 16u * kChunkStride;
-              const uint32_t va = sizeof(ValT) == 4 ? cah + (val_s0 - col_sa) : val_s0 + ((cah - col_sa) >> 1);
-              if constexpr (sizeof(ValT) == 4) {
-                const uint4 w = lds128(va);
-                v8[4 * h + 0] = __uint_as_float(w.x); v8[4 * h + 1] = __uint_as_float(w.y);
-                v8[4 * h + 2] = __uint_as_float(w.z); v8[4 * h + 3] = __uint_as_float(w.w);
-              } else {
-                const uint2 w = lds64(va);
-                v8[4 * h + 0] = __uint_as_float(w.x << 16); v8[4 * h + 1] = __uint_as_float(w.x & 0xffff0000u);
-                v8[4 * h + 2] = __uint_as_float(w.y << 16); v8[4 * h + 3] = __uint_as_float(w.y & 0xffff0000u);
-              }
-            }
-            ca += 32u * kChunkStride;
-#pragma unroll
-            for (int u = 0; u < 8; ++u)
-#pragma unroll
-              for (int ch = 0; ch < CH; ++ch) RV::fma(acc[ch], v8[u], x8[u][ch]);
-          }
           if (ca < cend) {
             uint4 cn = lds128(ca);
             do {

@@ -1,35 +1,42 @@
 """Multi-GPU SpMM inside one NVSwitch box: one process per GPU over
-``torch.distributed`` (NCCL over NVLink 5; gloo on CPU for the host-logic tests).
+``torch.distributed`` (NCCL for bootstrap / barriers; gloo on CPU for the host-logic tests).
 
-Partitioning
+Partitioning (both classes)
   * A (M×K) → ``world`` contiguous, **nnz-balanced whole-row blocks** from the device merge-path
-    partitioner (``row_blocks``); rank r keeps only its block's CSR.  Output rows stay local.
+    partitioner (``ops.row_blocks``); rank r keeps only its block's CSR, output rows stay local.
     Contrast: the reference can only split rows in equal counts (BalancedSplitter,
     oneflow/core/common/balanced_splitter.cpp:20-39) and its S(0)→B boxing needs dim0 % world == 0
     (oneflow/core/boxing/ccl_boxing_function.cpp:115), which is why this lives here and not in SBP.
-  * B (K×n) is row-sharded in equal blocks of ceil(K/world) rows (zero-padded), which is what an
-    all-gather needs.
+  * B (K×n) / dB are row-sharded in equal blocks of ceil(K/world) rows (zero-padded).
 
-Collectives and overlap (measured on 8 B200s, profiles/r1_multigpu.md)
-  * ``forward``: all-gather of the B shards, then ``C_blk = A_blk · B``.  ``backward``: partial
-    ``A_blkᵀ·dY_blk`` (K×n), then reduce-scatter — the dual collective.
-  * ``step`` (both products of a training step) hides the collectives of one product behind the
-    compute of the other: all-gather(B) ‖ A_blkᵀ·dY, then reduce-scatter(dB) ‖ A_blk·B.  The
-    reference instead finishes a blocking, unfused all-gather before the op is even issued
-    (oneflow/core/framework/op_interpreter/eager_global_op_interpreter.cpp:156-181).
-  * ``panels`` > 1 additionally pipelines a collective with its *own* product over column panels of
-    the dense operand (``ofspmm_fwd_strided`` writes panel j straight into C_blk's columns).
-    Measured slower than whole-width products on cfg2, so the default is 1.
-  * NCCL kernels need SMs; a persistent compute grid owns all of them, so by default the compute
-    kernels run as short-lived CTAs while collectives are in flight (``tasks_per_warp``), or the
-    exchange uses copy engines over symmetric peer memory (``comm="peer"``).
+``ShardedSpmm`` — the needed-rows exchange (default)
+  The reference materialises the WHOLE dense operand on every rank with a blocking all-gather
+  before the op is issued (oneflow/core/framework/op_interpreter/eager_global_op_interpreter.cpp:156-181,
+  oneflow/core/boxing/ccl_boxing_function.cpp:183-197).  Here each rank's block is split ONCE, by
+  the owner of the column, into a *local* sub-CSR (columns of its own B shard) and one or more
+  *remote* sub-CSRs whose columns are renumbered to the compact list of B rows the block really
+  touches.  Per product:
+      forward   C_blk  = A_local·B_shard                       (starts immediately, no communication)
+                C_blk += A_remote_g·pull_g(B)                   (accumulate pass per bucket, as it lands)
+      backward  dBc_g  = A_remote_gᵀ·dY_blk  → published        (compact partial rows, remote owners)
+                dB_shard = A_localᵀ·dY_blk + Σ_r pull(dBc of rank r) in rank order   (deterministic)
+      sddmm     per sub-CSR against the B rows the forward already holds
+  ``pull`` is ``ofspmm_gather_rows`` / ``ofspmm_scatter_add_rows`` reading the owners' shards
+  straight out of peer HBM over NVLink / NVSwitch (CUDA symmetric memory), ordered by device-side
+  barriers — no NCCL collective on the data path.  Only the rows a block touches cross the fabric
+  (R-MAT-24 on 8 GPUs: ~1/4 of an all-gather), and the local columns (70+ % of a community graph's
+  non-zeros) compute while they fly.
 
-The compute callbacks default to the CUDA ops; tests inject CPU stand-ins to exercise the
-partition / shard / pipeline logic under gloo with world_size 2.
+``AllGatherSpmm`` — round 1's scheme (all-gather(B) → product, partial product → reduce-scatter,
+  the collectives of one product hidden behind the other product of a step).  Kept as the
+  reference-style baseline the exchange above is measured against.
+
+The compute back end defaults to the CUDA ops; tests inject a CPU stand-in built on the oracle to
+exercise the split / renumbering / exchange / accumulation-order logic under gloo.
 """
 from __future__ import annotations
 
-from typing import Callable, List, Optional  # noqa: F401
+from typing import Callable, Dict, List, Optional, Tuple  # noqa: F401
 
 import torch
 import torch.distributed as dist
@@ -38,288 +45,432 @@ from . import ops
 from .graphs import CsrMatrix
 
 
-def _default_spmm(crow, col, val, b, rows, cols, out):
-    return ops.spmm_csr_compute(crow, col, val, b, rows, cols, out=out)
-
-
-def _default_transpose(crow, col, val, rows, cols):
-    return ops.csr_transpose(crow, col, val, rows, cols)
-
-
 def shard_rows_count(k: int, world: int) -> int:
     return (k + world - 1) // world
 
 
-class _PeerExchange:
-    """Collectives over NVSwitch peer memory without SMs: every rank exposes its send buffers
-    through CUDA symmetric memory (``torch.distributed._symmetric_memory``), synchronises with a
-    stream-ordered device barrier and *pulls* the peers' blocks with plain device-to-device copies
-    on a side stream — those run on the copy engines, so the persistent SpMM kernel keeps all 148
-    SMs while the next panel is in flight.  (NCCL's all-gather kernel needs SMs of its own; when
-    the persistent compute grid already owns them the two serialise instead of overlapping.)"""
+# ---------------------------------------------------------------------------------------------
+# compute back ends
 
-    def __init__(self, shard: int, kp: int, w: int, panels: int, dtype, device, rank: int, world: int, group):
+class CudaCompute:
+    """The product path: every call goes through the C ABI (ops.*)."""
+    is_cuda = True
+
+    def plan(self, crow, col, rows, cols, n, dtype):
+        return ops.SpmmPlan(crow, col, rows, cols, n, dtype, transpose=True)
+
+    def spmm(self, A: CsrMatrix, b, out, plan=None, accumulate=False, tasks_per_warp=0, bias=None, relu=False):
+        return ops.spmm_csr_compute(A.crow, A.col, A.val, b, A.rows, A.cols, out=out, plan=plan, accumulate=accumulate,
+                                    tasks_per_warp=tasks_per_warp, bias=bias, relu=relu)
+
+    def spmm_t(self, A: CsrMatrix, dy, out, plan=None, tasks_per_warp=0):
+        return ops.spmm_csr_grad_b_compute(A.crow, A.col, A.val, dy, A.rows, A.cols, out=out, plan=plan,
+                                           tasks_per_warp=tasks_per_warp)
+
+    def sddmm(self, A: CsrMatrix, dy, b, plan=None):
+        return ops.sddmm_csr_compute(A.crow, A.col, dy, b, A.rows, A.cols, A.val.dtype, plan=plan)
+
+    def gather_rows(self, dst, src, index, max_ctas=0):
+        return ops.gather_rows(dst, src, index, max_ctas=max_ctas)
+
+    def scatter_add_rows(self, dst, src, index, max_ctas=0):
+        return ops.scatter_add_rows(dst, src, index, max_ctas=max_ctas)
+
+
+# ---------------------------------------------------------------------------------------------
+# transports: how a rank sees the buffers its peers publish
+
+class SymmTransport:
+    """CUDA symmetric memory (``torch.distributed._symmetric_memory``): every published buffer is
+    mapped into every peer's address space, so a kernel on rank a reads rank b's HBM with ordinary
+    loads over NVLink; ``barrier`` is a stream-ordered device barrier (signal pads), no host sync."""
+
+    def __init__(self, rank: int, world: int, device, group=None):
         import torch.distributed._symmetric_memory as symm
-        self.rank, self.world, self.shard, self.w, self.panels = rank, world, shard, w, panels
-        gname = (group or dist.group.WORLD).group_name
-        # outgoing B panels (forward) and partial dB panels (backward), visible to every peer
-        self.send = symm.empty((panels, shard, w), dtype=dtype, device=device)
-        self.part = symm.empty((panels, kp, w), dtype=dtype, device=device)
-        self.h_send = symm.rendezvous(self.send, gname)
-        self.h_part = symm.rendezvous(self.part, gname)
-        self.peer_send = [self.h_send.get_buffer(r, (panels, shard, w), dtype) for r in range(world)]
-        self.peer_part = [self.h_part.get_buffer(r, (panels, kp, w), dtype) for r in range(world)]
-        self.copy_stream = torch.cuda.Stream(device=device)
-        self.stage = torch.empty((world, shard, w), dtype=dtype, device=device)
+        self._symm = symm
+        self.rank, self.world, self.device = rank, world, device
+        self.gname = (group or dist.group.WORLD).group_name
+        self.bufs: Dict[str, Tuple[torch.Tensor, list]] = {}
+        self._bar = symm.empty((64,), dtype=torch.float32, device=device)
+        self._hbar = symm.rendezvous(self._bar, self.gname)
 
-    def begin_forward(self):
-        # every peer has finished pulling the previous step's panels before they are overwritten
-        self.h_send.barrier(channel=0)
+    def alloc(self, name: str, rows: int, n: int, dtype) -> torch.Tensor:
+        t = self._symm.empty((rows, n), dtype=dtype, device=self.device)
+        h = self._symm.rendezvous(t, self.gname)
+        self.bufs[name] = (t, [h.get_buffer(r, (rows, n), dtype) for r in range(self.world)])
+        return t
 
-    def all_gather_panel(self, j: int, out_full: torch.Tensor) -> torch.cuda.Event:
-        """send[j] was filled on the current stream; returns the event after which out_full
-        (kp x w) holds every rank's panel j."""
-        self.h_send.barrier(channel=1 + j)          # all ranks have filled their panel j
-        cur = torch.cuda.current_stream()
-        self.copy_stream.wait_stream(cur)
-        with torch.cuda.stream(self.copy_stream):
-            for step in range(self.world):
-                r = (self.rank + step) % self.world   # own block first, then a ring of peers
-                out_full[r * self.shard:(r + 1) * self.shard].copy_(self.peer_send[r][j], non_blocking=True)
-            ev = torch.cuda.Event()
-            ev.record(self.copy_stream)
+    def peer(self, name: str, r: int) -> torch.Tensor:
+        return self.bufs[name][1][r]
+
+    def barrier(self, channel: int) -> None:
+        self._hbar.barrier(channel=channel)
+
+    def refresh(self, name: str) -> None:   # peers' memory is read in place
+        pass
+
+
+class GatherTransport:
+    """Host-logic stand-in (gloo / CPU): ``refresh`` all-gathers a published buffer so ``peer``
+    returns a copy of what that rank holds; same call sequence as the symmetric-memory path."""
+
+    def __init__(self, rank: int, world: int, device, group=None):
+        self.rank, self.world, self.device, self.group = rank, world, device, group
+        self.bufs: Dict[str, Tuple[torch.Tensor, list]] = {}
+
+    def alloc(self, name: str, rows: int, n: int, dtype) -> torch.Tensor:
+        t = torch.zeros((rows, n), dtype=dtype, device=self.device)
+        self.bufs[name] = (t, [torch.zeros_like(t) for _ in range(self.world)])
+        return t
+
+    def peer(self, name: str, r: int) -> torch.Tensor:
+        return self.bufs[name][1][r]
+
+    def barrier(self, channel: int) -> None:
+        dist.barrier(group=self.group)
+
+    def refresh(self, name: str) -> None:
+        t, copies = self.bufs[name]
+        dist.all_gather(copies, t.contiguous(), group=self.group)
+
+
+class _Streams:
+    """Current + communication stream (CUDA) or no-ops (CPU)."""
+
+    def __init__(self, device):
+        self.cuda = torch.device(device).type == "cuda"
+        self.comm = torch.cuda.Stream(device=device, priority=-1) if self.cuda else None
+
+    def cur(self):
+        return torch.cuda.current_stream() if self.cuda else None
+
+    def record(self, stream=None):
+        if not self.cuda:
+            return None
+        ev = torch.cuda.Event()
+        ev.record(stream or torch.cuda.current_stream())
         return ev
 
-    def begin_backward(self):
-        self.h_part.barrier(channel=0)
+    def wait(self, stream, ev):
+        if self.cuda and ev is not None:
+            stream.wait_event(ev)
 
-    def reduce_scatter_panel(self, j: int, out_shard: torch.Tensor) -> torch.cuda.Event:
-        """part[j] (this rank's partial kp x w) was written on the current stream; out_shard
-        (shard x w) = sum over ranks of their partial rows of this rank's shard, fixed order."""
-        self.h_part.barrier(channel=1 + j)          # every rank's partial panel j is complete
-        cur = torch.cuda.current_stream()
-        self.copy_stream.wait_stream(cur)
-        lo, hi = self.rank * self.shard, (self.rank + 1) * self.shard
-        with torch.cuda.stream(self.copy_stream):
-            for step in range(self.world):
-                r = (self.rank + step) % self.world
-                self.stage[r].copy_(self.peer_part[r][j, lo:hi], non_blocking=True)
-            torch.sum(self.stage, dim=0, out=out_shard)   # rank order 0..world-1: deterministic
-            ev = torch.cuda.Event()
-            ev.record(self.copy_stream)
-        return ev
+    def on_comm(self):
+        import contextlib
+        return torch.cuda.stream(self.comm) if self.cuda else contextlib.nullcontext()
+
+
+def _exchange_lists(send: List[torch.Tensor], rank: int, world: int, group) -> List[torch.Tensor]:
+    """send[s] (1-D int32) goes to rank s; returns recv[r] = what rank r sent to this rank."""
+    sizes = torch.tensor([t.numel() for t in send], dtype=torch.int64, device=send[0].device)
+    all_sizes = [torch.zeros_like(sizes) for _ in range(world)]
+    dist.all_gather(all_sizes, sizes, group=group)
+    recv_sizes = [int(all_sizes[r][rank]) for r in range(world)]
+    # one-off, at construction: pad to the longest list and all-gather (works on NCCL and gloo alike,
+    # and never hands a zero-length buffer to a collective)
+    m = max(1, int(torch.stack(all_sizes).max()))
+    packed = torch.zeros((world, m), dtype=send[0].dtype, device=send[0].device)
+    for s, t in enumerate(send):
+        packed[s, : t.numel()] = t
+    gathered = [torch.zeros_like(packed) for _ in range(world)]
+    dist.all_gather(gathered, packed, group=group)
+    return [gathered[r][rank, : recv_sizes[r]].clone() for r in range(world)]
+
+
+class _SubCsr:
+    """One column bucket of a rank's row block: its CSR over a compact column space, where those
+    columns come from, and the plan (variant, partition, structure of the transpose)."""
+    __slots__ = ("A", "pos", "segs", "ncols", "plan", "Bc", "dBc_name")
 
 
 class ShardedSpmm:
-    """Row-block-partitioned SpMM operator bound to one rank."""
+    """Row-block-partitioned SpMM operator bound to one rank — needed-rows exchange over peer memory."""
 
-    def __init__(self, A: CsrMatrix, n: int, dtype: torch.dtype, rank: int, world: int, device,
-                 bwd: str = "transpose", panels: int = 1,
-                 spmm_fn: Callable = _default_spmm, transpose_fn: Callable = _default_transpose,
-                 group=None, comm: str = "nccl", tasks_per_warp: int = 2):
+    def __init__(self, A: CsrMatrix, n: int, dtype: torch.dtype, rank: int, world: int, device, *,
+                 buckets: int = 1, tasks_per_warp: int = 4, pull_ctas: int = 32, group=None,
+                 compute=None, transport: Optional[str] = None, shard_like_rows: bool = False, slots: int = 1):
+        """``shard_like_rows`` (square A): shard B / dB by the SAME boundaries as the row blocks, so
+        the output block of one product is the input shard of the next (GCN layers chain without a
+        re-shard); default: equal shards of ceil(K/world) rows.  ``slots``: independent sets of
+        exchange buffers over the one shared structure (one per layer of a model)."""
         assert A.rows >= world, "fewer rows than ranks"
-        # Launch policy of the compute kernels while collectives are in flight: CTAs that retire
-        # after ~tasks_per_warp tasks per warp instead of one persistent wave, so the NCCL kernels
-        # (higher-priority stream) get SMs as soon as they are ready.  8 B200s, cfg2: 1.19 ms →
-        # 0.98 ms per step (profiles/r1_multigpu.md).  The library reads the knob at every launch.
-        if world > 1 and tasks_per_warp > 0 and comm == "nccl":
-            import os
-            os.environ.setdefault("OFSPMM_TASKS_PER_WARP", str(tasks_per_warp))
         self.rank, self.world, self.device, self.group = rank, world, device, group
         self.n, self.dtype = n, dtype
         self.rows, self.cols = A.rows, A.cols
-        self.spmm_fn, self.bwd_mode = spmm_fn, bwd
-        # column panels must keep 16-byte alignment of every panel start (8 bf16 / 4 fp32)
-        vec = 8 if dtype == torch.bfloat16 else 4
-        panels = max(1, min(panels, n // vec if n >= vec else 1))
-        while n % (panels * vec) != 0 and panels > 1:
-            panels -= 1
-        self.panels = panels
-        self.w = n // panels
+        self.cp = compute or CudaCompute()
+        self.st = _Streams(device)
+        self.tpw = tasks_per_warp if world > 1 else 0
+        self.pull_ctas = pull_ctas
         # nnz-balanced whole-row blocks (device partitioner when the graph is on the GPU)
         self.bounds = ops.row_blocks(A.crow, A.nnz, world).cpu().tolist()
         self.r0, self.r1 = int(self.bounds[rank]), int(self.bounds[rank + 1])
-        self.A_blk = A.row_slice(self.r0, self.r1)
-        self.shard = shard_rows_count(A.cols, world)
-        self.kp = self.shard * world  # padded K
-        self.At_blk = None
-        if bwd == "transpose":
-            t = transpose_fn(self.A_blk.crow, self.A_blk.col, self.A_blk.val, self.A_blk.rows, self.A_blk.cols)
-            self.At_blk = CsrMatrix(t[0], t[1], t[2], self.A_blk.cols, self.A_blk.rows)
-        m = self.A_blk.rows
-        # persistent buffers (allocated once: the op state of the multi-GPU path)
-        self._b_send = [torch.empty((self.shard, self.w), dtype=dtype, device=device) for _ in range(panels)]
-        self._b_full = [torch.empty((self.kp, self.w), dtype=dtype, device=device) for _ in range(panels)]
+        blk = A.row_slice(self.r0, self.r1)
+        self.A_blk = blk
+        if shard_like_rows:
+            assert A.rows == A.cols, "shard_like_rows needs a square matrix"
+            self.col_bounds = [int(b) for b in self.bounds]
+        else:
+            eq = shard_rows_count(A.cols, world)
+            self.col_bounds = [min(A.cols, s * eq) for s in range(world)] + [A.cols]
+        self.lo, self.hi = self.col_bounds[rank], self.col_bounds[rank + 1]
+        self.shard = max(1, max(self.col_bounds[s + 1] - self.col_bounds[s] for s in range(world))) if shard_like_rows \
+            else shard_rows_count(A.cols, world)                     # rows of every shard buffer (padded)
+        self.kp = self.shard * world
+        self.slots = slots
+        m = blk.rows
+        if transport is None:
+            nccl = world > 1 and dist.is_initialized() and dist.get_backend(group) == "nccl"
+            transport = "symm" if nccl else "gather"
+        self.comm = "pull/" + transport if world > 1 else "single"
+        self.T = (SymmTransport if transport == "symm" else GatherTransport)(rank, world, device, group) if world > 1 else None
+
+        # ---- split the block by the owner of the column; renumber remote columns compactly
+        nb = max(1, min(buckets, world - 1)) if world > 1 else 0
+        ring = [(rank + d) % world for d in range(1, world)]
+        chunk = [ring[(i * len(ring)) // nb:((i + 1) * len(ring)) // nb] for i in range(nb)] if nb else []
+        col = blk.col.long()
+        lens = blk.row_lengths()
+        rows_of = torch.repeat_interleave(torch.arange(m, device=col.device), lens)
+        cb = torch.tensor(self.col_bounds, dtype=torch.int64, device=col.device)
+        valid = (col >= 0) & (col < A.cols)
+        owner = (torch.searchsorted(cb, col.clamp(0, max(A.cols - 1, 0)), right=True) - 1).clamp(0, world - 1)
+        gid_of_shard = torch.zeros(world + 1, dtype=torch.int64, device=col.device)
+        for g, shards in enumerate(chunk, 1):
+            for s in shards:
+                gid_of_shard[s] = g
+        gid = torch.where(valid, gid_of_shard[owner.clamp(0, world)], torch.zeros_like(owner))  # skipped entries: bucket 0
+        touched = torch.unique(col[valid])
+        t_owner = (torch.searchsorted(cb, touched, right=True) - 1).clamp(0, world - 1)
+        remap = torch.full((A.cols + 1,), -1, dtype=torch.int64, device=col.device)
+        remap[self.lo:self.hi] = torch.arange(self.hi - self.lo, device=col.device)
+        self.sub: List[_SubCsr] = []
+        seg_table = torch.zeros((world, 3), dtype=torch.int64)       # [owner s] -> (bucket, offset, count) on this rank
+        send_lists: List[torch.Tensor] = [torch.empty(0, dtype=torch.int32, device=col.device) for _ in range(world)]
+        metas = [(0, [(rank, 0, self.hi - self.lo, None)], self.hi - self.lo)]
+        for g, shards in enumerate(chunk, 1):
+            off, segs = 0, []
+            for s in shards:
+                lst = touched[t_owner == s]
+                remap[lst] = off + torch.arange(lst.numel(), device=col.device)
+                local_ids = (lst - self.col_bounds[s]).to(torch.int32)
+                segs.append((s, off, int(lst.numel()), local_ids))
+                seg_table[s] = torch.tensor([g, off, int(lst.numel())])
+                send_lists[s] = local_ids
+                off += int(lst.numel())
+            metas.append((g, segs, off))
+        new_col = torch.where(valid, remap[col.clamp(0, A.cols)], torch.full_like(col, -1))
+        for g, segs, ncols in metas:
+            mask = gid == g
+            pos = torch.nonzero(mask).flatten()
+            cnt = torch.bincount(rows_of[pos], minlength=m)
+            crow = torch.zeros(m + 1, dtype=torch.int64, device=col.device)
+            crow[1:] = torch.cumsum(cnt, 0)
+            sc = _SubCsr()
+            sc.A = CsrMatrix(crow.to(blk.crow.dtype), new_col[pos].to(blk.col.dtype), blk.val[pos].contiguous(), m,
+                             max(ncols if g > 0 else self.hi - self.lo, 1))
+            sc.pos, sc.segs, sc.ncols = pos, segs, ncols
+            sc.plan = self.cp.plan(sc.A.crow, sc.A.col, m, sc.A.cols, n, dtype) if getattr(self.cp, "is_cuda", False) else None
+            sc.Bc = [torch.zeros((max(ncols, 1), n), dtype=dtype, device=device) for _ in range(slots)] if g > 0 else None
+            sc.dBc_name = f"dBc{g}" if g > 0 else None
+            self.sub.append(sc)
+        del rows_of, owner, gid, new_col, remap
+        self.local_fraction = float(self.sub[0].A.nnz) / max(1, blk.nnz)
+        self.pulled_rows = int(sum(sc.ncols for sc in self.sub[1:]))
+
+        # ---- published buffers and what every peer holds for this rank's shard
         self._c = torch.empty((m, n), dtype=dtype, device=device)
-        self._db_part = [torch.empty((self.kp, self.w), dtype=dtype, device=device) for _ in range(panels)]
-        self._db_out = [torch.empty((self.shard, self.w), dtype=dtype, device=device) for _ in range(panels)]
-        self._db = torch.empty((self.shard, n), dtype=dtype, device=device)
-        self._nccl = dist.is_initialized() and dist.get_backend(group) == "nccl"
-        # comm = "peer": copy-engine pulls over symmetric memory instead of NCCL kernels
-        self.comm, self._peer = "nccl" if self._nccl else "gloo", None
-        if comm == "peer" and self._nccl:
-            try:
-                self._peer = _PeerExchange(self.shard, self.kp, self.w, panels, dtype, device, rank, world, group)
-                self.comm = "peer"
-            except Exception as e:  # pragma: no cover - needs NVLink peers
-                import warnings
-                warnings.warn(f"symmetric-memory peer exchange unavailable ({e}); using NCCL collectives")
+        if world > 1:
+            self.B_pubs = [self.T.alloc(f"B{k}", self.shard, n, dtype) for k in range(slots)]
+            tbl = [torch.zeros_like(seg_table) for _ in range(world)]
+            dev_tbl = seg_table.to(device)
+            gl = [torch.zeros_like(dev_tbl) for _ in range(world)]
+            dist.all_gather(gl, dev_tbl, group=group)
+            tbl = [t.cpu() for t in gl]
+            mx = torch.tensor([max([sc.ncols for sc in self.sub[1:]] + [1])], dtype=torch.int64, device=device)
+            dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=group)
+            for sc in self.sub[1:]:
+                for k in range(slots):
+                    self.T.alloc(f"{sc.dBc_name}.{k}", int(mx), n, dtype)
+            recv = _exchange_lists(send_lists, rank, world, group)
+            # (peer r, its bucket name, offset, count, rows of MY shard it holds partials for)
+            self.incoming = [(r, f"dBc{int(tbl[r][rank][0])}", int(tbl[r][rank][1]), int(tbl[r][rank][2]), recv[r])
+                             for r in range(world) if r != rank]
+        else:
+            self.B_pubs = [torch.zeros((self.shard, n), dtype=dtype, device=device) for _ in range(slots)]
+            self.incoming = []
+        self.B_pub = self.B_pubs[0]
+        self._dbs = [torch.zeros((self.shard, n), dtype=dtype, device=device) for _ in range(slots)]
+        self._db = self._dbs[0]
+        self._ev_pulled = [None] * slots
+        self._ev_consumed = [None] * slots
 
     # ------------------------------------------------------------------ sharding helpers
     def shard_rows(self, B_full: torch.Tensor) -> torch.Tensor:
-        """This rank's equal-size row shard of a K×n dense operand (zero-padded past K)."""
-        s0 = self.rank * self.shard
+        """This rank's row shard of a K×n dense operand (zero-padded to the shard buffer size)."""
         out = torch.zeros((self.shard, self.n), dtype=B_full.dtype, device=B_full.device)
-        hi = min(self.cols, s0 + self.shard)
-        if hi > s0:
-            out[: hi - s0] = B_full[s0:hi]
+        if self.hi > self.lo:
+            out[: self.hi - self.lo] = B_full[self.lo:self.hi]
         return out
 
     def shard_rows_out(self, dY_full: torch.Tensor) -> torch.Tensor:
         """The rows of an M×n tensor that belong to this rank's row block of A."""
         return dY_full[self.r0:self.r1].contiguous()
 
-    # ------------------------------------------------------------------ collectives
-    def _all_gather(self, out: torch.Tensor, inp: torch.Tensor):
-        return dist.all_gather_into_tensor(out, inp, group=self.group, async_op=True)
+    def update_values(self, val_blk: torch.Tensor) -> None:
+        """New edge values for this rank's block (same structure): refresh every sub-CSR."""
+        for sc in self.sub:
+            sc.A.val.copy_(val_blk[sc.pos])
 
-    def _reduce_scatter(self, out: torch.Tensor, inp: torch.Tensor):
+    # ------------------------------------------------------------------ forward
+    def forward(self, B_shard: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
+                bias: Optional[torch.Tensor] = None, relu: bool = False, slot: int = 0) -> torch.Tensor:
+        """C_blk[m, n] = A_blk · B (B given as this rank's shard; None: ``self.B_pubs[slot]`` was filled
+        in place).  ``bias`` / ``relu`` are fused into the last accumulate pass."""
+        st, cp, C = self.st, self.cp, (out if out is not None else self._c)
+        B_pub, bname = self.B_pubs[slot], f"B{slot}"
+        cur = st.cur()
+        st.wait(cur, self._ev_pulled[slot])           # peers finished pulling the previous step's rows
+        if B_shard is not None and B_shard.data_ptr() != B_pub.data_ptr():
+            B_pub[: B_shard.shape[0]].copy_(B_shard)
+        last = len(self.sub) - 1
+        ev_g = []
+        if self.world > 1:
+            ev_pub = st.record()
+            with st.on_comm():
+                st.wait(st.comm, ev_pub)
+                self.T.barrier(0)                     # every rank has published its shard
+                self.T.refresh(bname)
+                for sc in self.sub[1:]:
+                    for s, off, cnt, ids in sc.segs:
+                        if cnt:
+                            cp.gather_rows(sc.Bc[slot][off:off + cnt], self.T.peer(bname, s), ids, max_ctas=self.pull_ctas)
+                    ev_g.append(st.record(st.comm))
+                self.T.barrier(1)                     # every rank is done reading the published shards
+                self._ev_pulled[slot] = st.record(st.comm)
+        ep = dict(bias=bias, relu=relu)
+        s0 = self.sub[0]
+        cp.spmm(s0.A, B_pub[: s0.A.cols], C, plan=s0.plan, tasks_per_warp=self.tpw, **(ep if last == 0 else {}))
+        for g, sc in enumerate(self.sub[1:], 1):
+            st.wait(cur, ev_g[g - 1])
+            cp.spmm(sc.A, sc.Bc[slot], C, plan=sc.plan, accumulate=True, tasks_per_warp=self.tpw if g < last else 0,
+                    **(ep if g == last else {}))
+        return C
+
+    # ------------------------------------------------------------------ backward wrt B
+    def backward(self, dY_blk: torch.Tensor, slot: int = 0) -> torch.Tensor:
+        """dB_shard[shard, n] = rows of A^T·dY owned by this rank, summed over ranks in rank order
+        (rows past this rank's shard size stay zero)."""
+        st, cp = self.st, self.cp
+        cur = st.cur()
+        dY_blk = dY_blk.contiguous()
+        db = self._dbs[slot]
+        st.wait(cur, self._ev_consumed[slot])         # peers finished reading the previous partials
+        for sc in self.sub[1:]:                       # remote partials first: peers are waiting for them
+            pub = self.T.bufs[f"{sc.dBc_name}.{slot}"][0]
+            cp.spmm_t(sc.A, dY_blk, pub[: sc.A.cols], plan=sc.plan, tasks_per_warp=self.tpw)
+        ev_rem = st.record()
+        s0 = self.sub[0]
+        cp.spmm_t(s0.A, dY_blk, db[: s0.A.cols], plan=s0.plan)
+        if self.world == 1:
+            return db
+        ev_loc = st.record()
+        with st.on_comm():
+            st.wait(st.comm, ev_rem)
+            self.T.barrier(2)                         # every rank's remote partials are complete
+            for sc in self.sub[1:]:
+                self.T.refresh(f"{sc.dBc_name}.{slot}")
+            st.wait(st.comm, ev_loc)
+            for r, name, off, cnt, ids in self.incoming:   # ascending rank order: deterministic sum
+                if cnt:
+                    cp.scatter_add_rows(db, self.T.peer(f"{name}.{slot}", r)[off:off + cnt], ids, max_ctas=0)
+            self.T.barrier(3)                         # every rank is done reading the partials
+            self._ev_consumed[slot] = st.record(st.comm)
+        st.wait(cur, self._ev_consumed[slot])
+        return db
+
+    # ------------------------------------------------------------------ SDDMM value gradient
+    def sddmm(self, dY_blk: torch.Tensor, slot: int = 0) -> torch.Tensor:
+        """dval of this rank's block, against the B rows the last ``forward`` of this slot holds
+        (its own shard + the pulled rows): no communication."""
+        dY_blk = dY_blk.contiguous()
+        dval = torch.zeros(self.A_blk.nnz, dtype=self.A_blk.val.dtype, device=dY_blk.device)
+        for g, sc in enumerate(self.sub):
+            if sc.A.nnz:
+                src = self.B_pubs[slot][: sc.A.cols] if g == 0 else sc.Bc[slot]
+                dval[sc.pos] = self.cp.sddmm(sc.A, dY_blk, src, plan=sc.plan)
+        return dval
+
+    def step(self, B_shard: torch.Tensor, dY_blk: torch.Tensor):
+        """One benchmark step: C_blk = A_blk·B and dB_shard = (A^T·dY)[own shard]."""
+        return self.forward(B_shard), self.backward(dY_blk)
+
+    def exchange_bytes(self) -> Dict[str, float]:
+        """Bytes this rank receives per product, next to what a full all-gather would move."""
+        s = 4 if self.dtype == torch.float32 else 2
+        return {"pulled": float(self.pulled_rows) * self.n * s,
+                "all_gather": float(self.cols - (self.hi - self.lo)) * self.n * s,
+                "local_nnz_fraction": self.local_fraction}
+
+
+# ---------------------------------------------------------------------------------------------
+# round 1's scheme, kept as the reference-style baseline
+
+class AllGatherSpmm:
+    """all-gather(B) → C_blk = A_blk·B;  partial A_blkᵀ·dY → reduce-scatter.  ``step`` hides the
+    collectives of one product behind the compute of the other; the compute kernels run as
+    short-lived CTAs (``tasks_per_warp``) so the NCCL kernels get SMs."""
+
+    def __init__(self, A: CsrMatrix, n: int, dtype: torch.dtype, rank: int, world: int, device, *,
+                 tasks_per_warp: int = 2, group=None, compute=None):
+        assert A.rows >= world, "fewer rows than ranks"
+        self.rank, self.world, self.device, self.group = rank, world, device, group
+        self.n, self.dtype, self.rows, self.cols = n, dtype, A.rows, A.cols
+        self.cp = compute or CudaCompute()
+        self.tpw = tasks_per_warp if world > 1 else 0
+        self.bounds = ops.row_blocks(A.crow, A.nnz, world).cpu().tolist()
+        self.r0, self.r1 = int(self.bounds[rank]), int(self.bounds[rank + 1])
+        self.A_blk = A.row_slice(self.r0, self.r1)
+        self.shard = shard_rows_count(A.cols, world)
+        self.kp = self.shard * world
+        self.lo, self.hi = min(A.cols, rank * self.shard), min(A.cols, (rank + 1) * self.shard)
+        blk = self.A_blk
+        self.plan = self.cp.plan(blk.crow, blk.col, blk.rows, blk.cols, n, dtype) if getattr(self.cp, "is_cuda", False) else None
+        self._b_full = torch.empty((self.kp, n), dtype=dtype, device=device)
+        self._c = torch.empty((blk.rows, n), dtype=dtype, device=device)
+        self._db_part = torch.zeros((self.kp, n), dtype=dtype, device=device)
+        self._db = torch.empty((self.shard, n), dtype=dtype, device=device)
+        self._nccl = dist.is_initialized() and dist.get_backend(group) == "nccl"
+        self.comm = "nccl all-gather / reduce-scatter" if self._nccl else "gloo"
+
+    shard_rows = ShardedSpmm.shard_rows
+    shard_rows_out = ShardedSpmm.shard_rows_out
+
+    def _reduce_scatter(self, out, inp):
         if self._nccl:
             return dist.reduce_scatter_tensor(out, inp, group=self.group, async_op=True)
-        # gloo has no reduce-scatter: all-reduce then keep the local shard (host-logic tests only)
-        dist.all_reduce(inp, group=self.group)
+        dist.all_reduce(inp, group=self.group)    # gloo has no reduce-scatter (host-logic tests only)
         out.copy_(inp[self.rank * self.shard:(self.rank + 1) * self.shard])
         return None
 
-    # ------------------------------------------------------------------ forward
     def forward(self, B_shard: torch.Tensor) -> torch.Tensor:
-        """C_blk[m, n] = A_blk · allgather(B_shard), panel-pipelined."""
-        A, w = self.A_blk, self.w
-        if self._peer is not None:
-            px = self._peer
-            px.begin_forward()
-            events = []
-            for j in range(self.panels):
-                px.send[j].copy_(B_shard[:, j * w:(j + 1) * w])
-                events.append(px.all_gather_panel(j, self._b_full[j]))
-            for j in range(self.panels):
-                torch.cuda.current_stream().wait_event(events[j])
-                self.spmm_fn(A.crow, A.col, A.val, self._b_full[j][: self.cols], A.rows, A.cols,
-                             self._c[:, j * w:(j + 1) * w])
-            return self._c
-        works = []
-        for j in range(self.panels):
-            self._b_send[j].copy_(B_shard[:, j * w:(j + 1) * w])
-            works.append(self._all_gather(self._b_full[j], self._b_send[j]))
-        for j in range(self.panels):
-            works[j].wait()  # compute stream waits for panel j only; later panels keep flowing
-            self.spmm_fn(A.crow, A.col, A.val, self._b_full[j][: self.cols], A.rows, A.cols,
-                         self._c[:, j * w:(j + 1) * w])
+        w = dist.all_gather_into_tensor(self._b_full, B_shard.contiguous(), group=self.group, async_op=True)
+        w.wait()
+        self.cp.spmm(self.A_blk, self._b_full[: self.cols], self._c, plan=self.plan)
         return self._c
 
-    # ------------------------------------------------------------------ backward wrt B
     def backward(self, dY_blk: torch.Tensor) -> torch.Tensor:
-        """dB_shard[shard, n] = reduce_scatter(A_blkᵀ · dY_blk), panel-pipelined."""
-        w = self.w
-        if self._peer is not None and self.At_blk is not None:
-            px, At = self._peer, self.At_blk
-            px.begin_backward()
-            events = []
-            for j in range(self.panels):
-                part = px.part[j]
-                if self.kp > self.cols:
-                    part[self.cols:].zero_()
-                self.spmm_fn(At.crow, At.col, At.val, dY_blk[:, j * w:(j + 1) * w], At.rows, At.cols, part[: self.cols])
-                events.append(px.reduce_scatter_panel(j, self._db_out[j]))
-            for j in range(self.panels):
-                torch.cuda.current_stream().wait_event(events[j])
-                self._db[:, j * w:(j + 1) * w].copy_(self._db_out[j])
-            return self._db
-        works: List[Optional[object]] = []
-        for j in range(self.panels):
-            part = self._db_part[j]
-            if self.kp > self.cols:
-                part[self.cols:].zero_()
-            dyj = dY_blk[:, j * w:(j + 1) * w]
-            if self.At_blk is not None:
-                At = self.At_blk
-                self.spmm_fn(At.crow, At.col, At.val, dyj, At.rows, At.cols, part[: self.cols])
-            else:
-                A = self.A_blk
-                part[: self.cols].copy_(ops.spmm_csr_grad_b_compute(A.crow, A.col, A.val, dyj.contiguous(),
-                                                                   A.rows, A.cols))
-            works.append(self._reduce_scatter(self._db_out[j], part))
-        for j in range(self.panels):
-            if works[j] is not None:
-                works[j].wait()
-            self._db[:, j * w:(j + 1) * w].copy_(self._db_out[j])
+        self.cp.spmm_t(self.A_blk, dY_blk.contiguous(), self._db_part[: self.cols], plan=self.plan)
+        w = self._reduce_scatter(self._db, self._db_part)
+        if w is not None:
+            w.wait()
         return self._db
 
-    def step(self, B_shard: torch.Tensor, dY_blk: torch.Tensor, overlap: bool = True):
-        """One benchmark step: C_blk = A_blk·allgather(B) and dB_shard = reduce_scatter(A_blkᵀ·dY).
-        The two halves are independent, so with ``overlap`` the collectives of one hide behind the
-        compute of the other:  all-gather(B) ‖ A_blkᵀ·dY,  then  reduce-scatter(dB) ‖ A_blk·B.
-        (Measured on 8 B200s, cfg2: splitting the dense width into column panels to overlap inside
-        one product costs more in narrower gathers than the overlap returns; whole-width products
-        with cross-product overlap are faster — profiles/r1_multigpu.md.)"""
-        if not overlap or self.At_blk is None or self.panels != 1:
-            return self.forward(B_shard), self.backward(dY_blk)
-        A, At, n = self.A_blk, self.At_blk, self.n
-        if self._peer is not None:
-            px = self._peer
-            cur = torch.cuda.current_stream()
-            px.begin_forward()
-            px.send[0].copy_(B_shard)
-            ev_ag = px.all_gather_panel(0, self._b_full[0])           # copy engines, side stream
-            px.begin_backward()
-            part = px.part[0]
-            if self.kp > self.cols:
-                part[self.cols:].zero_()
-            self.spmm_fn(At.crow, At.col, At.val, dY_blk, At.rows, At.cols, part[: self.cols])
-            ev_rs = px.reduce_scatter_panel(0, self._db_out[0])      # pulls + ordered sum, side stream
-            cur.wait_event(ev_ag)
-            self.spmm_fn(A.crow, A.col, A.val, self._b_full[0][: self.cols], A.rows, A.cols, self._c)
-            cur.wait_event(ev_rs)
-            self._db.copy_(self._db_out[0])
-            return self._c, self._db
-        self._b_send[0].copy_(B_shard)
-        w_ag = self._all_gather(self._b_full[0], self._b_send[0])     # NCCL stream
-        part = self._db_part[0]
-        if self.kp > self.cols:
-            part[self.cols:].zero_()
-        self.spmm_fn(At.crow, At.col, At.val, dY_blk, At.rows, At.cols, part[: self.cols])
-        w_rs = self._reduce_scatter(self._db_out[0], part)
+    def step(self, B_shard: torch.Tensor, dY_blk: torch.Tensor):
+        w_ag = dist.all_gather_into_tensor(self._b_full, B_shard.contiguous(), group=self.group, async_op=True)
+        self.cp.spmm_t(self.A_blk, dY_blk.contiguous(), self._db_part[: self.cols], plan=self.plan, tasks_per_warp=self.tpw)
+        w_rs = self._reduce_scatter(self._db, self._db_part)
         w_ag.wait()
-        self.spmm_fn(A.crow, A.col, A.val, self._b_full[0][: self.cols], A.rows, A.cols, self._c)
+        self.cp.spmm(self.A_blk, self._b_full[: self.cols], self._c, plan=self.plan, tasks_per_warp=self.tpw)
         if w_rs is not None:
             w_rs.wait()
-        self._db.copy_(self._db_out[0])
         return self._c, self._db
-
-    def capture(self, fn: Callable[[], object], warmup: int = 3):
-        """Capture ``fn`` (a closure over static input tensors, e.g. ``lambda: self.step(B, dY)``)
-        into a CUDA graph — kernels, copies and the NCCL collectives — and return the replay
-        callable.  A step at 8 GPUs is ~30 short launches; replaying one graph removes the host
-        launch gaps between them (the reference's lazy mode does the same per kernel,
-        oneflow/core/kernel/user_kernel.cpp:689-714).  Falls back to eager ``fn`` if capture is
-        not possible (e.g. gloo / CPU)."""
-        if not (torch.cuda.is_available() and str(self.device).startswith("cuda")):
-            return fn
-        try:
-            side = torch.cuda.Stream(device=self.device)
-            side.wait_stream(torch.cuda.current_stream(self.device))
-            with torch.cuda.stream(side):
-                for _ in range(warmup):
-                    fn()
-            torch.cuda.current_stream(self.device).wait_stream(side)
-            torch.cuda.synchronize(self.device)
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                fn()
-            torch.cuda.synchronize(self.device)
-            return graph.replay
-        except Exception as e:  # pragma: no cover - depends on the NCCL / driver combination
-            import warnings
-            warnings.warn(f"CUDA-graph capture of the sharded step failed ({e}); running eagerly")
-            torch.cuda.synchronize(self.device)
-            return fn

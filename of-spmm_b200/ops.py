@@ -134,6 +134,7 @@ class SpmmPlan:
         self.variant, self.part = self._build(a_crow, a_rows, self.nnz, variant)
         self.t_crow = self.t_col = self.t_perm = self.t_part = None
         self.t_variant = _lib.VARIANT_AUTO
+        self._t_val, self._t_val_key = None, None
         if transpose:
             self.t_crow, self.t_col, _, self.t_perm = csr_transpose(a_crow, a_col, None, a_rows, a_cols, want_perm=True)
             self.t_variant, self.t_part = self._build(self.t_crow, a_cols, self.nnz, None)
@@ -157,6 +158,20 @@ class SpmmPlan:
     def matches(self, a_crow, a_col, a_rows, a_cols, n, dtype) -> bool:
         return (self.key == (a_crow.data_ptr(), a_col.data_ptr(), a_crow._version, a_col._version, a_rows, a_cols,
                              int(a_col.numel())) and self.n == int(n) and self.dtype == dtype)
+
+    def transposed_values(self, a_val: torch.Tensor) -> torch.Tensor:
+        """Values of A^T for ``a_val`` = a_val[t_perm].  Re-gathered whenever the tensor's identity or
+        autograd version changed (in-place updates bump the version), reused otherwise — a proof of
+        "unchanged" the C++ glue does not have, which therefore gathers on every call."""
+        key = (a_val.data_ptr(), a_val._version, a_val.dtype)
+        if self._t_val is None or self._t_val_key != key:
+            out = torch.empty(self.nnz, dtype=a_val.dtype, device=a_val.device)
+            with torch.cuda.device(a_val.device):
+                check(_lib.lib().ofspmm_permute_values(_ptr(a_val), _DENSE[a_val.dtype], _ptr(self.t_perm),
+                                                       _INDEX[self.t_perm.dtype], self.nnz, _ptr(out),
+                                                       _stream_ptr(a_val)), "permute_values")
+            self._t_val, self._t_val_key = out, key
+        return self._t_val
 
     def variant_name(self, transposed: bool = False) -> str:
         v = self.t_variant if transposed else self.variant
@@ -214,11 +229,12 @@ def spmm_csr_compute(a_crow, a_col, a_val, b, a_rows: int, a_cols: int,
 def spmm_csr_grad_b_compute(a_crow, a_col, a_val, dy, a_rows: int, a_cols: int,
                             transposed: Optional[Tuple[torch.Tensor, torch.Tensor, torch.Tensor]] = None,
                             out: Optional[torch.Tensor] = None, *, plan: Optional[SpmmPlan] = None,
-                            atomic: bool = False, tasks_per_warp: int = 0) -> torch.Tensor:
+                            atomic: bool = False, tasks_per_warp: int = 0, regather: bool = False) -> torch.Tensor:
     """SpmmCsrGradBKernel::Compute — db[a_cols, n] = A^T · dy.  Routes, in order of preference:
 
-      * ``plan`` with a transposed structure → ``ofspmm_bwd_b_cached`` (values re-gathered through
-        ``t_perm`` each call; deterministic);
+      * ``plan`` with a transposed structure → forward kernel on the cached structure of A^T; the
+        values are re-gathered through ``t_perm`` whenever ``a_val``'s (pointer, version) changed,
+        or on every call with ``regather=True`` (= ``ofspmm_bwd_b_cached``, the glue's route);
       * ``transposed`` = (t_crow, t_col, t_val) from csr_transpose → forward kernel on that CSR;
       * default → ``ofspmm_bwd_b_transient`` (A^T built inside the workspace; deterministic and
         2-9x faster than the scatter on the BASELINE graphs);
@@ -236,16 +252,24 @@ def spmm_csr_grad_b_compute(a_crow, a_col, a_val, dy, a_rows: int, a_cols: int,
     if plan is not None and plan.t_crow is not None and not atomic:
         _chk(plan.matches(a_crow, a_col, a_rows, a_cols, n, dt), "plan was built for another CSR structure / n / dtype")
         with torch.cuda.device(dy.device):
-            A = _csr_struct(a_crow, a_col, a_val, a_rows, a_cols)
-            vs = 4 if A.val_dtype == _lib.DTYPE_FLOAT else 2
-            nbytes = ((max(A.nnz, 1) * vs + 255) // 256) * 256 + \
-                L.ofspmm_fwd_ex_workspace_bytes(a_cols, a_rows, A.nnz, n, _DENSE[dt], plan.t_variant)
-            nbytes = max(nbytes, L.ofspmm_bwd_b_cached_workspace_bytes(a_rows, a_cols, A.nnz, n, _DENSE[dt], A.val_dtype))
-            ws, wsp = _workspace(nbytes, dy.device)
-            o = _opts(0, tasks_per_warp, plan.t_variant, plan.t_part)
-            check(L.ofspmm_bwd_b_cached(ctypes.byref(A), _ptr(plan.t_crow), _ptr(plan.t_col), _ptr(plan.t_perm),
-                                        _ptr(dy), _ptr(out), n, _DENSE[dt], ctypes.byref(o), wsp, nbytes,
-                                        _stream_ptr(dy)), "spmm_csr_grad_b(cached structure)")
+            if regather:   # the C ABI route the OneFlow glue uses: values gathered inside the call
+                A = _csr_struct(a_crow, a_col, a_val, a_rows, a_cols)
+                vs = 4 if A.val_dtype == _lib.DTYPE_FLOAT else 2
+                nbytes = ((max(A.nnz, 1) * vs + 255) // 256) * 256 + \
+                    L.ofspmm_fwd_ex_workspace_bytes(a_cols, a_rows, A.nnz, n, _DENSE[dt], plan.t_variant)
+                nbytes = max(nbytes, L.ofspmm_bwd_b_cached_workspace_bytes(a_rows, a_cols, A.nnz, n, _DENSE[dt], A.val_dtype))
+                ws, wsp = _workspace(nbytes, dy.device)
+                o = _opts(0, tasks_per_warp, plan.t_variant, plan.t_part)
+                check(L.ofspmm_bwd_b_cached(ctypes.byref(A), _ptr(plan.t_crow), _ptr(plan.t_col), _ptr(plan.t_perm),
+                                            _ptr(dy), _ptr(out), n, _DENSE[dt], ctypes.byref(o), wsp, nbytes,
+                                            _stream_ptr(dy)), "spmm_csr_grad_b(cached structure)")
+            else:          # values of A^T kept while a_val's (pointer, version) is unchanged
+                At = _csr_struct(plan.t_crow, plan.t_col, plan.transposed_values(a_val), a_cols, a_rows)
+                nbytes = L.ofspmm_fwd_ex_workspace_bytes(a_cols, a_rows, At.nnz, n, _DENSE[dt], plan.t_variant)
+                ws, wsp = _workspace(nbytes, dy.device)
+                o = _opts(0, tasks_per_warp, plan.t_variant, plan.t_part)
+                check(L.ofspmm_fwd_ex(ctypes.byref(At), _ptr(dy), n, _ptr(out), n, n, _DENSE[dt], ctypes.byref(o), wsp, nbytes,
+                                      _stream_ptr(dy)), "spmm_csr_grad_b(cached structure + values)")
         return out
     if transposed is None and not atomic:
         return spmm_csr_grad_b_transient_compute(a_crow, a_col, a_val, dy, a_rows, a_cols, out=out)

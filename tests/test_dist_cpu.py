@@ -1,8 +1,10 @@
 """World-size-2/3 gloo tests (CPU) of the multi-GPU host logic in of-spmm_b200/dist.py: nnz-balanced
-row blocks, equal B shards with padding, panel-pipelined all-gather / reduce-scatter and the
-reassembly of C and dB.  The per-rank compute callbacks are CPU stand-ins built on the oracle
-(tests may use it as the checker's arithmetic); the CUDA kernels themselves are covered by the
--m gpu tests and the N>1 bench."""
+row blocks, equal B shards with padding, the split of a block into a local and compact remote
+sub-CSRs, the needed-rows pull / ordered scatter-add exchange (and round 1's all-gather /
+reduce-scatter scheme), the SDDMM on the pulled rows and the reassembly of C, dB and dval.  The
+per-rank compute is a CPU stand-in built on the oracle (tests may use it as the checker's
+arithmetic) and the transport is the all-gather emulation of peer memory; the CUDA kernels and the
+symmetric-memory transport are covered by tests/test_gpu_multi.py and the N>1 bench."""
 import os
 import socket
 import sys
@@ -24,20 +26,44 @@ def _free_port():
     return p
 
 
-def _cpu_spmm(crow, col, val, b, rows, cols, out):
-    from oracle import oracle as O
-    res = O.spmm_f32(crow.numpy(), col.numpy(), val.numpy(), b.contiguous().numpy(), cols)
-    out.copy_(torch.from_numpy(res))
-    return out
+class OracleCompute:
+    """CPU stand-in for dist.CudaCompute: same interface, oracle arithmetic."""
+    is_cuda = False
+
+    def plan(self, *a, **k):
+        return None
+
+    def spmm(self, A, b, out, plan=None, accumulate=False, tasks_per_warp=0, bias=None, relu=False):
+        from oracle import oracle as O
+        res = torch.from_numpy(O.spmm_f32(A.crow.numpy(), A.col.numpy(), A.val.numpy(), b.contiguous().numpy(), A.cols))
+        if accumulate:
+            res = res + out
+        if bias is not None:
+            res = res + bias
+        if relu:
+            res = res.clamp(min=0)
+        out.copy_(res)
+        return out
+
+    def spmm_t(self, A, dy, out, plan=None, tasks_per_warp=0):
+        from oracle import oracle as O
+        out.copy_(torch.from_numpy(O.spmm_t_f32(A.crow.numpy(), A.col.numpy(), A.val.numpy(), dy.contiguous().numpy(), A.cols)))
+        return out
+
+    def sddmm(self, A, dy, b, plan=None):
+        from oracle import oracle as O
+        return torch.from_numpy(O.sddmm_f32(A.crow.numpy(), A.col.numpy(), dy.contiguous().numpy(), b.contiguous().numpy()))
+
+    def gather_rows(self, dst, src, index, max_ctas=0):
+        dst.copy_(src[index.long()])
+        return dst
+
+    def scatter_add_rows(self, dst, src, index, max_ctas=0):
+        dst[index.long()] += src
+        return dst
 
 
-def _cpu_transpose(crow, col, val, rows, cols):
-    from oracle import oracle as O
-    tc, tcol, tv, _ = O.csr_transpose(crow.numpy(), col.numpy(), val.numpy(), cols)
-    return (torch.from_numpy(tc.astype(np.int32)), torch.from_numpy(tcol.astype(np.int32)), torch.from_numpy(tv))
-
-
-def _worker(rank, world, port, n, panels, q):
+def _worker(rank, world, port, n, scheme, buckets, q):
     sys.path.insert(0, ROOT)
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -47,14 +73,26 @@ def _worker(rank, world, port, n, panels, q):
         import ofspmm_b200 as ofs
         dmod = importlib.import_module("of-spmm_b200.dist")
         A = ofs.graphs.rmat_csr(10, 12, seed=4)        # skewed rows: equal-count blocks would be unbalanced
-        A = ofs.graphs.CsrMatrix(A.crow, A.col, A.val, A.rows, A.cols)
-        K = A.cols
-        B = ofs.graphs.dense_operand(K, n, 5)
+        B = ofs.graphs.dense_operand(A.cols, n, 5)
         dY = ofs.graphs.upstream_grad(A.rows, n, 6)
-        sh = dmod.ShardedSpmm(A, n, torch.float32, rank, world, "cpu", bwd="transpose", panels=panels,
-                              spmm_fn=_cpu_spmm, transpose_fn=_cpu_transpose)
-        C_blk, dB_shard = sh.step(sh.shard_rows(B), sh.shard_rows_out(dY))
-        q.put((rank, sh.bounds, sh.r0, sh.r1, sh.shard, C_blk.clone().numpy(), dB_shard.clone().numpy()))
+        bias = torch.linspace(-1, 1, n)
+        if scheme == "pull":
+            sh = dmod.ShardedSpmm(A, n, torch.float32, rank, world, "cpu", buckets=buckets, compute=OracleCompute())
+        else:
+            sh = dmod.AllGatherSpmm(A, n, torch.float32, rank, world, "cpu", compute=OracleCompute())
+        out = {}
+        for it in range(2):                             # twice: the publish / consume hand-shake repeats
+            C_blk, dB_shard = sh.step(sh.shard_rows(B), sh.shard_rows_out(dY))
+        out["C"], out["dB"] = C_blk.clone().numpy(), dB_shard.clone().numpy()
+        if scheme == "pull":
+            out["dval"] = sh.sddmm(sh.shard_rows_out(dY)).numpy()
+            out["C_ep"] = sh.forward(sh.shard_rows(B), bias=bias, relu=True).clone().numpy()
+            out["stats"] = sh.exchange_bytes()
+            out["nsub"] = len(sh.sub)
+            # new edge values, same structure
+            sh.update_values(sh.A_blk.val * -2.0)
+            out["C_scaled"] = sh.forward(sh.shard_rows(B)).clone().numpy()
+        q.put((rank, sh.bounds, sh.r0, sh.r1, sh.shard, out))
         dist.barrier()
         dist.destroy_process_group()
     except Exception:   # report instead of leaving the parent (and the peer rank) waiting
@@ -63,20 +101,21 @@ def _worker(rank, world, port, n, panels, q):
         os._exit(1)
 
 
-@pytest.mark.parametrize("world,n,panels", [(2, 16, 2), (2, 12, 1), (3, 32, 4)])
-def test_sharded_spmm_gloo(world, n, panels):
+@pytest.mark.parametrize("world,n,scheme,buckets", [(2, 16, "pull", 1), (3, 12, "pull", 1), (3, 8, "pull", 2),
+                                                    (2, 12, "allgather", 1)])
+def test_sharded_spmm_gloo(world, n, scheme, buckets):
     sys.path.insert(0, ROOT)
     import ofspmm_b200 as ofs
     from oracle import oracle as O
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, n, panels, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n, scheme, buckets, q)) for r in range(world)]
     for p in procs:
         p.start()
     results = []
     for _ in range(world):
-        r = q.get(timeout=120)
+        r = q.get(timeout=180)
         if r[0] == "error":
             for p in procs:
                 p.kill()
@@ -91,7 +130,7 @@ def test_sharded_spmm_gloo(world, n, panels):
     B = ofs.graphs.dense_operand(A.cols, n, 5).numpy()
     dY = ofs.graphs.upstream_grad(A.rows, n, 6).numpy()
     crow, col, val = A.crow.numpy(), A.col.numpy(), A.val.numpy()
-    C_ref = O.spmm_f32(crow, col, val, B)
+    C_ref = O.spmm_f64(crow, col, val, B)
     dB_ref = O.spmm_t_f64(crow, col, val, dY, A.cols)
 
     bounds = results[0][1]
@@ -99,11 +138,26 @@ def test_sharded_spmm_gloo(world, n, panels):
     assert bounds[0] == 0 and bounds[-1] == A.rows
     per_rank_nnz = np.diff(crow[np.array(bounds)])
     assert per_rank_nnz.max() <= 1.25 * per_rank_nnz.mean()   # nnz-balanced (equal-count would not be)
-    C = np.concatenate([r[5] for r in results], axis=0)
+    C = np.concatenate([r[5]["C"] for r in results], axis=0)
     assert C.shape == C_ref.shape
-    assert np.array_equal(C, C_ref)                           # same arithmetic per row → bitwise
+    np.testing.assert_allclose(C, C_ref, rtol=1e-4, atol=1e-4)
     shard = results[0][4]
-    dB = np.concatenate([r[6] for r in results], axis=0)
+    dB = np.concatenate([r[5]["dB"] for r in results], axis=0)
     assert dB.shape[0] == shard * world >= A.cols
     np.testing.assert_allclose(dB[: A.cols], dB_ref, rtol=1e-4, atol=1e-4)
     assert np.all(dB[A.cols:] == 0)                            # padding rows stay zero
+    if scheme != "pull":
+        return
+    dval = np.concatenate([r[5]["dval"] for r in results])
+    dv_ref, _ = O.sddmm_f64(crow, col, dY, B)
+    np.testing.assert_allclose(dval, dv_ref, rtol=1e-4, atol=1e-4)
+    bias = np.linspace(-1, 1, n)
+    C_ep = np.concatenate([r[5]["C_ep"] for r in results], axis=0)
+    np.testing.assert_allclose(C_ep, np.maximum(C_ref + bias[None, :], 0), rtol=1e-4, atol=1e-4)
+    C_scaled = np.concatenate([r[5]["C_scaled"] for r in results], axis=0)
+    np.testing.assert_allclose(C_scaled, -2.0 * C_ref, rtol=1e-4, atol=2e-4)
+    for r in results:
+        st = r[5]["stats"]
+        assert r[5]["nsub"] == 1 + min(buckets, world - 1)
+        assert 0 < st["pulled"] <= st["all_gather"]           # never more than an all-gather moves
+        assert 0.0 < st["local_nnz_fraction"] < 1.0
