@@ -232,7 +232,8 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------
 # verification of the timed outputs against the oracle (sampled rows, any size)
 
-def verify_sample(A, B_full, dY_full, C_blk, r0, r1, dB_shard, s0, s1, dtype, nsample=256, seed=7):
+def verify_sample(A, B_full, dY_full, C_blk, r0, r1, dB_shard, s0, s1, dtype, nsample=256, seed=7, relu=False,
+                  only_c=False):
     """>= nsample rows of C and of dB taken from the buffers the timed loop wrote, against the fp64
     oracle on exactly those rows (SURVEY.md §8c tolerances).  A / B_full / dY_full are the whole
     operands on this rank's device; C_blk = rows [r0, r1) of C, dB_shard = rows [s0, s1) of dB."""
@@ -258,10 +259,15 @@ def verify_sample(A, B_full, dY_full, C_blk, r0, r1, dB_shard, s0, s1, dtype, ns
     val = A.val[pos].float().cpu().numpy()
     want = O.spmm_f64(crow, mini_col.cpu().numpy(), val, Bh, max(1, ucol.numel()))
     amax = O.spmm_absmax(crow, mini_col.cpu().numpy(), val, Bh, max(1, ucol.numel()))
+    if relu:
+        want = np.maximum(want, 0.0)
     got = C_blk[(rows - r0)].float().cpu().numpy().astype(np.float64)
     tol = (O.fp32_tolerance(want, amax, np.diff(crow)) + 2.0 ** -21 * np.abs(want)) if f32 else (1e-2 * np.abs(want) + 2.0 ** -6 * amax)
     res["C_rows"] = int(rows.numel())
     res["C_ok"] = bool((np.abs(got - want) <= tol + 1e-30).all())
+    if only_c:
+        res["ok"] = res["C_ok"]
+        return res
     # ---- dB rows (= columns of A): every non-zero of the sampled columns, over the whole matrix
     cols_s = torch.unique(torch.randint(s0, max(s0 + 1, s1), (nsample,), generator=g)).to(A.crow.device)
     hit = torch.isin(A.col, cols_s.to(A.col.dtype))

@@ -45,7 +45,7 @@ int launch_full(FwdParams p, int panels, const FwdLaunch& L, cudaStream_t stream
     }
   }
   if (gx64 == ctas_all) p.counter = nullptr;  // one task per warp: nothing to draw
-  if (p.counter != nullptr) OFSPMM_CUDA_OK(cudaMemsetAsync(p.counter, 0, sizeof(unsigned long long), stream));
+  if (p.counter != nullptr) OFSPMM_CUDA_OK(cudaMemsetAsync(p.counter, 0, sizeof(unsigned int), stream));
   const int gx = static_cast<int>(gx64);
   kern<<<gx, WARPS * 32, smem, stream>>>(p);
   count_launch();

@@ -22,7 +22,7 @@ int launch_persistent(Kern kern, SddmmParams p, size_t smem, bool dynamic_ok, Ke
   const int64_t resident = static_cast<int64_t>(dev.sms) * occ;
   const int gx = static_cast<int>(ctas_needed < resident ? ctas_needed : resident);
   if (!dynamic_ok || gx == ctas_needed) p.counter = nullptr;
-  if (p.counter != nullptr) OFSPMM_CUDA_OK(cudaMemsetAsync(p.counter, 0, sizeof(unsigned long long), stream));
+  if (p.counter != nullptr) OFSPMM_CUDA_OK(cudaMemsetAsync(p.counter, 0, sizeof(unsigned int), stream));
   kern<<<gx, WARPS * 32, smem, stream>>>(p);
   count_launch();
   OFSPMM_CUDA_OK(cudaGetLastError());
@@ -83,7 +83,7 @@ int launch_idx(const SddmmParams& p, int dense_dtype, int val_dtype, bool aligne
 int launch_sddmm(const ofspmm_csr* A, const void* dY, const void* B, void* dval, int64_t n,
                  int dense_dtype, const void* part, void* counter, int64_t P, cudaStream_t stream) {
   SddmmParams p;
-  p.counter = static_cast<unsigned long long*>(counter);
+  p.counter = static_cast<unsigned int*>(counter);
   p.crow = A->crow;
   p.col = A->col;
   p.dY = dY;

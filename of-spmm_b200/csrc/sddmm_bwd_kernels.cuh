@@ -12,7 +12,7 @@ struct SddmmParams {
   const void* B;    // cols x n
   void* dval;       // nnz
   const int2* part;
-  unsigned long long* counter;  // dynamic task order (see spmm_merge_kernel); nullptr = static
+  unsigned int* counter;  // dynamic task order (see spmm_merge_kernel); nullptr = static
   long long cols;
   int rows;
   int nnz;
@@ -83,16 +83,22 @@ sddmm_merge_kernel(const SddmmParams p) {
 
   const int total_warps = gridDim.x * WARPS;
   uint32_t phase = 0;
+  unsigned pending = 0;
 
-  // task order: static interleave, or drawn from a counter in launch order (spmm_merge_kernel)
-  for (long long kk = blockIdx.x * WARPS + warp; kk < p.P;) {
-    const int k = static_cast<int>(kk);
-    kk += total_warps;
-    if (p.counter != nullptr) {
-      unsigned long long drawn = 0;
-      if (lane == 0) drawn = atomicAdd(p.counter, 1ull);
-      kk = static_cast<long long>(__shfl_sync(0xffffffffu, drawn, 0)) + total_warps;
-    }
+  // task order: static interleave, or drawn from a counter in launch order; two tasks in hand, the
+  // next draw in flight during the task, the next partition entry prefetched (spmm_merge_kernel)
+  const bool dynamic = p.counter != nullptr;
+  auto draw_now = [&]() -> int {
+    unsigned drawn = 0;
+    if (lane == 0) drawn = atomicAdd(p.counter, 1u);
+    return static_cast<int>(__shfl_sync(0xffffffffu, drawn, 0));
+  };
+  int k = dynamic ? draw_now() : blockIdx.x * WARPS + warp;
+  int k1 = dynamic ? draw_now() : k + total_warps;
+  for (; k < p.P; k = k1, k1 = dynamic ? static_cast<int>(__shfl_sync(0xffffffffu, pending, 0)) : k1 + total_warps) {
+    pending = 0;
+    if (dynamic && lane == 0) pending = atomicAdd(p.counter, 1u);
+    if (k1 < p.P && lane == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(&p.part[k1]));
     const int2 ps = __ldg(&p.part[k]);
     const int2 pe = __ldg(&p.part[k + 1]);
     const int rs = ps.x, ns = ps.y, re = pe.x, ne = pe.y;

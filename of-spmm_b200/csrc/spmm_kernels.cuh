@@ -63,7 +63,7 @@ struct FwdParams {
   long long ldb;     // row stride of B in elements (>= n)
   long long ldc;     // row stride of C in elements (>= n)
   const void* bias;  // n elements of the dense dtype (kFwdBias)
-  unsigned long long* counter;  // dynamic task order: zeroed before the launch; nullptr = static
+  unsigned int* counter;  // dynamic task order: zeroed before the launch; nullptr = static
   unsigned flags;    // kFwd* epilogue bits
   int max_tasks;     // tasks a warp runs before its CTA may retire (0: until the list is empty)
 };
@@ -301,24 +301,32 @@ spmm_merge_kernel(const FwdParams p) {
   // Task order.  Static: warp w runs tasks w, w + W, w + 2W, ...  Dynamic (p.counter != nullptr):
   // every task is drawn from a global counter, i.e. handed out in the order warps ask for work, so
   // the rows in flight chip-wide always form ONE contiguous window of the matrix however unevenly
-  // the warps progress (keeps the B rows of that window L2-resident — measured -13 % on the
-  // Reddit-shaped, -26 % on the products-shaped graph — and evens out the tail).  The next draw is
-  // issued at the top of a task and consumed at its end: its latency is hidden.  A warp stops
-  // after p.max_tasks tasks (short-lived CTAs for the multi-GPU overlap); it never draws a task it
+  // the warps progress (keeps the B rows of that window L2-resident — measured -11 % on the
+  // Reddit-shaped, -23 % on the products-shaped graph — and evens out the tail).
+  // A warp holds two tasks: the one it runs (t) and the next (t1); the draw for the one after is
+  // issued at the top of a task and its result is only read at the end (the atomic's latency hides
+  // behind the task), and the partition entry of t1 is prefetched into L2 meanwhile.  A warp stops
+  // after p.max_tasks tasks (short-lived CTAs for the multi-GPU overlap) and never draws a task it
   // will not run.
+  const int total = static_cast<int>(total_tasks);
   const int max_tasks = p.max_tasks > 0 ? p.max_tasks : 0x7fffffff;
-  auto draw = [&]() -> long long {
-    unsigned long long drawn = 0;
-    if (lane == 0) drawn = atomicAdd(p.counter, 1ull);
-    return static_cast<long long>(__shfl_sync(0xffffffffu, drawn, 0));
+  const bool dynamic = p.counter != nullptr;
+  auto draw_now = [&]() -> int {
+    unsigned drawn = 0;
+    if (lane == 0) drawn = atomicAdd(p.counter, 1u);
+    return static_cast<int>(__shfl_sync(0xffffffffu, drawn, 0));
   };
-  long long t = p.counter != nullptr ? draw() : static_cast<long long>(blockIdx.x) * WARPS + warp;
-  for (int done = 0; t < total_tasks && done < max_tasks; ++done) {
-    long long t_next = t + total_warps;
-    if (p.counter != nullptr) t_next = done + 1 < max_tasks ? draw() : total_tasks;
+  int t = dynamic ? draw_now() : blockIdx.x * WARPS + warp;
+  int t1 = dynamic ? (max_tasks > 1 ? draw_now() : total) : t + total_warps;
+  for (int done = 0; t < total && done < max_tasks; ++done) {
+    unsigned pending = 0;
+    const bool more = done + 2 < max_tasks;
+    if (dynamic && more && lane == 0) pending = atomicAdd(p.counter, 1u);   // read at the end of the task
+    if (t1 < total && lane == 0)
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(&p.part[t1 % p.P]));
     // panel-major: all tasks of column panel 0, then panel 1, ... (keeps the B panel in L2)
-    const int panel = static_cast<int>(t / p.P);
-    const int k = static_cast<int>(t - static_cast<long long>(panel) * p.P);
+    const int panel = t / p.P;
+    const int k = t - panel * p.P;
     const int col0 = panel * (LPR * VEC * CH) + lig * VEC;
     unsigned chmask = 0;
     uint32_t choff[CH];  // byte offset of chunk ch from the lane base (0-column for masked chunks)
@@ -501,7 +509,8 @@ spmm_merge_kernel(const FwdParams p) {
         }
       }
     }
-    t = t_next;
+    t = t1;
+    t1 = dynamic ? (more ? static_cast<int>(__shfl_sync(0xffffffffu, pending, 0)) : total) : t1 + total_warps;
   }
 }
 

@@ -73,3 +73,80 @@ class GCN2:
         [+ SDDMM when edge weights need a gradient], each 2·nnz·hidden."""
         per = 2 * self.A.nnz * self.W1.shape[1]
         return 2 * (2 + (1 if self.val.requires_grad else 0)) * per
+
+
+class ShardedGCN2:
+    """The same two GCNConv layers on N GPUs (BASELINE configs[4], 8 x B200): node-parallel — rank r
+    owns the nnz-balanced row block of Â and the matching rows of X, H1, the logits and the labels;
+    W1 / W2 are replicated, their gradients all-reduced.  Both aggregations and all four sparse
+    gradients go through ONE ``dist.ShardedSpmm`` (needed-rows exchange over peer memory), built
+    with ``shard_like_rows`` so the output block of layer 1 *is* the input shard of layer 2, and two
+    buffer slots so the rows each layer pulled in the forward are still there for its SDDMM:
+
+        forward   Z1 = X_r W1            H1_r = relu(Â_r · Z1)     [ReLU fused into the SpMM store]
+                  G_r = Â_r · H1         logits_r = G_r W2
+        backward  dG = dlogits W2ᵀ       dH1_r = (Âᵀ dG)_r          dval += sddmm(dG, H1)
+                  dZ = dH1 ⊙ [H1 > 0]    dZ1_r = (Âᵀ dZ)_r          dval += sddmm(dZ, Z1)
+                  dW2 = Σ_r G_rᵀ dlogits_r        dW1 = Σ_r X_rᵀ dZ1_r          (all-reduce)
+
+    The backward is written out by hand (no autograd graph across the exchange)."""
+
+    def __init__(self, A: CsrMatrix, rank: int, world: int, device, in_dim: int = 602, hidden: int = 256,
+                 out_dim: int = 41, seed: int = 5, edge_weight_grad: bool = True, group=None, compute=None,
+                 tasks_per_warp: int = 4, buckets: int = 1):
+        import importlib
+        dmod = importlib.import_module(__package__ + ".dist")
+        self.rank, self.world, self.group, self.device = rank, world, group, device
+        self.sh = dmod.ShardedSpmm(A, hidden, torch.float32, rank, world, device, shard_like_rows=True, slots=2,
+                                   group=group, compute=compute, tasks_per_warp=tasks_per_warp, buckets=buckets)
+        self.nodes = A.rows
+        self.m = self.sh.r1 - self.sh.r0
+        self.W1 = glorot(in_dim, hidden, seed, device)
+        self.W2 = glorot(hidden, out_dim, seed + 1, device)
+        self.edge_weight_grad = edge_weight_grad
+        self.grads = {}
+        self._h1 = torch.empty((self.m, hidden), dtype=torch.float32, device=device)
+        self._g = torch.empty((self.m, hidden), dtype=torch.float32, device=device)
+
+    def local_rows(self, T: torch.Tensor) -> torch.Tensor:
+        return T[self.sh.r0:self.sh.r1].contiguous()
+
+    def _all_reduce(self, t: torch.Tensor) -> torch.Tensor:
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(t, group=self.group)
+        return t
+
+    def train_step(self, X_r: torch.Tensor, labels_r: torch.Tensor, lr: float = 0.0) -> torch.Tensor:
+        """One forward + backward on this rank's nodes; returns the global mean cross-entropy."""
+        sh, m = self.sh, self.m
+        z1 = X_r @ self.W1
+        h1 = sh.forward(z1, out=self._h1, relu=True, slot=0)[:m]
+        g = sh.forward(h1, out=self._g, slot=1)[:m]
+        logits = g @ self.W2
+        logp = torch.log_softmax(logits, dim=1)
+        loss_sum = -logp.gather(1, labels_r[:, None]).sum()
+        dlogits = (torch.exp(logp) - torch.nn.functional.one_hot(labels_r, logits.shape[1]).to(logp.dtype)) / self.nodes
+        dW2 = g.t() @ dlogits
+        dG = dlogits @ self.W2.t()
+        dval = None
+        if self.edge_weight_grad:
+            dval = sh.sddmm(dG, slot=1)                       # against H1 rows pulled by the 2nd forward
+        dH1 = sh.backward(dG, slot=1)[:m]
+        dZ = dH1 * (h1 > 0)
+        if self.edge_weight_grad:
+            dval = dval + sh.sddmm(dZ, slot=0)                # against Z1 rows pulled by the 1st forward
+        dZ1 = sh.backward(dZ, slot=0)[:m]
+        dW1 = X_r.t() @ dZ1
+        packed = torch.cat([dW1.flatten(), dW2.flatten(), loss_sum.reshape(1)])
+        self._all_reduce(packed)
+        n1 = dW1.numel()
+        self.grads = {"W1": packed[:n1].view_as(dW1), "W2": packed[n1:n1 + dW2.numel()].view_as(dW2), "val": dval}
+        if lr > 0:
+            self.W1 -= lr * self.grads["W1"]
+            self.W2 -= lr * self.grads["W2"]
+        return packed[-1] / self.nodes
+
+    def spmm_flops_per_step(self) -> int:
+        per = 2 * self.sh.A_blk.nnz * self.W1.shape[1]        # this rank's block
+        return 2 * (2 + (1 if self.edge_weight_grad else 0)) * per

@@ -161,3 +161,72 @@ def test_sharded_spmm_gloo(world, n, scheme, buckets):
         assert r[5]["nsub"] == 1 + min(buckets, world - 1)
         assert 0 < st["pulled"] <= st["all_gather"]           # never more than an all-gather moves
         assert 0.0 < st["local_nnz_fraction"] < 1.0
+
+
+# ------------------------------------------------------------------ sharded 2-layer GCN (configs[4] host logic)
+
+def _gcn_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import importlib
+        import ofspmm_b200 as ofs
+        gcn = importlib.import_module("of-spmm_b200.gcn")
+        A = ofs.graphs.gcn_normalize(ofs.graphs.add_self_loops(ofs.graphs.uniform_csr(300, 300, 0.03, seed=9)))
+        X = ofs.graphs.dense_operand(300, 24, 3)
+        labels = torch.randint(0, 7, (300,), generator=torch.Generator().manual_seed(1))
+        model = gcn.ShardedGCN2(A, rank, world, "cpu", in_dim=24, hidden=16, out_dim=7, seed=5, compute=OracleCompute())
+        Xr, yr = model.local_rows(X), model.local_rows(labels)
+        loss = model.train_step(Xr, yr)
+        loss2 = model.train_step(Xr, yr)                  # second step: slots / hand-shakes are reusable
+        q.put((rank, model.sh.r0, model.sh.r1, float(loss), float(loss2), model.grads["W1"].clone().numpy(),
+               model.grads["W2"].clone().numpy(), model.grads["val"].clone().numpy()))
+        dist.barrier()
+        dist.destroy_process_group()
+    except Exception:
+        import traceback
+        q.put(("error", rank, traceback.format_exc()))
+        os._exit(1)
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_gcn_gloo_matches_dense_fp64(world):
+    sys.path.insert(0, ROOT)
+    import ofspmm_b200 as ofs
+    import importlib
+    gcn = importlib.import_module("of-spmm_b200.gcn")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gcn_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = []
+    for _ in range(world):
+        r = q.get(timeout=180)
+        if r[0] == "error":
+            for p in procs:
+                p.kill()
+            raise AssertionError(f"rank {r[1]} failed:\n{r[2]}")
+        results.append(r)
+    for p in procs:
+        p.join(timeout=60)
+    results.sort(key=lambda t: t[0])
+    A = ofs.graphs.gcn_normalize(ofs.graphs.add_self_loops(ofs.graphs.uniform_csr(300, 300, 0.03, seed=9)))
+    X = ofs.graphs.dense_operand(300, 24, 3).double()
+    labels = torch.randint(0, 7, (300,), generator=torch.Generator().manual_seed(1))
+    rows = torch.repeat_interleave(torch.arange(A.rows), A.row_lengths())
+    val = A.val.double().requires_grad_(True)
+    dense = torch.zeros(A.rows, A.cols, dtype=torch.float64).index_put((rows, A.col.long()), val)
+    W1 = gcn.glorot(24, 16, 5, "cpu").double().requires_grad_(True)
+    W2 = gcn.glorot(16, 7, 6, "cpu").double().requires_grad_(True)
+    ref = torch.nn.functional.cross_entropy((dense @ torch.relu(dense @ (X @ W1))) @ W2, labels)
+    ref.backward()
+    for r in results:
+        assert abs(r[3] - float(ref)) < 1e-5 and r[4] == pytest.approx(r[3], abs=1e-6)
+        assert np.allclose(r[5], W1.grad.numpy(), rtol=1e-4, atol=1e-6)
+        assert np.allclose(r[6], W2.grad.numpy(), rtol=1e-4, atol=1e-6)
+    dval = np.concatenate([r[7] for r in results])
+    assert np.allclose(dval, val.grad.numpy(), rtol=1e-4, atol=1e-6)

@@ -142,3 +142,85 @@ def test_sharded_spmm_nccl_vs_oracle(world):
             assert rec["C"] and rec["dB"] and rec["dval"] and rec["det"] and rec["ep"], f"rank {rank}: {rec}"
             if rec["case"][3] == "pull":
                 assert rec["comm"] == "pull/symm", rec     # the peer-memory transport really ran
+
+
+# ------------------------------------------------------------------ sharded 2-layer GCN (configs[4]) on real kernels
+
+def _gcn_worker(rank, world, port, q):
+    import threading
+    threading.Timer(200.0, lambda: os._exit(3)).start()
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    try:
+        import importlib
+        import torch.distributed as dist
+        torch.cuda.set_device(rank)
+        dev = torch.device("cuda", rank)
+        if world > 1:
+            dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+        import ofspmm_b200 as ofs
+        gcn = importlib.import_module("of-spmm_b200.gcn")
+        A = ofs.graphs.gcn_normalize(ofs.graphs.add_self_loops(ofs.graphs.reddit_like(256, seed=2)))
+        X = ofs.graphs.dense_operand(A.rows, 40, 3)
+        labels = torch.randint(0, 7, (A.rows,), generator=torch.Generator().manual_seed(1))
+        model = gcn.ShardedGCN2(A.to(dev), rank, world, dev, in_dim=40, hidden=64, out_dim=7, seed=5)
+        Xr, yr = model.local_rows(X.to(dev)), model.local_rows(labels.to(dev))
+        loss = model.train_step(Xr, yr)
+        loss2 = model.train_step(Xr, yr)
+        torch.cuda.synchronize()
+        q.put((rank, float(loss), float(loss2), model.grads["W1"].cpu().numpy(), model.grads["W2"].cpu().numpy(),
+               model.grads["val"].cpu().numpy(), model.sh.comm))
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+    except Exception:
+        import traceback
+        q.put(("error", rank, traceback.format_exc()))
+        os._exit(1)
+    os._exit(0)
+
+
+@pytest.mark.parametrize("world", [1, 2, 4])
+def test_sharded_gcn_vs_dense_fp64(world):
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs, {torch.cuda.device_count()} visible")
+    import importlib
+    import torch.multiprocessing as mp
+    sys.path.insert(0, ROOT)
+    import ofspmm_b200 as ofs
+    gcn = importlib.import_module("of-spmm_b200.gcn")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gcn_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = []
+    for _ in range(world):
+        r = q.get(timeout=240)
+        if r[0] == "error":
+            for p in procs:
+                p.kill()
+            raise AssertionError(f"rank {r[1]} failed:\n{r[2]}")
+        results.append(r)
+    for p in procs:
+        p.join(timeout=60)
+    results.sort(key=lambda t: t[0])
+    A = ofs.graphs.gcn_normalize(ofs.graphs.add_self_loops(ofs.graphs.reddit_like(256, seed=2)))
+    X = ofs.graphs.dense_operand(A.rows, 40, 3).double()
+    labels = torch.randint(0, 7, (A.rows,), generator=torch.Generator().manual_seed(1))
+    rows = torch.repeat_interleave(torch.arange(A.rows), A.row_lengths())
+    val = A.val.double().requires_grad_(True)
+    dense = torch.zeros(A.rows, A.cols, dtype=torch.float64).index_put((rows, A.col.long()), val)
+    W1 = gcn.glorot(40, 64, 5, "cpu").double().requires_grad_(True)
+    W2 = gcn.glorot(64, 7, 6, "cpu").double().requires_grad_(True)
+    ref = torch.nn.functional.cross_entropy((dense @ torch.relu(dense @ (X @ W1))) @ W2, labels)
+    ref.backward()
+    for r in results:
+        assert abs(r[1] - float(ref.detach())) < 1e-5 and abs(r[2] - r[1]) < 1e-6
+        assert np.allclose(r[3], W1.grad.numpy(), rtol=1e-4, atol=1e-6)
+        assert np.allclose(r[4], W2.grad.numpy(), rtol=1e-4, atol=1e-6)
+        assert r[6] == ("pull/symm" if world > 1 else "single")
+    dval = np.concatenate([r[5] for r in results])
+    assert np.allclose(dval, val.grad.numpy(), rtol=1e-4, atol=1e-6)

@@ -65,7 +65,7 @@ def main():
         cases = {
             "unplanned": lambda: ops.spmm_csr_compute(A.crow, A.col, A.val, B, A.rows, A.cols, out=C, variant=plan.variant, order=order),
             "planned": lambda: ops.spmm_csr_compute(A.crow, A.col, A.val, B, A.rows, A.cols, out=C, plan=plan, order=order),
-            "tiny kernel + planned": lambda: (tiny.add_(1.0), ops.spmm_csr_compute(A.crow, A.col, A.val, B, A.rows, A.cols, out=C, plan=plan, order=order)),
+            "partition kernel + planned": lambda: (ofs.merge_path_partition(A.crow, A.nnz, (A.rows + A.nnz + 255) // 256), ops.spmm_csr_compute(A.crow, A.col, A.val, B, A.rows, A.cols, out=C, plan=plan, order=order)),
             "row_hist(crow) + planned": lambda: (ops.row_hist(A.crow), ops.spmm_csr_compute(A.crow, A.col, A.val, B, A.rows, A.cols, out=C, plan=plan, order=order)),
         }
         for name, fn in cases.items():
