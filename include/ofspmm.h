@@ -94,7 +94,12 @@ enum {
   OFSPMM_FWD_RELU = 4,       /* fused epilogue: max(., 0), after the bias (GCNConv; precedent for a
                                 fused epilogue: oneflow/user/kernels/cublas_fused_mlp_kernel.cu)        */
   OFSPMM_ORDER_DYNAMIC = 8,  /* persistent grid draws its tasks from a counter, in launch order         */
-  OFSPMM_ORDER_STATIC = 16   /* persistent grid uses the fixed interleave (warp w: tasks w, w+W, ...)   */
+  OFSPMM_ORDER_STATIC = 16,  /* persistent grid uses the fixed interleave (warp w: tasks w, w+W, ...)   */
+  /* bf16 products computed in several passes (column buckets): the running row sums stay in the
+   * fp32 buffer opts->acc32 (rows x n, packed) between the passes, so the result is rounded to
+   * bf16 once.  first pass: ACC32_OUT; middle: IN | OUT; last: IN (+ epilogue) -> C.             */
+  OFSPMM_FWD_ACC32_IN = 32,
+  OFSPMM_FWD_ACC32_OUT = 64
 };
 /* Task order when neither ORDER bit is set (measured default). */
 #ifndef OFSPMM_DEFAULT_DYNAMIC_ORDER
@@ -122,6 +127,7 @@ typedef struct ofspmm_opts {
                              partition is recomputed inside the call                                */
   size_t plan_bytes;
   const void* bias;       /* OFSPMM_FWD_BIAS: n elements of the dense dtype                          */
+  void* acc32;            /* OFSPMM_FWD_ACC32_*: rows x n fp32, 16-byte aligned                      */
 } ofspmm_opts;
 
 /* ---- SpMM forward: C[rows × n] = A · B[cols × n]  (replaces the `spmm_csr` kernel body; data
@@ -270,6 +276,16 @@ OFSPMM_API int ofspmm_scatter_add_rows(void* dst, int64_t ld_dst, const void* sr
                                        const void* list, int idx_dtype, int64_t idx_offset,
                                        int64_t count, int64_t n, int dense_dtype, int max_ctas,
                                        ofspmm_stream_t stream);
+
+/* fp32-accumulator forms for 16-bit operands: the owner of a dB shard adds the peers' bf16 partial
+ * rows into an fp32 buffer and rounds once at the end (ofspmm_cast_from_f32), instead of rounding
+ * to bf16 after every rank's contribution. */
+OFSPMM_API int ofspmm_scatter_add_rows_f32(float* dst, int64_t ld_dst, const void* src, int64_t ld_src,
+                                           const void* list, int idx_dtype, int64_t idx_offset,
+                                           int64_t count, int64_t n, int src_dtype, int max_ctas,
+                                           ofspmm_stream_t stream);
+OFSPMM_API int ofspmm_cast_from_f32(const float* src, void* dst, int64_t count, int dst_dtype,
+                                    ofspmm_stream_t stream);
 
 /* ---- Host-buffer convenience entry (what a CPU-tensor caller / the e2e benchmark uses): copies
  * the CSR arrays and B from HOST memory (pinned recommended) to device staging carved from

@@ -24,11 +24,12 @@ EXPORTS = (
     "ofspmm_launch_count", "ofspmm_fwd_variant", "ofspmm_variant_name",
     "ofspmm_fwd_ex_workspace_bytes", "ofspmm_fwd_ex", "ofspmm_plan_bytes", "ofspmm_plan_build",
     "ofspmm_choose_variant", "ofspmm_bwd_b_cached_workspace_bytes", "ofspmm_bwd_b_cached", "ofspmm_sddmm_ex",
-    "ofspmm_gather_rows", "ofspmm_scatter_add_rows", "ofspmm_permute_values",
+    "ofspmm_gather_rows", "ofspmm_scatter_add_rows", "ofspmm_permute_values", "ofspmm_scatter_add_rows_f32",
+    "ofspmm_cast_from_f32",
 )
 
 # ofspmm_opts.flags / variant codes (include/ofspmm.h)
-FWD_ACCUMULATE, FWD_BIAS, FWD_RELU, ORDER_DYNAMIC, ORDER_STATIC = 1, 2, 4, 8, 16
+FWD_ACCUMULATE, FWD_BIAS, FWD_RELU, ORDER_DYNAMIC, ORDER_STATIC, FWD_ACC32_IN, FWD_ACC32_OUT = 1, 2, 4, 8, 16, 32, 64
 VARIANT_AUTO, VARIANT_ITEMS64, VARIANT_ROWPAR, VARIANT_EXPLICIT = 0, 1, 2, 0x100
 
 
@@ -54,7 +55,7 @@ class OptsStruct(ctypes.Structure):
     """struct ofspmm_opts (include/ofspmm.h)."""
     _fields_ = [("flags", ctypes.c_uint32), ("tasks_per_warp", ctypes.c_int32), ("variant", ctypes.c_int32),
                 ("reserved", ctypes.c_int32), ("plan", ctypes.c_void_p), ("plan_bytes", ctypes.c_size_t),
-                ("bias", ctypes.c_void_p)]
+                ("bias", ctypes.c_void_p), ("acc32", ctypes.c_void_p)]
 
 
 _LIB = None
@@ -131,6 +132,10 @@ def lib() -> ctypes.CDLL:
     L.ofspmm_bwd_b_cached.restype = i32
     L.ofspmm_sddmm_ex.argtypes = [csr_p, vp, vp, vp, i64, i32, opts_p, vp, sz, vp]
     L.ofspmm_sddmm_ex.restype = i32
+    L.ofspmm_scatter_add_rows_f32.argtypes = [vp, i64, vp, i64, vp, i32, i64, i64, i64, i32, i32, vp]
+    L.ofspmm_scatter_add_rows_f32.restype = i32
+    L.ofspmm_cast_from_f32.argtypes = [vp, vp, i64, i32, vp]
+    L.ofspmm_cast_from_f32.restype = i32
     L.ofspmm_permute_values.argtypes = [vp, i32, vp, i32, i64, vp, vp]
     L.ofspmm_permute_values.restype = i32
     L.ofspmm_gather_rows.argtypes = [vp, i64, vp, i64, vp, i32, i64, i64, i64, i32, i32, vp]

@@ -93,8 +93,9 @@ FwdLaunch make_launch(const ofspmm_opts* opts, int64_t rows, int64_t nnz, int64_
   const uint32_t fl = opts ? opts->flags : 0u;
   // task order: dynamic (drawn from a counter) unless the caller pins the static interleave
   L.dynamic = OFSPMM_DEFAULT_DYNAMIC_ORDER ? (fl & OFSPMM_ORDER_STATIC) == 0 : (fl & OFSPMM_ORDER_DYNAMIC) != 0;
-  L.flags = fl & (OFSPMM_FWD_ACCUMULATE | OFSPMM_FWD_BIAS | OFSPMM_FWD_RELU);
+  L.flags = fl & (OFSPMM_FWD_ACCUMULATE | OFSPMM_FWD_BIAS | OFSPMM_FWD_RELU | OFSPMM_FWD_ACC32_IN | OFSPMM_FWD_ACC32_OUT);
   L.bias = opts ? opts->bias : nullptr;
+  L.acc32 = opts ? static_cast<float*>(opts->acc32) : nullptr;
   return L;
 }
 
@@ -105,8 +106,14 @@ int run_fwd(const ofspmm_csr* A, const void* B, int64_t ldb, void* C, int64_t ld
   if (ldb < n || ldc < n || ldb >= (int64_t{1} << 30)) return OFSPMM_ERR_INVALID_ARG;
   FwdLaunch L = make_launch(opts, A->rows, A->nnz, n, dense_dtype);
   if ((L.flags & OFSPMM_FWD_BIAS) && L.bias == nullptr) return OFSPMM_ERR_INVALID_ARG;
+  if (L.flags & (OFSPMM_FWD_ACC32_IN | OFSPMM_FWD_ACC32_OUT)) {
+    // fp32 row accumulator between the passes of a 16-bit product (fp32 products accumulate in C)
+    if (dense_dtype == OFSPMM_DTYPE_FLOAT || L.acc32 == nullptr || (reinterpret_cast<uintptr_t>(L.acc32) & 15) ||
+        (L.flags & OFSPMM_FWD_ACCUMULATE))
+      return OFSPMM_ERR_INVALID_ARG;
+  }
   if (A->nnz == 0 || A->cols == 0) {
-    if (L.flags == OFSPMM_FWD_ACCUMULATE) return OFSPMM_OK;  // C += 0
+    if (L.flags == OFSPMM_FWD_ACCUMULATE || L.flags == (OFSPMM_FWD_ACC32_IN | OFSPMM_FWD_ACC32_OUT)) return OFSPMM_OK;  // += 0
     if (L.flags == 0) {
       OFSPMM_CUDA_OK(cudaMemset2DAsync(C, static_cast<size_t>(ldc) * dense_size(dense_dtype), 0,
                                        static_cast<size_t>(n) * dense_size(dense_dtype),
@@ -356,6 +363,21 @@ int ofspmm_gather_rows(void* dst, int64_t ld_dst, const void* src, int64_t ld_sr
   if (list != nullptr && !idx_ok(idx_dtype)) return OFSPMM_ERR_UNSUPPORTED_DTYPE;
   return launch_gather_rows(dst, ld_dst, src, ld_src, list, list ? idx_dtype : OFSPMM_DTYPE_INT32, idx_offset, count, n,
                             dense_dtype, max_ctas, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int ofspmm_scatter_add_rows_f32(float* dst, int64_t ld_dst, const void* src, int64_t ld_src, const void* list,
+                                int idx_dtype, int64_t idx_offset, int64_t count, int64_t n, int src_dtype,
+                                int max_ctas, ofspmm_stream_t stream) {
+  if (count < 0 || n < 0 || ld_dst < n || ld_src < n) return OFSPMM_ERR_INVALID_ARG;
+  if (count > 0 && n > 0 && (dst == nullptr || src == nullptr)) return OFSPMM_ERR_INVALID_ARG;
+  if (list != nullptr && !idx_ok(idx_dtype)) return OFSPMM_ERR_UNSUPPORTED_DTYPE;
+  return launch_scatter_add_rows_f32(dst, ld_dst, src, ld_src, list, list ? idx_dtype : OFSPMM_DTYPE_INT32, idx_offset,
+                                     count, n, src_dtype, max_ctas, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int ofspmm_cast_from_f32(const float* src, void* dst, int64_t count, int dst_dtype, ofspmm_stream_t stream) {
+  if (count < 0 || (count > 0 && (src == nullptr || dst == nullptr))) return OFSPMM_ERR_INVALID_ARG;
+  return launch_cast_from_f32(src, dst, count, dst_dtype, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int ofspmm_scatter_add_rows(void* dst, int64_t ld_dst, const void* src, int64_t ld_src, const void* list,

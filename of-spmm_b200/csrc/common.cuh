@@ -172,33 +172,36 @@ template <> struct RowVec<__nv_bfloat16, 1> {
   }
 };
 
-// fp32 scratch rows (carry / head partials) are always stored as plain fp32, VEC at a time.
+// fp32 scratch rows (carry / head partials, fp32 accumulators of multi-pass products) are stored
+// as plain fp32, VEC at a time, with the streaming hint: they are written once and read once by a
+// later kernel, and must not evict the dense operand from L2 on the way (cfg2: 230 MB of carries
+// per launch next to a 119 MB B).
 template <int VEC>
 __device__ __forceinline__ void store_f32(float* p, const float (&v)[VEC]) {
   if constexpr (VEC == 4) {
-    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    __stcs(reinterpret_cast<float4*>(p), make_float4(v[0], v[1], v[2], v[3]));
   } else if constexpr (VEC == 8) {
-    reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
-    reinterpret_cast<float4*>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
+    __stcs(reinterpret_cast<float4*>(p), make_float4(v[0], v[1], v[2], v[3]));
+    __stcs(reinterpret_cast<float4*>(p) + 1, make_float4(v[4], v[5], v[6], v[7]));
   } else {
 #pragma unroll
-    for (int i = 0; i < VEC; ++i) p[i] = v[i];
+    for (int i = 0; i < VEC; ++i) __stcs(p + i, v[i]);
   }
 }
 
 template <int VEC>
 __device__ __forceinline__ void load_f32(const float* p, float (&v)[VEC]) {
   if constexpr (VEC == 4) {
-    const float4 a = *reinterpret_cast<const float4*>(p);
+    const float4 a = __ldcs(reinterpret_cast<const float4*>(p));
     v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
   } else if constexpr (VEC == 8) {
-    const float4 a = reinterpret_cast<const float4*>(p)[0];
-    const float4 b = reinterpret_cast<const float4*>(p)[1];
+    const float4 a = __ldcs(reinterpret_cast<const float4*>(p));
+    const float4 b = __ldcs(reinterpret_cast<const float4*>(p) + 1);
     v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
     v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
   } else {
 #pragma unroll
-    for (int i = 0; i < VEC; ++i) v[i] = p[i];
+    for (int i = 0; i < VEC; ++i) v[i] = __ldcs(p + i);
   }
 }
 

@@ -146,6 +146,51 @@ __global__ void scatter_add_rows_scalar_kernel(DT* __restrict__ dst, long long l
   }
 }
 
+// fp32 accumulator variant: dst is fp32, src rows are bf16 (the peers' partials, each rounded
+// once); 16 bytes of src = 8 values = 32 bytes of dst.  Keeps a sum over many ranks from being
+// rounded to bf16 after every addend.
+template <typename IdxT>
+__global__ void __launch_bounds__(kThreads) scatter_add_rows_bf16_to_f32_kernel(
+    float* __restrict__ dst, long long ld_dst, const char* __restrict__ src, long long src_stride,
+    const IdxT* __restrict__ list, long long off, long long count, int units) {
+  const long long total = count * units;
+  const long long stride = static_cast<long long>(gridDim.x) * kThreads;
+  for (long long u = static_cast<long long>(blockIdx.x) * kThreads + threadIdx.x; u < total; u += stride) {
+    const long long r = u / units;
+    const int c = static_cast<int>(u - r * units);
+    const uint4 v = ld_peer16(src + r * src_stride + c * 16);
+    float4* dp = reinterpret_cast<float4*>(dst + list_at(list, r, off) * ld_dst + c * 8);
+    float4 a = dp[0], b = dp[1];
+    a.x += __uint_as_float(v.x << 16); a.y += __uint_as_float(v.x & 0xffff0000u);
+    a.z += __uint_as_float(v.y << 16); a.w += __uint_as_float(v.y & 0xffff0000u);
+    b.x += __uint_as_float(v.z << 16); b.y += __uint_as_float(v.z & 0xffff0000u);
+    b.z += __uint_as_float(v.w << 16); b.w += __uint_as_float(v.w & 0xffff0000u);
+    dp[0] = a;
+    dp[1] = b;
+  }
+}
+
+template <typename IdxT>
+__global__ void scatter_add_rows_bf16_to_f32_scalar_kernel(float* __restrict__ dst, long long ld_dst,
+                                                           const __nv_bfloat16* __restrict__ src, long long ld_src,
+                                                           const IdxT* __restrict__ list, long long off,
+                                                           long long count, int n) {
+  const long long total = count * n;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long u = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; u < total; u += stride) {
+    const long long r = u / n;
+    const int c = static_cast<int>(u - r * n);
+    dst[list_at(list, r, off) * ld_dst + c] += to_float(*static_cast<const volatile __nv_bfloat16*>(src + r * ld_src + c));
+  }
+}
+
+template <typename DT>
+__global__ void cast_rows_from_f32_kernel(const float* __restrict__ in, DT* __restrict__ out, long long count) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < count; i += stride)
+    out[i] = from_float<DT>(in[i]);
+}
+
 template <typename IdxT, typename ValT>
 __global__ void gather_vals_kernel(const ValT* __restrict__ val, const IdxT* __restrict__ perm, long long nnz,
                                    ValT* __restrict__ out) {
@@ -219,6 +264,50 @@ int launch_scatter_add_rows(void* dst, int64_t ld_dst, const void* src, int64_t 
                             int idx_dtype, int64_t idx_offset, int64_t count, int64_t n, int dense_dtype,
                             int max_ctas, cudaStream_t stream) {
   return rows_dispatch(true, dst, ld_dst, src, ld_src, list, idx_dtype, idx_offset, count, n, dense_dtype, max_ctas, stream);
+}
+
+int launch_scatter_add_rows_f32(float* dst, int64_t ld_dst, const void* src, int64_t ld_src, const void* list,
+                                int idx_dtype, int64_t idx_offset, int64_t count, int64_t n, int src_dtype,
+                                int max_ctas, cudaStream_t stream) {
+  if (count == 0 || n == 0) return OFSPMM_OK;
+  if (src_dtype == OFSPMM_DTYPE_FLOAT)   // fp32 partials: the plain kernel already accumulates in fp32
+    return launch_scatter_add_rows(dst, ld_dst, src, ld_src, list, idx_dtype, idx_offset, count, n, src_dtype, max_ctas, stream);
+  if (src_dtype != OFSPMM_DTYPE_BFLOAT16) return OFSPMM_ERR_UNSUPPORTED_DTYPE;
+  DevInfo dev;
+  if (int rc = get_dev_info(&dev)) return rc;
+  const bool vec = n % 8 == 0 && ld_dst % 8 == 0 && ld_src % 8 == 0 &&
+                   ((reinterpret_cast<uintptr_t>(dst) & 31) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
+  const bool i32 = idx_dtype == OFSPMM_DTYPE_INT32;
+  if (vec) {
+    const int units = static_cast<int>(n / 8);
+    const int grid = grid_for(count * units, kThreads, max_ctas, dev.sms);
+    if (i32) scatter_add_rows_bf16_to_f32_kernel<int32_t><<<grid, kThreads, 0, stream>>>(dst, ld_dst, static_cast<const char*>(src), ld_src * 2, static_cast<const int32_t*>(list), idx_offset, count, units);
+    else scatter_add_rows_bf16_to_f32_kernel<int64_t><<<grid, kThreads, 0, stream>>>(dst, ld_dst, static_cast<const char*>(src), ld_src * 2, static_cast<const int64_t*>(list), idx_offset, count, units);
+  } else {
+    const int grid = grid_for(count * n, 256, max_ctas, dev.sms);
+    if (i32) scatter_add_rows_bf16_to_f32_scalar_kernel<int32_t><<<grid, 256, 0, stream>>>(dst, ld_dst, static_cast<const __nv_bfloat16*>(src), ld_src, static_cast<const int32_t*>(list), idx_offset, count, static_cast<int>(n));
+    else scatter_add_rows_bf16_to_f32_scalar_kernel<int64_t><<<grid, 256, 0, stream>>>(dst, ld_dst, static_cast<const __nv_bfloat16*>(src), ld_src, static_cast<const int64_t*>(list), idx_offset, count, static_cast<int>(n));
+  }
+  count_launch();
+  OFSPMM_CUDA_OK(cudaGetLastError());
+  return OFSPMM_OK;
+}
+
+int launch_cast_from_f32(const float* src, void* dst, int64_t count, int dst_dtype, cudaStream_t stream) {
+  if (count == 0) return OFSPMM_OK;
+  DevInfo dev;
+  if (int rc = get_dev_info(&dev)) return rc;
+  const int grid = grid_for(count, 256, dev.sms * 8, dev.sms);
+  if (dst_dtype == OFSPMM_DTYPE_BFLOAT16) {
+    cast_rows_from_f32_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(src, static_cast<__nv_bfloat16*>(dst), count);
+  } else if (dst_dtype == OFSPMM_DTYPE_FLOAT) {
+    cast_rows_from_f32_kernel<float><<<grid, 256, 0, stream>>>(src, static_cast<float*>(dst), count);
+  } else {
+    return OFSPMM_ERR_UNSUPPORTED_DTYPE;
+  }
+  count_launch();
+  OFSPMM_CUDA_OK(cudaGetLastError());
+  return OFSPMM_OK;
 }
 
 int launch_gather_vals(const void* val, int val_dtype, const void* perm, int idx_dtype, int64_t nnz,

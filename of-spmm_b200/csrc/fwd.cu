@@ -83,6 +83,7 @@ int launch_fwd(const ofspmm_csr* A, const void* B, int64_t ldb, void* C, int64_t
   p.panels = 1;
   p.bias = L.bias;
   p.flags = L.flags;
+  p.acc32 = L.acc32;
   p.counter = L.dynamic ? static_cast<unsigned int*>(counter) : nullptr;
   const int64_t v = vec_width(dense_dtype);
   const bool aligned = ((reinterpret_cast<uintptr_t>(B) | reinterpret_cast<uintptr_t>(C) |

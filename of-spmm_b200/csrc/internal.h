@@ -47,6 +47,7 @@ struct FwdLaunch {
   bool dynamic;        // tasks drawn from a global counter (persistent grid only)
   unsigned flags;      // kFwd* epilogue bits
   const void* bias;
+  float* acc32;        // fp32 accumulator of multi-pass 16-bit products
 };
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
@@ -96,6 +97,10 @@ int launch_gather_vals(const void* val, int val_dtype, const void* perm, int idx
 int launch_gather_rows(void* dst, int64_t ld_dst, const void* src, int64_t ld_src, const void* list,
                        int idx_dtype, int64_t idx_offset, int64_t count, int64_t n, int dense_dtype,
                        int max_ctas, cudaStream_t stream);
+int launch_scatter_add_rows_f32(float* dst, int64_t ld_dst, const void* src, int64_t ld_src, const void* list,
+                                int idx_dtype, int64_t idx_offset, int64_t count, int64_t n, int src_dtype,
+                                int max_ctas, cudaStream_t stream);
+int launch_cast_from_f32(const float* src, void* dst, int64_t count, int dst_dtype, cudaStream_t stream);
 int launch_scatter_add_rows(void* dst, int64_t ld_dst, const void* src, int64_t ld_src, const void* list,
                             int idx_dtype, int64_t idx_offset, int64_t count, int64_t n, int dense_dtype,
                             int max_ctas, cudaStream_t stream);

@@ -66,6 +66,7 @@ struct FwdParams {
   unsigned int* counter;  // dynamic task order: zeroed before the launch; nullptr = static
   unsigned flags;    // kFwd* epilogue bits
   int max_tasks;     // tasks a warp runs before its CTA may retire (0: until the list is empty)
+  float* acc32;      // rows x n fp32 accumulator of a multi-pass product with a 16-bit output (kFwdAcc32*)
 };
 
 // Epilogue bits (= OFSPMM_FWD_* of include/ofspmm.h).  A row's epilogue runs exactly once, where
@@ -74,6 +75,11 @@ struct FwdParams {
 constexpr unsigned kFwdAccumulate = 1u;  // C += A·B instead of C = A·B
 constexpr unsigned kFwdBias = 2u;        // + bias[j]
 constexpr unsigned kFwdRelu = 4u;        // max(., 0)
+// 16-bit outputs only: a product computed in several accumulate passes (column buckets of the
+// multi-GPU path) keeps its running row sums in fp32 between the passes, so the result is rounded
+// to bf16 exactly once, like a single-pass product.
+constexpr unsigned kFwdAcc32In = 32u;    // add the fp32 row of acc32 to this pass's sum
+constexpr unsigned kFwdAcc32Out = 64u;   // store the fp32 sum into acc32 instead of C (no epilogue)
 
 // acc (+ old C) (+ bias) (relu) for VEC consecutive columns starting at column `c0` of row `crow_ptr`.
 template <typename DT, int VEC>
@@ -491,6 +497,27 @@ spmm_merge_kernel(const FwdParams p) {
             if (chmask & (1u << ch)) store_f32<VEC>(dst + ch * LPR * VEC, acc[ch]);
         } else {
           DT* dst = static_cast<DT*>(p.C) + static_cast<size_t>(r) * p.ldc + col0;
+          if constexpr (!kF32Out) {
+            if (p.flags & (kFwdAcc32In | kFwdAcc32Out)) {
+              float* a32 = p.acc32 + static_cast<size_t>(r) * n + col0;
+              if (p.flags & kFwdAcc32In) {
+#pragma unroll
+                for (int ch = 0; ch < CH; ++ch)
+                  if (chmask & (1u << ch)) {
+                    float o[VEC];
+                    load_f32<VEC>(a32 + ch * LPR * VEC, o);
+#pragma unroll
+                    for (int i = 0; i < VEC; ++i) acc[ch][i] += o[i];
+                  }
+              }
+              if (p.flags & kFwdAcc32Out) {
+#pragma unroll
+                for (int ch = 0; ch < CH; ++ch)
+                  if (chmask & (1u << ch)) store_f32<VEC>(a32 + ch * LPR * VEC, acc[ch]);
+                continue;   // next row: nothing goes to C in this pass
+              }
+            }
+          }
           if (p.flags != 0) {
             // complete row: whole epilogue here.  Final segment of a stitched row (fp32 output
             // only — bf16 went to head[] above): fold the old C in now, the fix-up kernel adds
@@ -575,6 +602,21 @@ __global__ void __launch_bounds__(WARPS * 32) spmm_fixup_kernel(const FwdParams 
       }
 #pragma unroll
       for (int i = 0; i < VEC; ++i) sum[i] += h[i];
+      if constexpr (!kF32Out) {
+        if (p.flags & (kFwdAcc32In | kFwdAcc32Out)) {
+          float* a32 = p.acc32 + static_cast<size_t>(row) * n + c0;
+          if (p.flags & kFwdAcc32In) {
+            float o[VEC];
+            load_f32<VEC>(a32, o);
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) sum[i] += o[i];
+          }
+          if (p.flags & kFwdAcc32Out) {
+            store_f32<VEC>(a32, sum);
+            continue;
+          }
+        }
+      }
       if (p.flags != 0)
         row_epilogue<DT, VEC>(sum, crow_out + c0, p.bias, c0, p.flags, !kF32Out && (p.flags & kFwdAccumulate) != 0);
       RowVec<DT, VEC>::store_stream(crow_out + c0, sum);

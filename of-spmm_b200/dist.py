@@ -59,13 +59,15 @@ class CudaCompute:
     def plan(self, crow, col, rows, cols, n, dtype):
         return ops.SpmmPlan(crow, col, rows, cols, n, dtype, transpose=True)
 
-    def spmm(self, A: CsrMatrix, b, out, plan=None, accumulate=False, tasks_per_warp=0, bias=None, relu=False):
+    def spmm(self, A: CsrMatrix, b, out, plan=None, accumulate=False, tasks_per_warp=0, bias=None, relu=False,
+             acc32=None, acc32_in=False, acc32_out=False):
         return ops.spmm_csr_compute(A.crow, A.col, A.val, b, A.rows, A.cols, out=out, plan=plan, accumulate=accumulate,
-                                    tasks_per_warp=tasks_per_warp, bias=bias, relu=relu)
+                                    tasks_per_warp=tasks_per_warp, bias=bias, relu=relu, acc32=acc32, acc32_in=acc32_in,
+                                    acc32_out=acc32_out)
 
-    def spmm_t(self, A: CsrMatrix, dy, out, plan=None, tasks_per_warp=0):
+    def spmm_t(self, A: CsrMatrix, dy, out, plan=None, tasks_per_warp=0, acc32_out=None):
         return ops.spmm_csr_grad_b_compute(A.crow, A.col, A.val, dy, A.rows, A.cols, out=out, plan=plan,
-                                           tasks_per_warp=tasks_per_warp)
+                                           tasks_per_warp=tasks_per_warp, acc32_out=acc32_out)
 
     def sddmm(self, A: CsrMatrix, dy, b, plan=None):
         return ops.sddmm_csr_compute(A.crow, A.col, dy, b, A.rows, A.cols, A.val.dtype, plan=plan)
@@ -74,7 +76,12 @@ class CudaCompute:
         return ops.gather_rows(dst, src, index, max_ctas=max_ctas)
 
     def scatter_add_rows(self, dst, src, index, max_ctas=0):
+        if dst.dtype == torch.float32 and src.dtype != torch.float32:
+            return ops.scatter_add_rows_f32(dst, src, index, max_ctas=max_ctas)
         return ops.scatter_add_rows(dst, src, index, max_ctas=max_ctas)
+
+    def cast_from_f32(self, dst, src):
+        return ops.cast_from_f32(dst, src)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -300,6 +307,11 @@ class ShardedSpmm:
             self.incoming = []
         self.B_pub = self.B_pubs[0]
         self._dbs = [torch.zeros((self.shard, n), dtype=dtype, device=device) for _ in range(slots)]
+        # 16-bit operands on several ranks: running sums of the accumulate passes (forward) and of the
+        # ranks' partials (backward) stay in fp32 and are rounded once — same error as a single pass
+        self._wide = world > 1 and dtype != torch.float32
+        self._acc32 = torch.zeros((m, n), dtype=torch.float32, device=device) if self._wide else None
+        self._db32 = torch.zeros((self.shard, n), dtype=torch.float32, device=device) if self._wide else None
         self._db = self._dbs[0]
         self._ev_pulled = [None] * slots
         self._ev_consumed = [None] * slots
@@ -348,12 +360,15 @@ class ShardedSpmm:
                 self.T.barrier(1)                     # every rank is done reading the published shards
                 self._ev_pulled[slot] = st.record(st.comm)
         ep = dict(bias=bias, relu=relu)
+        wide = self._wide and last > 0       # bf16: fp32 running sums between the passes
         s0 = self.sub[0]
-        cp.spmm(s0.A, B_pub[: s0.A.cols], C, plan=s0.plan, tasks_per_warp=self.tpw, **(ep if last == 0 else {}))
+        cp.spmm(s0.A, B_pub[: s0.A.cols], C, plan=s0.plan, tasks_per_warp=self.tpw, **(ep if last == 0 else {}),
+                **(dict(acc32=self._acc32, acc32_out=True) if wide else {}))
         for g, sc in enumerate(self.sub[1:], 1):
             st.wait(cur, ev_g[g - 1])
-            cp.spmm(sc.A, sc.Bc[slot], C, plan=sc.plan, accumulate=True, tasks_per_warp=self.tpw if g < last else 0,
-                    **(ep if g == last else {}))
+            acc = dict(acc32=self._acc32, acc32_in=True, acc32_out=g < last) if wide else dict(accumulate=True)
+            cp.spmm(sc.A, sc.Bc[slot], C, plan=sc.plan, tasks_per_warp=self.tpw if g < last else 0,
+                    **acc, **(ep if g == last else {}))
         return C
 
     # ------------------------------------------------------------------ backward wrt B
@@ -370,7 +385,11 @@ class ShardedSpmm:
             cp.spmm_t(sc.A, dY_blk, pub[: sc.A.cols], plan=sc.plan, tasks_per_warp=self.tpw)
         ev_rem = st.record()
         s0 = self.sub[0]
-        cp.spmm_t(s0.A, dY_blk, db[: s0.A.cols], plan=s0.plan)
+        acc = self._db32 if self._wide else db           # bf16: the ranks' partials are summed in fp32
+        if self._wide:
+            cp.spmm_t(s0.A, dY_blk, db[: s0.A.cols], plan=s0.plan, acc32_out=self._db32[: s0.A.cols])
+        else:
+            cp.spmm_t(s0.A, dY_blk, db[: s0.A.cols], plan=s0.plan)
         if self.world == 1:
             return db
         ev_loc = st.record()
@@ -382,7 +401,9 @@ class ShardedSpmm:
             st.wait(st.comm, ev_loc)
             for r, name, off, cnt, ids in self.incoming:   # ascending rank order: deterministic sum
                 if cnt:
-                    cp.scatter_add_rows(db, self.T.peer(f"{name}.{slot}", r)[off:off + cnt], ids, max_ctas=0)
+                    cp.scatter_add_rows(acc, self.T.peer(f"{name}.{slot}", r)[off:off + cnt], ids, max_ctas=0)
+            if self._wide:
+                cp.cast_from_f32(db, self._db32)      # one rounding of the complete sum
             self.T.barrier(3)                         # every rank is done reading the partials
             self._ev_consumed[slot] = st.record(st.comm)
         st.wait(cur, self._ev_consumed[slot])

@@ -14,6 +14,9 @@ struct SpmmCsrCaptureState : public AutoGradCaptureState {
   int64_t a_rows = 0;
   int64_t a_cols = 0;
   size_t crow_index = 0, col_index = 0, val_index = 0, b_index = 0;
+  DataType val_dtype = DataType::kInvalidDataType;   // the SDDMM gradient takes the dtype of a_val
+  bool has_at = false;                               // optional cached structure of A^T (inputs 4..6)
+  size_t t_crow_index = 0, t_col_index = 0, t_perm_index = 0;
 };
 
 class SpmmCsr : public OpExprGradFunction<SpmmCsrCaptureState> {
@@ -25,7 +28,7 @@ class SpmmCsr : public OpExprGradFunction<SpmmCsrCaptureState> {
     return Maybe<void>::Ok();
   }
 
-  // inputs: a_crow, a_col, a_val, b — index inputs never receive a gradient
+  // inputs: a_crow, a_col, a_val, b [, t_crow, t_col, t_perm] — index inputs never receive a gradient
   Maybe<void> Capture(SpmmCsrCaptureState* ctx, const TensorTuple& inputs, const TensorTuple& outputs,
                       const AttrMap& attrs) const override {
     ctx->val_requires_grad = inputs.at(2)->requires_grad();
@@ -36,8 +39,15 @@ class SpmmCsr : public OpExprGradFunction<SpmmCsrCaptureState> {
     ctx->a_cols = JUST(composed_attrs.GetAttr<int64_t>("a_cols"));
     ctx->crow_index = ctx->SaveTensorForBackward(inputs.at(0));
     ctx->col_index = ctx->SaveTensorForBackward(inputs.at(1));
+    ctx->val_dtype = inputs.at(2)->dtype();
     if (ctx->b_requires_grad) { ctx->val_index = ctx->SaveTensorForBackward(inputs.at(2)); }
     if (ctx->val_requires_grad) { ctx->b_index = ctx->SaveTensorForBackward(inputs.at(3)); }
+    ctx->has_at = inputs.size() == 7 && ctx->b_requires_grad;
+    if (ctx->has_at) {
+      ctx->t_crow_index = ctx->SaveTensorForBackward(inputs.at(4));
+      ctx->t_col_index = ctx->SaveTensorForBackward(inputs.at(5));
+      ctx->t_perm_index = ctx->SaveTensorForBackward(inputs.at(6));
+    }
     return Maybe<void>::Ok();
   }
 
@@ -45,16 +55,25 @@ class SpmmCsr : public OpExprGradFunction<SpmmCsrCaptureState> {
                     TensorTuple* in_grads) const override {
     if (!ctx->val_requires_grad && !ctx->b_requires_grad) { return Maybe<void>::Ok(); }
     CHECK_EQ_OR_RETURN(out_grads.size(), 1);  // NOLINT(maybe-need-error-msg)
-    in_grads->resize(4);
+    in_grads->resize(ctx->has_at ? 7 : 4);
     const auto& crow = ctx->SavedTensors().at(ctx->crow_index);
     const auto& col = ctx->SavedTensors().at(ctx->col_index);
     if (ctx->val_requires_grad) {  // dval[p] = <dy[i,:], b[col[p],:]>
       const auto& b = ctx->SavedTensors().at(ctx->b_index);
-      in_grads->at(2) = JUST(functional::SddmmCsr(crow, col, out_grads.at(0), b, ctx->a_rows, ctx->a_cols));
+      in_grads->at(2) = JUST(functional::SddmmCsr(crow, col, out_grads.at(0), b, ctx->a_rows, ctx->a_cols, ctx->val_dtype));
     }
     if (ctx->b_requires_grad) {    // db = A^T · dy
       const auto& val = ctx->SavedTensors().at(ctx->val_index);
-      in_grads->at(3) = JUST(functional::SpmmCsrGradB(crow, col, val, out_grads.at(0), ctx->a_rows, ctx->a_cols));
+      // with the cached structure of A^T: forward kernel on it, values re-gathered every call;
+      // without: A^T built transiently inside the op's tmp_buffer.  Both deterministic.
+      Optional<Tensor> t_crow, t_col, t_perm;
+      if (ctx->has_at) {
+        t_crow = ctx->SavedTensors().at(ctx->t_crow_index);
+        t_col = ctx->SavedTensors().at(ctx->t_col_index);
+        t_perm = ctx->SavedTensors().at(ctx->t_perm_index);
+      }
+      in_grads->at(3) = JUST(functional::SpmmCsrGradB(crow, col, val, out_grads.at(0), ctx->a_rows, ctx->a_cols, t_crow,
+                                                      t_col, t_perm, /*atomic=*/false));
     }
     return Maybe<void>::Ok();
   }

@@ -36,20 +36,37 @@ Maybe<void> NoGradForIndices(const user_op::GetInputArgModifier& GetInputArgModi
     CHECK_NOTNULL_OR_RETURN(m);  // NOLINT(maybe-need-error-msg)
     m->set_requires_grad(false);
   }
+  for (const char* name : {"t_crow", "t_col", "t_perm"}) {   // optional cached structure of A^T
+    user_op::InputArgModifier* m = GetInputArgModifierFn(name, 0);
+    if (m != nullptr) { m->set_requires_grad(false); }
+  }
   return Maybe<void>::Ok();
 }
 
-// A split of a_col / a_val is not a row split of A, so the CSR arrays are always broadcast; the
-// dense side may be column-split (always legal for a row-wise linear map).  nnz-balanced row
-// blocks live inside the library (of-spmm_b200/dist.py), outside SBP.
-Maybe<void> DenseColumnSplitSbp(user_op::SbpContext* ctx, const char* dense_in, const char* out) {
-  ctx->NewBuilder()
-      .Broadcast(user_op::OpArg("a_crow", 0))
-      .Broadcast(user_op::OpArg("a_col", 0))
-      .Broadcast(user_op::OpArg("a_val", 0))
-      .Split(user_op::OpArg(dense_in, 0), 1)
-      .Split(user_op::OpArg(out, 0), 1)
-      .Build();
+// A split of a_col / a_val is not a row split of A, so the CSR structure is always broadcast; the
+// dense side may be column-split (always legal for a row-wise linear map).  Both products are
+// bilinear in (a_val, dense operand), which gives the two partial-sum signatures — the analogue of
+// matmul's P(a)·B(b) -> P and B(a)·P(b) -> P (oneflow/user/ops/matmul_op.cpp:112-136).
+// nnz-balanced row blocks live inside the library (of-spmm_b200/dist.py), outside SBP.
+Maybe<void> BilinearSbp(user_op::SbpContext* ctx, const char* dense_in, const char* out) {
+  auto structure = [&](user_op::SbpSignatureBuilder& b) -> user_op::SbpSignatureBuilder& {
+    b.Broadcast(user_op::OpArg("a_crow", 0)).Broadcast(user_op::OpArg("a_col", 0));
+    for (const auto& in : ctx->inputs())   // optional cached structure of A^T: index tensors, broadcast
+      if (in.first == "t_crow" || in.first == "t_col" || in.first == "t_perm") b.Broadcast(user_op::OpArg(in.first, in.second));
+    return b;
+  };
+  {  // dense width split
+    auto b = ctx->NewBuilder();
+    structure(b).Broadcast(user_op::OpArg("a_val", 0)).Split(user_op::OpArg(dense_in, 0), 1).Split(user_op::OpArg(out, 0), 1).Build();
+  }
+  {  // partial sums of the edge values
+    auto b = ctx->NewBuilder();
+    structure(b).PartialSum(user_op::OpArg("a_val", 0)).Broadcast(user_op::OpArg(dense_in, 0)).PartialSum(user_op::OpArg(out, 0)).Build();
+  }
+  {  // partial sums of the dense operand
+    auto b = ctx->NewBuilder();
+    structure(b).Broadcast(user_op::OpArg("a_val", 0)).PartialSum(user_op::OpArg(dense_in, 0)).PartialSum(user_op::OpArg(out, 0)).Build();
+  }
   ctx->NewBuilder().Broadcast(ctx->inputs()).Broadcast(ctx->outputs()).Build();
   return Maybe<void>::Ok();
 }
@@ -79,7 +96,7 @@ Maybe<void> DenseColumnSplitSbp(user_op::SbpContext* ctx, const char* dense_in, 
   return Maybe<void>::Ok();
 }
 /*static*/ Maybe<void> SpmmCsrOp::GetSbp(user_op::SbpContext* ctx) {
-  return DenseColumnSplitSbp(ctx, "b", "out");
+  return BilinearSbp(ctx, "b", "out");
 }
 /*static*/ Maybe<void> SpmmCsrOp::ModifyInputArg(const GetInputArgModifier& fn,
                                                  const user_op::UserOpConfWrapper&) {
@@ -93,6 +110,13 @@ Maybe<void> DenseColumnSplitSbp(user_op::SbpContext* ctx, const char* dense_in, 
   const Shape& dy = ctx->InputShape("dy", 0);
   CHECK_EQ_OR_RETURN(dy.NumAxes(), 2) << "dy must be 2-D (a_rows x n)";
   CHECK_EQ_OR_RETURN(dy.At(0), ctx->Attr<int64_t>("a_rows")) << "dy rows must equal a_rows";
+  if (ctx->has_input("t_crow", 0)) {  // cached structure of A^T (csr_transpose_structure): all three or none
+    CHECK_OR_RETURN(ctx->has_input("t_col", 0) && ctx->has_input("t_perm", 0)) << "t_crow, t_col and t_perm come together";
+    CHECK_EQ_OR_RETURN(ctx->InputShape("t_crow", 0).elem_cnt(), ctx->Attr<int64_t>("a_cols") + 1)
+        << "t_crow must have a_cols+1 entries";
+    CHECK_EQ_OR_RETURN(ctx->InputShape("t_col", 0).elem_cnt(), nnz) << "t_col must have nnz entries";
+    CHECK_EQ_OR_RETURN(ctx->InputShape("t_perm", 0).elem_cnt(), nnz) << "t_perm must have nnz entries";
+  }
   ctx->SetOutputShape("db", 0, Shape({ctx->Attr<int64_t>("a_cols"), dy.At(1)}));
   return Maybe<void>::Ok();
 }
@@ -105,7 +129,7 @@ Maybe<void> DenseColumnSplitSbp(user_op::SbpContext* ctx, const char* dense_in, 
   return Maybe<void>::Ok();
 }
 /*static*/ Maybe<void> SpmmCsrGradBOp::GetSbp(user_op::SbpContext* ctx) {
-  return DenseColumnSplitSbp(ctx, "dy", "db");
+  return BilinearSbp(ctx, "dy", "db");
 }
 /*static*/ Maybe<void> SpmmCsrGradBOp::ModifyInputArg(const GetInputArgModifier& fn,
                                                       const user_op::UserOpConfWrapper&) {
@@ -132,7 +156,13 @@ Maybe<void> DenseColumnSplitSbp(user_op::SbpContext* ctx, const char* dense_in, 
 /*static*/ Maybe<void> SddmmCsrOp::InferDataType(user_op::InferContext* ctx) {
   JUST(CheckIndexTypes(ctx));
   CHECK_EQ_OR_RETURN(ctx->InputDType("dy", 0), ctx->InputDType("b", 0)) << "dy and b must share a dtype";
-  ctx->SetOutputDType("dval", 0, ctx->InputDType("b", 0));
+  // dval has the dtype of the values it is the gradient of (attr val_dtype, set by the grad
+  // function from a_val) — with fp32 values and a bf16 dense operand that is fp32, not b's dtype
+  const DataType val_dtype = ctx->Attr<DataType>("val_dtype");
+  const DataType dense = ctx->InputDType("b", 0);
+  CHECK_OR_RETURN(val_dtype == DataType::kInvalidDataType || val_dtype == DataType::kFloat || val_dtype == dense)
+      << "val_dtype must be float32 or match b";
+  ctx->SetOutputDType("dval", 0, val_dtype == DataType::kInvalidDataType ? dense : val_dtype);
   return Maybe<void>::Ok();
 }
 /*static*/ Maybe<void> SddmmCsrOp::GetSbp(user_op::SbpContext* ctx) {
@@ -144,11 +174,42 @@ Maybe<void> DenseColumnSplitSbp(user_op::SbpContext* ctx, const char* dense_in, 
       .Split(user_op::OpArg("b", 0), 1)
       .PartialSum(user_op::OpArg("dval", 0))
       .Build();
+  // linear in dy and in b: partial sums pass through
+  ctx->NewBuilder().Broadcast(user_op::OpArg("a_crow", 0)).Broadcast(user_op::OpArg("a_col", 0))
+      .PartialSum(user_op::OpArg("dy", 0)).Broadcast(user_op::OpArg("b", 0)).PartialSum(user_op::OpArg("dval", 0)).Build();
+  ctx->NewBuilder().Broadcast(user_op::OpArg("a_crow", 0)).Broadcast(user_op::OpArg("a_col", 0))
+      .Broadcast(user_op::OpArg("dy", 0)).PartialSum(user_op::OpArg("b", 0)).PartialSum(user_op::OpArg("dval", 0)).Build();
   ctx->NewBuilder().Broadcast(ctx->inputs()).Broadcast(ctx->outputs()).Build();
   return Maybe<void>::Ok();
 }
 /*static*/ Maybe<void> SddmmCsrOp::ModifyInputArg(const GetInputArgModifier& fn,
                                                   const user_op::UserOpConfWrapper&) {
+  return NoGradForIndices(fn);
+}
+
+// ---------------------------------------------------------------- csr_transpose_structure
+/*static*/ Maybe<void> CsrTransposeStructureOp::InferLogicalTensorDesc(user_op::InferContext* ctx) {
+  int64_t nnz = 0;
+  JUST(CheckCsr(ctx, &nnz));
+  ctx->SetOutputShape("t_crow", 0, Shape({ctx->Attr<int64_t>("a_cols") + 1}));
+  ctx->SetOutputShape("t_col", 0, Shape({nnz}));
+  ctx->SetOutputShape("t_perm", 0, Shape({nnz}));
+  return Maybe<void>::Ok();
+}
+/*static*/ Maybe<void> CsrTransposeStructureOp::InferPhysicalTensorDesc(user_op::InferContext* ctx) {
+  return InferLogicalTensorDesc(ctx);
+}
+/*static*/ Maybe<void> CsrTransposeStructureOp::InferDataType(user_op::InferContext* ctx) {
+  JUST(CheckIndexTypes(ctx));
+  for (const char* out : {"t_crow", "t_col", "t_perm"}) { ctx->SetOutputDType(out, 0, ctx->InputDType("a_crow", 0)); }
+  return Maybe<void>::Ok();
+}
+/*static*/ Maybe<void> CsrTransposeStructureOp::GetSbp(user_op::SbpContext* ctx) {
+  ctx->NewBuilder().Broadcast(ctx->inputs()).Broadcast(ctx->outputs()).Build();   // index work: replicated
+  return Maybe<void>::Ok();
+}
+/*static*/ Maybe<void> CsrTransposeStructureOp::ModifyInputArg(const GetInputArgModifier& fn,
+                                                               const user_op::UserOpConfWrapper&) {
   return NoGradForIndices(fn);
 }
 

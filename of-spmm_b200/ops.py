@@ -180,20 +180,34 @@ class SpmmPlan:
 
 
 def _opts(flags: int = 0, tasks_per_warp: int = 0, variant: int = 0, part: Optional[torch.Tensor] = None,
-          bias: Optional[torch.Tensor] = None) -> OptsStruct:
+          bias: Optional[torch.Tensor] = None, acc32: Optional[torch.Tensor] = None) -> OptsStruct:
     return OptsStruct(flags, tasks_per_warp, variant, 0, part.data_ptr() if part is not None else None,
-                      part.numel() if part is not None else 0, bias.data_ptr() if bias is not None else None)
+                      part.numel() if part is not None else 0, bias.data_ptr() if bias is not None else None,
+                      acc32.data_ptr() if acc32 is not None else None)
+
+
+def _acc32_flags(acc32, acc32_in: bool, acc32_out: bool, rows: int, n: int, dt) -> int:
+    if not (acc32_in or acc32_out):
+        return 0
+    _chk(dt != torch.float32, "acc32 passes are for 16-bit products (fp32 products accumulate in `out`)")
+    _chk(acc32 is not None and acc32.dtype == torch.float32 and acc32.is_contiguous() and acc32.is_cuda
+         and acc32.dim() == 2 and acc32.shape[0] >= rows and acc32.shape[1] == n,
+         "acc32 must be a contiguous CUDA float32 tensor of shape (>= rows, n)")
+    return (_lib.FWD_ACC32_IN if acc32_in else 0) | (_lib.FWD_ACC32_OUT if acc32_out else 0)
 
 
 def spmm_csr_compute(a_crow, a_col, a_val, b, a_rows: int, a_cols: int,
                      out: Optional[torch.Tensor] = None, *, plan: Optional[SpmmPlan] = None,
                      accumulate: bool = False, bias: Optional[torch.Tensor] = None, relu: bool = False,
-                     tasks_per_warp: int = 0, variant: Optional[int] = None, order: Optional[str] = None) -> torch.Tensor:
+                     tasks_per_warp: int = 0, variant: Optional[int] = None, order: Optional[str] = None,
+                     acc32: Optional[torch.Tensor] = None, acc32_in: bool = False, acc32_out: bool = False) -> torch.Tensor:
     """SpmmCsrKernel::Compute — out[a_rows, n] = A · b  (``accumulate``: out += A · b; ``bias`` /
     ``relu``: epilogue fused into the store, applied to the complete row sum).
 
     ``plan`` supplies the histogram-chosen variant and the cached task partition; ``tasks_per_warp``
-    > 0 launches short-lived CTAs (multi-GPU overlap); ``order`` in {None, "dynamic", "static"}."""
+    > 0 launches short-lived CTAs (multi-GPU overlap); ``order`` in {None, "dynamic", "static"}.
+    ``acc32`` (+ ``acc32_in`` / ``acc32_out``): fp32 running sums of a bf16 product that is computed
+    in several passes — rounded to bf16 once, by the pass without ``acc32_out``."""
     _check_device(a_crow, a_col, a_val, b, bias)
     (m, n), dt = infer_spmm_csr(a_crow, a_col, a_val, b, a_rows, a_cols)
     if out is None:
@@ -210,7 +224,8 @@ def spmm_csr_compute(a_crow, a_col, a_val, b, a_rows: int, a_cols: int,
         _chk(plan.matches(a_crow, a_col, a_rows, a_cols, n, dt), "plan was built for another CSR structure / n / dtype")
     L = _lib.lib()
     flags = (_lib.FWD_ACCUMULATE if accumulate else 0) | (_lib.FWD_BIAS if bias is not None else 0) | \
-            (_lib.FWD_RELU if relu else 0) | {None: 0, "dynamic": _lib.ORDER_DYNAMIC, "static": _lib.ORDER_STATIC}[order]
+            (_lib.FWD_RELU if relu else 0) | {None: 0, "dynamic": _lib.ORDER_DYNAMIC, "static": _lib.ORDER_STATIC}[order] | \
+            _acc32_flags(acc32, acc32_in, acc32_out, m, n, dt)
     v = variant if variant is not None else (plan.variant if plan is not None else _lib.VARIANT_AUTO)
     part = plan.part if (plan is not None and v == plan.variant) else None
     with torch.cuda.device(b.device):
@@ -219,7 +234,7 @@ def spmm_csr_compute(a_crow, a_col, a_val, b, a_rows: int, a_cols: int,
         ws, wsp = _workspace(nbytes, b.device)
         ldb = b.stride(0) if b.shape[0] > 1 else max(n, 1)
         ldc = out.stride(0) if out.shape[0] > 1 else max(n, 1)
-        o = _opts(flags, tasks_per_warp, v, part, bias)
+        o = _opts(flags, tasks_per_warp, v, part, bias, acc32 if (acc32_in or acc32_out) else None)
         rc = L.ofspmm_fwd_ex(ctypes.byref(A), _ptr(b), ldb, _ptr(out), ldc, n, _DENSE[dt], ctypes.byref(o), wsp, nbytes,
                              _stream_ptr(b))
         check(rc, "spmm_csr")
@@ -229,7 +244,8 @@ def spmm_csr_compute(a_crow, a_col, a_val, b, a_rows: int, a_cols: int,
 def spmm_csr_grad_b_compute(a_crow, a_col, a_val, dy, a_rows: int, a_cols: int,
                             transposed: Optional[Tuple[torch.Tensor, torch.Tensor, torch.Tensor]] = None,
                             out: Optional[torch.Tensor] = None, *, plan: Optional[SpmmPlan] = None,
-                            atomic: bool = False, tasks_per_warp: int = 0, regather: bool = False) -> torch.Tensor:
+                            atomic: bool = False, tasks_per_warp: int = 0, regather: bool = False,
+                            acc32_out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """SpmmCsrGradBKernel::Compute — db[a_cols, n] = A^T · dy.  Routes, in order of preference:
 
       * ``plan`` with a transposed structure → forward kernel on the cached structure of A^T; the
@@ -249,6 +265,8 @@ def spmm_csr_grad_b_compute(a_crow, a_col, a_val, dy, a_rows: int, a_cols: int,
     else:
         _chk(out.shape == (a_cols, n) and out.dtype == dt and out.device == dy.device, "out has the wrong shape / dtype / device")
     L = _lib.lib()
+    _chk(acc32_out is None or (plan is not None and plan.t_crow is not None and not atomic and not regather),
+         "acc32_out needs the plan route with cached transposed values")
     if plan is not None and plan.t_crow is not None and not atomic:
         _chk(plan.matches(a_crow, a_col, a_rows, a_cols, n, dt), "plan was built for another CSR structure / n / dtype")
         with torch.cuda.device(dy.device):
@@ -267,7 +285,10 @@ def spmm_csr_grad_b_compute(a_crow, a_col, a_val, dy, a_rows: int, a_cols: int,
                 At = _csr_struct(plan.t_crow, plan.t_col, plan.transposed_values(a_val), a_cols, a_rows)
                 nbytes = L.ofspmm_fwd_ex_workspace_bytes(a_cols, a_rows, At.nnz, n, _DENSE[dt], plan.t_variant)
                 ws, wsp = _workspace(nbytes, dy.device)
-                o = _opts(0, tasks_per_warp, plan.t_variant, plan.t_part)
+                # acc32_out: the fp32 sums go to that buffer instead of `out` (16-bit products whose
+                # partial results are combined across ranks in fp32)
+                fl = _acc32_flags(acc32_out, False, acc32_out is not None, a_cols, n, dt)
+                o = _opts(fl, tasks_per_warp, plan.t_variant, plan.t_part, None, acc32_out)
                 check(L.ofspmm_fwd_ex(ctypes.byref(At), _ptr(dy), n, _ptr(out), n, n, _DENSE[dt], ctypes.byref(o), wsp, nbytes,
                                       _stream_ptr(dy)), "spmm_csr_grad_b(cached structure + values)")
         return out
@@ -432,4 +453,33 @@ def scatter_add_rows(dst: torch.Tensor, src: torch.Tensor, index: Optional[torch
                                                  _INDEX[index.dtype] if index is not None else _lib.DTYPE_INT32,
                                                  index_offset, count, n, _DENSE[dst.dtype], max_ctas, _stream_ptr(dst)),
               "scatter_add_rows")
+    return dst
+
+
+def scatter_add_rows_f32(dst: torch.Tensor, src: torch.Tensor, index: Optional[torch.Tensor] = None, index_offset: int = 0,
+                         count: Optional[int] = None, max_ctas: int = 0) -> torch.Tensor:
+    """fp32 dst[index[i] - index_offset, :] += float(src[i, :]) — src bf16 (or fp32) partial rows, e.g. a
+    peer's; the sum over many contributors is rounded once at the end (``cast_from_f32``)."""
+    _check_device(dst, index)
+    _chk(dst.dtype == torch.float32 and dst.dim() == 2 and src.dim() == 2 and dst.shape[1] == src.shape[1]
+         and src.dtype in _DENSE and dst.stride(1) == 1 and src.stride(1) == 1, "scatter_add_rows_f32: fp32 dst, dense src")
+    count = int(index.numel() if index is not None else (src.shape[0] if count is None else count))
+    n = int(dst.shape[1])
+    with torch.cuda.device(dst.device):
+        check(_lib.lib().ofspmm_scatter_add_rows_f32(_ptr(dst), dst.stride(0) if dst.shape[0] > 1 else n, _ptr(src),
+                                                     src.stride(0) if src.shape[0] > 1 else n, _ptr(index),
+                                                     _INDEX[index.dtype] if index is not None else _lib.DTYPE_INT32,
+                                                     index_offset, count, n, _DENSE[src.dtype], max_ctas, _stream_ptr(dst)),
+              "scatter_add_rows_f32")
+    return dst
+
+
+def cast_from_f32(dst: torch.Tensor, src: torch.Tensor) -> torch.Tensor:
+    """dst = dtype(dst)(src) elementwise, src fp32, both contiguous with the same number of elements."""
+    _check_device(dst, src)
+    _chk(src.dtype == torch.float32 and dst.dtype in _DENSE and dst.is_contiguous() and src.is_contiguous()
+         and dst.numel() == src.numel(), "cast_from_f32: contiguous fp32 source and dense destination of equal size")
+    with torch.cuda.device(dst.device):
+        check(_lib.lib().ofspmm_cast_from_f32(_ptr(src), _ptr(dst), dst.numel(), _DENSE[dst.dtype], _stream_ptr(dst)),
+              "cast_from_f32")
     return dst

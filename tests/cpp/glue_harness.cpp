@@ -45,8 +45,8 @@ std::map<std::string, std::function<OpExprGradFunctionIf*()>>& GradFunctionRegis
   return r;
 }
 namespace functional {
-std::map<std::string, SpmmFn>& FunctionLibraryStore() {
-  static std::map<std::string, SpmmFn> r;
+std::map<std::string, std::any>& FunctionLibraryStore() {
+  static std::map<std::string, std::any> r;
   return r;
 }
 }  // namespace functional
@@ -69,6 +69,9 @@ struct TensorDescs {
   std::map<std::string, Shape> shapes;
   std::map<std::string, DataType> dtypes;
   std::map<std::string, int64_t> attrs;
+  std::map<std::string, bool> battrs{{"atomic", false}};
+  std::map<std::string, DataType> dattrs{{"val_dtype", kInvalidDataType}};
+  std::vector<std::string> present;   // optional inputs that are bound
 };
 
 class MockInferContext final : public user_op::InferContext {
@@ -78,8 +81,13 @@ class MockInferContext final : public user_op::InferContext {
   void SetOutputShape(const std::string& n, int32_t, const Shape& s) override { d_->shapes[n] = s; }
   DataType InputDType(const std::string& n, int32_t) const override { return d_->dtypes.at(n); }
   void SetOutputDType(const std::string& n, int32_t, DataType t) override { d_->dtypes[n] = t; }
+  bool has_input(const std::string& n, int32_t) const override {
+    return std::find(d_->present.begin(), d_->present.end(), n) != d_->present.end();
+  }
  protected:
   const int64_t& AttrInt64(const std::string& n) const override { return d_->attrs.at(n); }
+  const bool& AttrBool(const std::string& n) const override { return d_->battrs.at(n); }
+  const DataType& AttrDataType(const std::string& n) const override { return d_->dattrs.at(n); }
  private:
   TensorDescs* d_;
 };
@@ -131,6 +139,24 @@ void HostChecks() {
   EXPECT(d.shapes.at("db") == Shape({200, 64}));
   EXPECT(SddmmCsrOp::InferLogicalTensorDesc(&ic).IsOk());
   EXPECT(d.shapes.at("dval") == Shape({1234}));
+  // the SDDMM gradient takes the dtype of the values it differentiates (attr val_dtype), not b's
+  TensorDescs db16 = SpmmDescs(300, 200, 1234, 64, kBFloat16, kInt32);
+  db16.dattrs["val_dtype"] = kFloat;
+  MockInferContext ic_b16(&db16);
+  EXPECT(SddmmCsrOp::InferDataType(&ic_b16).IsOk() && db16.dtypes.at("dval") == kFloat);
+  db16.dattrs["val_dtype"] = kInvalidDataType;
+  EXPECT(SddmmCsrOp::InferDataType(&ic_b16).IsOk() && db16.dtypes.at("dval") == kBFloat16);
+  // csr_transpose_structure: three index outputs
+  EXPECT(CsrTransposeStructureOp::InferLogicalTensorDesc(&ic).IsOk() && CsrTransposeStructureOp::InferDataType(&ic).IsOk());
+  EXPECT(d.shapes.at("t_crow") == Shape({201}) && d.shapes.at("t_col") == Shape({1234}) && d.shapes.at("t_perm") == Shape({1234}));
+  EXPECT(d.dtypes.at("t_perm") == kInt32);
+  // spmm_csr_grad_b with the cached structure bound: shapes are checked
+  d.present = {"t_crow", "t_col", "t_perm"};
+  EXPECT(SpmmCsrGradBOp::InferLogicalTensorDesc(&ic).IsOk());
+  d.shapes["t_crow"] = Shape({7});
+  Maybe<void> mt = SpmmCsrGradBOp::InferLogicalTensorDesc(&ic);
+  EXPECT(!mt.IsOk() && mt.msg().find("a_cols+1") != std::string::npos);
+  d.present.clear();
   // errors surface as failed Maybe<void> with the message of the failing CHECK
   TensorDescs bad = SpmmDescs(300, 200, 1234, 64, kFloat, kInt32);
   bad.attrs["a_cols"] = 7;
@@ -150,12 +176,25 @@ void HostChecks() {
   // ---- SBP: CSR arrays broadcast, dense side column-split; SDDMM column split -> partial sum
   MockSbpContext sc({{"a_crow", 0}, {"a_col", 0}, {"a_val", 0}, {"b", 0}}, {{"out", 0}});
   EXPECT(SpmmCsrOp::GetSbp(&sc).IsOk());
-  EXPECT(sc.signatures.size() == 2);
+  EXPECT(sc.signatures.size() == 4);
   EXPECT(sc.signatures[0].find("b:S(1)") != std::string::npos && sc.signatures[0].find("out:S(1)") != std::string::npos);
   EXPECT(sc.signatures[0].find("a_col:B") != std::string::npos);
+  // bilinear: partial sums of the values or of the dense operand give a partial-sum output
+  EXPECT(sc.signatures[1].find("a_val:P") != std::string::npos && sc.signatures[1].find("b:B") != std::string::npos &&
+         sc.signatures[1].find("out:P") != std::string::npos && sc.signatures[1].find("a_col:B") != std::string::npos);
+  EXPECT(sc.signatures[2].find("a_val:B") != std::string::npos && sc.signatures[2].find("b:P") != std::string::npos &&
+         sc.signatures[2].find("out:P") != std::string::npos);
+  // spmm_csr_grad_b: same family (incl. the P-sum signatures), cached structure broadcast
+  MockSbpContext sg({{"a_crow", 0}, {"a_col", 0}, {"a_val", 0}, {"dy", 0}, {"t_crow", 0}, {"t_col", 0}, {"t_perm", 0}}, {{"db", 0}});
+  EXPECT(SpmmCsrGradBOp::GetSbp(&sg).IsOk() && sg.signatures.size() == 4);
+  EXPECT(sg.signatures[2].find("dy:P") != std::string::npos && sg.signatures[2].find("db:P") != std::string::npos &&
+         sg.signatures[2].find("t_perm:B") != std::string::npos);
+  EXPECT(sg.signatures[1].find("a_val:P") != std::string::npos && sg.signatures[1].find("db:P") != std::string::npos);
   MockSbpContext sd({{"a_crow", 0}, {"a_col", 0}, {"dy", 0}, {"b", 0}}, {{"dval", 0}});
   EXPECT(SddmmCsrOp::GetSbp(&sd).IsOk());
   EXPECT(sd.signatures[0].find("dval:P") != std::string::npos);
+  EXPECT(sd.signatures.size() == 4 && sd.signatures[1].find("dy:P") != std::string::npos &&
+         sd.signatures[2].find("b:P") != std::string::npos);
   // ---- index inputs never require grad (ModifyInputArg)
   std::map<std::string, user_op::InputArgModifier> mods;
   auto getter = [&](const std::string& n, int32_t) { return &mods[n]; };
@@ -183,6 +222,18 @@ void HostChecks() {
   TensorDescs d2 = SpmmDescs(300, 200, 1234, 64, kFloat, kInt32);
   MockInferContext ic2(&d2);
   EXPECT(reg->infer_tmp_size(&ic2) == ofspmm_fwd_workspace_bytes(300, 200, 1234, 64, OFSPMM_DTYPE_FLOAT));
+  // spmm_csr_grad_b: the route decides the tmp size — transient (default), atomic, cached structure
+  user_op::KernelMatchQuery qg{DeviceType::kCUDA, {{"dy", kFloat}, {"a_col", kInt32}}};
+  const auto* regg = FindKernel("spmm_csr_grad_b", qg, &matches);
+  EXPECT(regg->infer_tmp_size(&ic2) ==
+         ofspmm_bwd_b_transient_workspace_bytes(300, 200, 1234, 64, OFSPMM_DTYPE_FLOAT, OFSPMM_DTYPE_INT32, OFSPMM_DTYPE_FLOAT));
+  d2.battrs["atomic"] = true;
+  EXPECT(regg->infer_tmp_size(&ic2) == ofspmm_bwd_b_workspace_bytes(300, 200, 1234, 64, OFSPMM_DTYPE_FLOAT, 0));
+  d2.battrs["atomic"] = false;
+  d2.present = {"t_crow", "t_col", "t_perm"};
+  EXPECT(regg->infer_tmp_size(&ic2) == ofspmm_bwd_b_cached_workspace_bytes(300, 200, 1234, 64, OFSPMM_DTYPE_FLOAT, OFSPMM_DTYPE_FLOAT));
+  user_op::KernelMatchQuery qt{DeviceType::kCUDA, {{"a_col", kInt64}}};
+  EXPECT(FindKernel("csr_transpose_structure", qt, &matches) != nullptr && matches == 1);
   std::printf("glue host checks ok: %zu kernel registrations\n", user_op::KernelRegistry().size());
 }
 
@@ -199,6 +250,17 @@ void AutogradChecks() {
   auto out = one::functional::SpmmCsr(crow, col, T("val", {1234}, true), T("b", {200, 64}, true), 300, 200);
   EXPECT(out.IsOk() && log.size() == 1 && log[0].op == "spmm_csr");
   EXPECT((log[0].inputs == std::vector<std::string>{"crow", "col", "val", "b"}));
+  // ... with the cached structure of A^T riding along as optional inputs
+  auto tcrow = T("t_crow", {201}, false), tcol = T("t_col", {1234}, false), tperm = T("t_perm", {1234}, false);
+  log.clear();
+  out = one::functional::SpmmCsr(crow, col, T("val", {1234}, true), T("b", {200, 64}, true), 300, 200, tcrow, tcol, tperm);
+  EXPECT(out.IsOk() && log.size() == 1 && log[0].inputs.size() == 7 && log[0].inputs[6] == "t_perm");
+  auto half = one::functional::SpmmCsr(crow, col, T("val", {1234}, true), T("b", {200, 64}, true), 300, 200, tcrow);
+  EXPECT(!half.IsOk() && half.msg().find("come together") != std::string::npos);
+  // flow._C.csr_transpose_structure -> three tensors
+  log.clear();
+  auto ts = one::functional::CsrTransposeStructure(crow, col, 300, 200);
+  EXPECT(ts.IsOk() && ts.Value()->size() == 3 && log[0].op == "csr_transpose_structure");
   EXPECT(log[0].attrs.at("a_rows") == 300 && log[0].attrs.at("a_cols") == 200);
   auto bad = one::functional::SpmmCsr(crow, col, T("val", {1234}, true), T("b", {200}, true), 300, 200);
   EXPECT(!bad.IsOk() && bad.msg().find("RuntimeError") != std::string::npos && bad.msg().find("2-D") != std::string::npos);
@@ -210,15 +272,17 @@ void AutogradChecks() {
   one::UserOpExpr fw;
   fw.op_type_name = "spmm_csr";
   fw.proto_.attrs.ints = {{"a_rows", 300}, {"a_cols", 200}};
-  auto run_case = [&](bool val_rg, bool b_rg, one::TensorTuple* in_grads) {
+  auto run_case = [&](bool val_rg, bool b_rg, one::TensorTuple* in_grads, bool with_at = false, DataType vdt = kFloat) {
     std::unique_ptr<one::OpExprGradFunctionIf> g(one::GradFunctionRegistry().at("spmm_csr")());
     EXPECT(g->Init(fw).IsOk());
     auto state = g->MakeCustomState();
-    one::TensorTuple inputs = {crow, col, T("val", {1234}, val_rg), T("b", {200, 64}, b_rg)};
+    one::TensorTuple inputs = {crow, col, std::make_shared<Tensor>("val", std::vector<int64_t>{1234}, val_rg, vdt),
+                               T("b", {200, 64}, b_rg)};
+    if (with_at) { inputs.push_back(tcrow); inputs.push_back(tcol); inputs.push_back(tperm); }
     one::TensorTuple outputs = {T("out", {300, 64}, val_rg || b_rg)};
     EXPECT(g->CaptureIf(state.get(), inputs, outputs, AttrMap()).IsOk());
     log.clear();
-    in_grads->assign(4, nullptr);
+    in_grads->assign(with_at ? 7 : 4, nullptr);
     EXPECT(g->ApplyIf(state.get(), {T("dy", {300, 64}, false)}, in_grads).IsOk());
     return state->SavedTensors().size();
   };
@@ -228,8 +292,15 @@ void AutogradChecks() {
   EXPECT(saved == 4 && log.size() == 2);
   EXPECT(log[0].op == "sddmm_csr" && (log[0].inputs == std::vector<std::string>{"crow", "col", "dy", "b"}));
   EXPECT(log[1].op == "spmm_csr_grad_b" && (log[1].inputs == std::vector<std::string>{"crow", "col", "val", "dy"}));
-  EXPECT(log[1].attrs.at("a_rows") == 300 && log[1].attrs.at("a_cols") == 200);
+  EXPECT(log[1].attrs.at("a_rows") == 300 && log[1].attrs.at("a_cols") == 200 && log[1].attrs.at("atomic") == 0);
+  EXPECT(log[0].attrs.at("val_dtype") == kFloat);   // SDDMM gradient in the dtype of a_val
   EXPECT(ig[0] == nullptr && ig[1] == nullptr && ig[2] != nullptr && ig[3] != nullptr);
+  // cached structure of A^T given to the forward: saved and handed to spmm_csr_grad_b, no grads for it
+  saved = run_case(true, true, &ig, /*with_at=*/true, kBFloat16);
+  EXPECT(saved == 7 && log.size() == 2 && log[1].op == "spmm_csr_grad_b");
+  EXPECT((log[1].inputs == std::vector<std::string>{"crow", "col", "val", "dy", "t_crow", "t_col", "t_perm"}));
+  EXPECT(log[0].attrs.at("val_dtype") == kBFloat16);
+  EXPECT(ig.size() == 7 && ig[4] == nullptr && ig[5] == nullptr && ig[6] == nullptr);
   // only b: no SDDMM, b itself is not saved
   saved = run_case(false, true, &ig);
   EXPECT(saved == 3 && log.size() == 1 && log[0].op == "spmm_csr_grad_b" && ig[2] == nullptr && ig[3] != nullptr);
@@ -293,9 +364,12 @@ class MockComputeContext final : public user_op::KernelComputeContext {
     return it == tensors.end() ? nullptr : it->second;
   }
   ep::Stream* stream() override { return stream_; }
+  bool has_input(const std::string& n, int32_t) const override { return tensors.count(n) != 0; }
   std::map<std::string, user_op::Tensor*> tensors;
+  bool atomic = false;
  protected:
   const int64_t& AttrInt64(const std::string& n) const override { return attrs_.at(n); }
+  const bool& AttrBool(const std::string&) const override { return atomic; }
  private:
   ep::Stream* stream_;
   std::map<std::string, int64_t> attrs_;
@@ -346,15 +420,21 @@ void GpuChecks() {
   MockInferContext ic(&d);
   int matches = 0;
 
-  auto run = [&](const char* op, const char* dense_arg, std::map<std::string, user_op::Tensor*> tensors, int repeat) {
-    user_op::KernelMatchQuery q{DeviceType::kCUDA, {{dense_arg, kFloat}, {"a_col", kInt32}}};
+  auto run = [&](const char* op, const char* dense_arg, std::map<std::string, user_op::Tensor*> tensors, int repeat,
+                 bool atomic = false) {
+    user_op::KernelMatchQuery q{DeviceType::kCUDA, {{dense_arg, std::string(dense_arg) == "a_col" ? kInt32 : kFloat}, {"a_col", kInt32}}};
     const auto* reg = FindKernel(op, q, &matches);
     EXPECT(reg != nullptr && matches == 1);
+    d.battrs["atomic"] = atomic;
+    d.present.clear();
+    for (const char* opt : {"t_crow", "t_col", "t_perm"})
+      if (tensors.count(opt) && std::string(op) != "csr_transpose_structure") d.present.push_back(opt);
     const size_t tmp = reg->infer_tmp_size(&ic);
     DevTensor t_tmp(Shape({static_cast<int64_t>(tmp)}), kChar, nullptr, tmp);
     tensors["tmp_buffer"] = &t_tmp;
     MockComputeContext ctx(&stream, {{"a_rows", M}, {"a_cols", K}});
     ctx.tensors = tensors;
+    ctx.atomic = atomic;
     std::unique_ptr<user_op::OpKernel> kernel = reg->create();
     user_op::KernelInitContext init;
     std::shared_ptr<user_op::OpKernelState> state = kernel->CreateOpKernelState(&init);
@@ -376,7 +456,31 @@ void GpuChecks() {
   got.resize(dB.size());
   t_db.ToHost(got.data());
   EXPECT(max_err(got, dB) < 2e-5);
-  EXPECT(device.live == 0);  // the transpose state released its device buffers with the kernel state
+  EXPECT(device.live == 0);  // nothing is ever allocated through the stream's device: no hidden op state
+  // atomic route (attr)
+  run("spmm_csr_grad_b", "dy", {{"a_crow", &t_crow}, {"a_col", &t_col}, {"a_val", &t_val}, {"dy", &t_dy}, {"db", &t_db}}, 1, true);
+  t_db.ToHost(got.data());
+  EXPECT(max_err(got, dB) < 2e-5);
+  // cached-structure route: csr_transpose_structure once, then spmm_csr_grad_b with the three optional
+  // inputs; the values are re-gathered on every call, so an in-place update of a_val is seen
+  DevTensor t_tcrow(Shape({K + 1}), kInt32, nullptr, (K + 1) * 4), t_tcol(Shape({nnz}), kInt32, nullptr, nnz * 4);
+  DevTensor t_tperm(Shape({nnz}), kInt32, nullptr, nnz * 4);
+  run("csr_transpose_structure", "a_col", {{"a_crow", &t_crow}, {"a_col", &t_col}, {"t_crow", &t_tcrow}, {"t_col", &t_tcol},
+                                          {"t_perm", &t_tperm}}, 1);
+  std::map<std::string, user_op::Tensor*> cached = {{"a_crow", &t_crow}, {"a_col", &t_col}, {"a_val", &t_val}, {"dy", &t_dy},
+                                                    {"db", &t_db}, {"t_crow", &t_tcrow}, {"t_col", &t_tcol}, {"t_perm", &t_tperm}};
+  run("spmm_csr_grad_b", "dy", cached, 1);
+  t_db.ToHost(got.data());
+  EXPECT(max_err(got, dB) < 2e-5);
+  std::vector<float> val2(val);
+  for (auto& v : val2) v = -2.f * v;
+  CUDA_OK(cudaMemcpy(t_val.mut_raw_dptr(), val2.data(), val2.size() * 4, cudaMemcpyHostToDevice));   // same pointer, new values
+  run("spmm_csr_grad_b", "dy", cached, 1);
+  t_db.ToHost(got.data());
+  std::vector<double> dB2(dB);
+  for (auto& x : dB2) x *= -2.0;
+  EXPECT(max_err(got, dB2) < 4e-5);
+  CUDA_OK(cudaMemcpy(t_val.mut_raw_dptr(), val.data(), val.size() * 4, cudaMemcpyHostToDevice));
 
   run("sddmm_csr", "b", {{"a_crow", &t_crow}, {"a_col", &t_col}, {"dy", &t_dy}, {"b", &t_b}, {"dval", &t_dval}}, 1);
   got.resize(dval.size());

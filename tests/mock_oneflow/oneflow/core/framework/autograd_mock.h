@@ -1,6 +1,7 @@
 // Stand-ins for the functional / autograd slice used by oneflow_glue/spmm_functor.cpp and
 // spmm_grad.cpp.  TEST INFRASTRUCTURE; each declaration cites the reference header it mirrors.
 #pragma once
+#include <any>
 #include <tuple>
 
 #include "oneflow/core/framework/framework.h"
@@ -43,11 +44,27 @@ class ComposedAttrMap {  // oneflow/core/framework/attr_map.h (prior attrs shado
 namespace one {
 
 // oneflow/core/framework/tensor.h
+// oneflow/core/common/optional.h (the slice the functors use): an optional tensor argument is an
+// Optional<Tensor>; `if (opt)` tests it and JUST(opt) yields the std::shared_ptr<Tensor>.
+template <typename T> class Optional {
+ public:
+  Optional() = default;
+  Optional(std::shared_ptr<T> v) : v_(std::move(v)) {}  // NOLINT
+  bool has_value() const { return v_ != nullptr; }
+  explicit operator bool() const { return has_value(); }
+  bool IsOk() const { return has_value(); }
+  std::string msg() const { return "Optional has no value"; }
+  std::shared_ptr<T> Value() const { return v_; }
+ private:
+  std::shared_ptr<T> v_;
+};
+
 class Tensor {
  public:
-  Tensor(std::string name, std::vector<int64_t> dims, bool requires_grad)
-      : name_(std::move(name)), dims_(std::move(dims)), requires_grad_(requires_grad) {}
+  Tensor(std::string name, std::vector<int64_t> dims, bool requires_grad, DataType dtype = kFloat)
+      : name_(std::move(name)), dims_(std::move(dims)), requires_grad_(requires_grad), dtype_(dtype) {}
   bool requires_grad() const { return requires_grad_; }
+  DataType dtype() const { return dtype_; }
   int64_t ndim() const { return static_cast<int64_t>(dims_.size()); }
   int64_t dim(int64_t i) const { return dims_.at(i); }
   const std::string& name() const { return name_; }
@@ -55,6 +72,7 @@ class Tensor {
   std::string name_;
   std::vector<int64_t> dims_;
   bool requires_grad_;
+  DataType dtype_;
 };
 using TensorTuple = std::vector<std::shared_ptr<Tensor>>;
 
@@ -93,7 +111,13 @@ struct OpInterpUtil {
     for (const auto& t : inputs) r.inputs.push_back(t->name());
     r.attrs = attrs.ints;
     DispatchLog().push_back(r);
-    return std::make_shared<Tensor>(op.op_type_name + ":" + op.outputs.at(0), std::vector<int64_t>{}, false);
+    if constexpr (std::is_same<T, TensorTuple>::value) {
+      auto outs = std::make_shared<TensorTuple>();
+      for (const auto& o : op.outputs) outs->push_back(std::make_shared<Tensor>(op.op_type_name + ":" + o, std::vector<int64_t>{}, false));
+      return outs;
+    } else {
+      return std::make_shared<Tensor>(op.op_type_name + ":" + op.outputs.at(0), std::vector<int64_t>{}, false);
+    }
   }
 };
 
@@ -136,20 +160,20 @@ struct GradRegisterTrigger {
 #define REGISTER_OP_EXPR_GRAD_FUNCTION(op_type, op_grad) \
   static ::oneflow::one::GradRegisterTrigger OF_MOCK_CAT(g_grad_trigger_, __COUNTER__)(op_type, [] { return static_cast<::oneflow::one::OpExprGradFunctionIf*>(new op_grad); })
 
-// oneflow/core/functional/function_library.h + generated functional.h: the three functors share
-// one signature, so the library stores them type-erased under their YAML names.
+// oneflow/core/functional/function_library.h + generated functional.h: functors are stored
+// type-erased under their YAML names, each with the signature of its operator().
 namespace functional {
-using SpmmFn = std::function<Maybe<Tensor>(const std::shared_ptr<Tensor>&, const std::shared_ptr<Tensor>&,
-                                           const std::shared_ptr<Tensor>&, const std::shared_ptr<Tensor>&,
-                                           const int64_t&, const int64_t&)>;
-std::map<std::string, SpmmFn>& FunctionLibraryStore();
+template <typename T> struct FunctorSignature;
+template <typename C, typename R, typename... A> struct FunctorSignature<R (C::*)(A...) const> {
+  using type = std::function<R(A...)>;
+  template <typename F> static type Wrap(std::shared_ptr<F> f) { return [f](A... a) { return (*f)(a...); }; }
+};
+std::map<std::string, std::any>& FunctionLibraryStore();
 class FunctionLibrary {
  public:
   template <typename F> void add_functor(const std::string& name) {
-    auto f = std::make_shared<F>();
-    FunctionLibraryStore()[name] = [f](const std::shared_ptr<Tensor>& a, const std::shared_ptr<Tensor>& b,
-                                       const std::shared_ptr<Tensor>& c, const std::shared_ptr<Tensor>& d,
-                                       const int64_t& r, const int64_t& k) { return (*f)(a, b, c, d, r, k); };
+    using Sig = FunctorSignature<decltype(&F::operator())>;
+    FunctionLibraryStore()[name] = Sig::Wrap(std::make_shared<F>());
   }
 };
 struct FunctionLibraryTrigger { explicit FunctionLibraryTrigger(void (*fn)(FunctionLibrary&)) { FunctionLibrary m; fn(m); } };
@@ -158,17 +182,37 @@ struct FunctionLibraryTrigger { explicit FunctionLibraryTrigger(void (*fn)(Funct
   static ::oneflow::one::functional::FunctionLibraryTrigger OF_MOCK_CAT(g_fl_trigger_, __LINE__)(        \
       &OF_MOCK_CAT(of_function_library_, __LINE__));                                    \
   static void OF_MOCK_CAT(of_function_library_, __LINE__)(::oneflow::one::functional::FunctionLibrary& m)
-// what functional_api.yaml.patch generates (tools/functional/*.py): free functions by YAML name
-#define OF_MOCK_FUNCTIONAL(Name)                                                                   \
-  inline Maybe<Tensor> Name(const std::shared_ptr<Tensor>& a, const std::shared_ptr<Tensor>& b,   \
-                            const std::shared_ptr<Tensor>& c, const std::shared_ptr<Tensor>& d,   \
-                            const int64_t& r, const int64_t& k) {                                  \
-    return FunctionLibraryStore().at(#Name)(a, b, c, d, r, k);                                    \
-  }
-OF_MOCK_FUNCTIONAL(SpmmCsr)
-OF_MOCK_FUNCTIONAL(SpmmCsrGradB)
-OF_MOCK_FUNCTIONAL(SddmmCsr)
-#undef OF_MOCK_FUNCTIONAL
+// what functional_api.yaml.patch generates (tools/functional/*.py): free functions by YAML name,
+// signatures exactly as in the YAML entries
+using TensorPtr = std::shared_ptr<Tensor>;
+template <typename R, typename... A> R CallFunctor(const char* name, A... a) {
+  return std::any_cast<const std::function<R(A...)>&>(FunctionLibraryStore().at(name))(a...);
+}
+using OptTensor = Optional<Tensor>;
+inline Maybe<Tensor> SpmmCsr(const TensorPtr& crow, const TensorPtr& col, const TensorPtr& val, const TensorPtr& b,
+                             const int64_t& rows, const int64_t& cols, const OptTensor& t_crow = OptTensor(),
+                             const OptTensor& t_col = OptTensor(), const OptTensor& t_perm = OptTensor()) {
+  return CallFunctor<Maybe<Tensor>, const TensorPtr&, const TensorPtr&, const TensorPtr&, const TensorPtr&, const int64_t&,
+                     const int64_t&, const OptTensor&, const OptTensor&, const OptTensor&>("SpmmCsr", crow, col, val, b, rows,
+                                                                                          cols, t_crow, t_col, t_perm);
+}
+inline Maybe<Tensor> SpmmCsrGradB(const TensorPtr& crow, const TensorPtr& col, const TensorPtr& val, const TensorPtr& dy,
+                                  const int64_t& rows, const int64_t& cols, const OptTensor& t_crow, const OptTensor& t_col,
+                                  const OptTensor& t_perm, const bool& atomic) {
+  return CallFunctor<Maybe<Tensor>, const TensorPtr&, const TensorPtr&, const TensorPtr&, const TensorPtr&, const int64_t&,
+                     const int64_t&, const OptTensor&, const OptTensor&, const OptTensor&, const bool&>(
+      "SpmmCsrGradB", crow, col, val, dy, rows, cols, t_crow, t_col, t_perm, atomic);
+}
+inline Maybe<Tensor> SddmmCsr(const TensorPtr& crow, const TensorPtr& col, const TensorPtr& dy, const TensorPtr& b,
+                              const int64_t& rows, const int64_t& cols, const DataType& val_dtype) {
+  return CallFunctor<Maybe<Tensor>, const TensorPtr&, const TensorPtr&, const TensorPtr&, const TensorPtr&, const int64_t&,
+                     const int64_t&, const DataType&>("SddmmCsr", crow, col, dy, b, rows, cols, val_dtype);
+}
+inline Maybe<TensorTuple> CsrTransposeStructure(const TensorPtr& crow, const TensorPtr& col, const int64_t& rows,
+                                                const int64_t& cols) {
+  return CallFunctor<Maybe<TensorTuple>, const TensorPtr&, const TensorPtr&, const int64_t&, const int64_t&>(
+      "CsrTransposeStructure", crow, col, rows, cols);
+}
 }  // namespace functional
 }  // namespace one
 }  // namespace oneflow

@@ -149,11 +149,16 @@ class InferContext {
   virtual void SetOutputShape(const std::string&, int32_t, const Shape&) = 0;
   virtual DataType InputDType(const std::string&, int32_t) const = 0;
   virtual void SetOutputDType(const std::string&, int32_t, DataType) = 0;
+  virtual bool has_input(const std::string& arg_name, int32_t index) const = 0;   // infer_util.h:71
   template <typename T> const T& Attr(const std::string& name) const;
  protected:
   virtual const int64_t& AttrInt64(const std::string& name) const = 0;
+  virtual const bool& AttrBool(const std::string& name) const = 0;
+  virtual const DataType& AttrDataType(const std::string& name) const = 0;
 };
 template <> inline const int64_t& InferContext::Attr<int64_t>(const std::string& name) const { return AttrInt64(name); }
+template <> inline const bool& InferContext::Attr<bool>(const std::string& name) const { return AttrBool(name); }
+template <> inline const DataType& InferContext::Attr<DataType>(const std::string& name) const { return AttrDataType(name); }
 
 // oneflow/core/framework/sbp_context.h (UserOpSbpSignatureBuilder)
 class SbpSignatureBuilder {
@@ -198,11 +203,14 @@ class KernelComputeContext {
   virtual ~KernelComputeContext() = default;
   virtual Tensor* Tensor4ArgNameAndIndex(const std::string&, int32_t) = 0;
   virtual ep::Stream* stream() = 0;
+  virtual bool has_input(const std::string& arg_name, int32_t index) const = 0;   // op_kernel.h:120-122
   template <typename T> const T& Attr(const std::string& name) const;
  protected:
   virtual const int64_t& AttrInt64(const std::string& name) const = 0;
+  virtual const bool& AttrBool(const std::string& name) const = 0;
 };
 template <> inline const int64_t& KernelComputeContext::Attr<int64_t>(const std::string& name) const { return AttrInt64(name); }
+template <> inline const bool& KernelComputeContext::Attr<bool>(const std::string& name) const { return AttrBool(name); }
 
 class OpKernel {
  public:

@@ -15,5 +15,6 @@ namespace oneflow {
 OF_MOCK_DECLARE_OP(SpmmCsrOp)
 OF_MOCK_DECLARE_OP(SpmmCsrGradBOp)
 OF_MOCK_DECLARE_OP(SddmmCsrOp)
+OF_MOCK_DECLARE_OP(CsrTransposeStructureOp)
 #undef OF_MOCK_DECLARE_OP
 }  // namespace oneflow

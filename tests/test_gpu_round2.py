@@ -378,3 +378,55 @@ def test_full_size_rmat24_properties():
     assert A.rows == 1 << 24 and A.nnz > 250_000_000
     assert int(A.row_lengths().max()) > 100_000
     _full_size_properties(A, 128, torch.float32, "cfg4")
+
+
+# ------------------------------------------------------------------ fp32 running sums for multi-pass bf16 products
+
+@pytest.mark.parametrize("N", [64, 256, 264])
+def test_bf16_multi_pass_with_fp32_accumulator_rounds_once(N):
+    """Three column buckets, bf16 in / bf16 out, running sums in the fp32 buffer: the result must meet
+    the SINGLE-pass bf16 tolerance (one rounding), hub rows stitched by the fix-up kernel included."""
+    A = graphs.rmat_csr(12, 16, seed=4)
+    B = graphs.dense_operand(A.cols, N, 7).to(torch.bfloat16)
+    crow_np, col_np, val_np = A.crow.numpy(), A.col.numpy(), A.val.numpy()
+    C64 = O.spmm_f64(crow_np, col_np, val_np, B.float().numpy(), A.cols)
+    amax = O.spmm_absmax(crow_np, col_np, val_np, B.float().numpy(), A.cols)
+    crow = A.crow.long()
+    rows_of = torch.repeat_interleave(torch.arange(A.rows), crow[1:] - crow[:-1])
+    cuts = [0, A.cols // 4, A.cols // 2, A.cols]
+    parts = []
+    for lo, hi in zip(cuts[:-1], cuts[1:]):
+        mask = (A.col >= lo) & (A.col < hi)
+        c = torch.zeros(A.rows + 1, dtype=torch.int32)
+        c[1:] = torch.bincount(rows_of[mask], minlength=A.rows).cumsum(0)
+        parts.append((c.to(DEV), A.col[mask].to(DEV), A.val[mask].to(DEV)))
+    Bd = B.to(DEV)
+    acc = torch.full((A.rows, N), float("nan"), dtype=torch.float32, device=DEV)
+    out = torch.full((A.rows, N), float("nan"), dtype=torch.bfloat16, device=DEV)
+    bias = (torch.arange(N, dtype=torch.float32) * 0.01 - 0.3).to(torch.bfloat16).to(DEV)
+    ops.spmm_csr_compute(*parts[0], Bd, A.rows, A.cols, out=out, acc32=acc, acc32_out=True)
+    ops.spmm_csr_compute(*parts[1], Bd, A.rows, A.cols, out=out, acc32=acc, acc32_in=True, acc32_out=True)
+    ops.spmm_csr_compute(*parts[2], Bd, A.rows, A.cols, out=out, acc32=acc, acc32_in=True, bias=bias, relu=True)
+    ref = np.maximum(C64 + bias.float().cpu().numpy().astype(np.float64)[None, :], 0.0)
+    got = out.float().cpu().numpy().astype(np.float64)
+    tol = 1e-2 * np.abs(ref) + 2.0 ** -8 * (amax + np.abs(bias.float().cpu().numpy())[None, :]) + 1e-30
+    assert (np.abs(got - ref) <= tol).all(), float((np.abs(got - ref) - tol).max())
+    # fp32 products must not take the acc32 route
+    with pytest.raises(ofs.OpInferError):
+        ops.spmm_csr_compute(*parts[0], Bd.float(), A.rows, A.cols, acc32=acc, acc32_out=True)
+
+
+def test_scatter_add_rows_into_fp32_then_cast_once():
+    g = torch.Generator().manual_seed(3)
+    K, n, cnt = 3000, 256, 900
+    acc = torch.randn(K, n, generator=g).to(DEV)
+    want = acc.clone()
+    for r in range(5):                                    # five "ranks" contribute bf16 partial rows
+        idx = torch.randperm(K, generator=g)[:cnt].sort().values.int().to(DEV)
+        part = torch.randn(cnt, n, generator=g).to(torch.bfloat16).to(DEV)
+        ops.scatter_add_rows_f32(acc, part, idx)
+        want[idx.long()] += part.float()
+    assert torch.equal(acc, want)                         # fp32 adds in the same order: exact
+    out = torch.empty((K, n), dtype=torch.bfloat16, device=DEV)
+    ops.cast_from_f32(out, acc)
+    assert torch.equal(out, want.to(torch.bfloat16))
