@@ -439,7 +439,7 @@ def main():
                     help="N>1: needed-rows pull over peer memory (default) or round 1's all-gather / reduce-scatter")
     ap.add_argument("--buckets", type=int, default=1, help="N>1, pull: remote column buckets (accumulate passes)")
     ap.add_argument("--tasks-per-warp", type=int, default=4, help="N>1: CTAs of the overlapped products retire after k tasks")
-    ap.add_argument("--pull-ctas", type=int, default=32, help="N>1, pull: grid cap of the peer-pull kernels")
+    ap.add_argument("--pull-ctas", type=int, default=64, help="N>1, pull: grid cap of the peer-pull kernels")
     args = ap.parse_args()
     args.warmup = max(3, args.warmup)
     if args.impl == "reference":

@@ -194,7 +194,7 @@ class ShardedSpmm:
     """Row-block-partitioned SpMM operator bound to one rank — needed-rows exchange over peer memory."""
 
     def __init__(self, A: CsrMatrix, n: int, dtype: torch.dtype, rank: int, world: int, device, *,
-                 buckets: int = 1, tasks_per_warp: int = 4, pull_ctas: int = 32, group=None,
+                 buckets: int = 1, tasks_per_warp: int = 4, pull_ctas: int = 64, group=None,
                  compute=None, transport: Optional[str] = None, shard_like_rows: bool = False, slots: int = 1):
         """``shard_like_rows`` (square A): shard B / dB by the SAME boundaries as the row blocks, so
         the output block of one product is the input shard of the next (GCN layers chain without a
