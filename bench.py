@@ -284,7 +284,9 @@ def verify_sample(A, B_full, dY_full, C_blk, r0, r1, dB_shard, s0, s1, dtype, ns
     want = O.spmm_f64(tcrow, inv.cpu().numpy(), tval, dYh, max(1, urow.numel()))
     amax = O.spmm_absmax(tcrow, inv.cpu().numpy(), tval, dYh, max(1, urow.numel()))
     got = dB_shard[(cols_s - s0)].float().cpu().numpy().astype(np.float64)
-    tol = (O.fp32_tolerance(want, amax, np.diff(tcrow)) + 2.0 ** -20 * np.abs(want)) if f32 else (1e-2 * np.abs(want) + 2.0 ** -5 * amax)
+    # bf16 on several ranks: each rank's partial column sum is rounded to bf16 for transport
+    tol = (O.fp32_tolerance(want, amax, np.diff(tcrow)) + 2.0 ** -20 * np.abs(want)) if f32 else \
+        (1e-2 * np.abs(want) + 2.0 ** -7 * amax * (1 + np.sqrt(np.diff(tcrow)))[:, None])
     res["dB_rows"] = int(cols_s.numel())
     res["dB_ok"] = bool((np.abs(got - want) <= tol + 1e-30).all())
     res["ok"] = res["C_ok"] and res["dB_ok"]
@@ -309,6 +311,7 @@ def _e2e_pipelined(args, ofs, ops, A, B, dY, n, dtype, dev, flops_step, blocks=8
     d = {k: torch.empty_like(v, device=dev) for k, v in host.items()}
     C_d = torch.empty((A.rows, n), dtype=dtype, device=dev)
     dB_d = torch.empty((A.cols, n), dtype=dtype, device=dev)
+    per_block_bwd = dtype == torch.float32   # fp32: dB accumulates block by block; bf16: one pass at the end
     bounds = ofs.row_blocks(host["crow"], A.nnz, blocks).tolist()      # host twin of the partitioner
     offs = [int(host["crow"][r]) for r in bounds]
     s_in, s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
@@ -340,9 +343,12 @@ def _e2e_pipelined(args, ofs, ops, A, B, dY, n, dtype, dev, flops_step, blocks=8
                 e = torch.cuda.Event()
                 e.record(cur)
                 ev_c.append((e, r0, r1))
-                t = ops.csr_transpose(crow_blk, col_blk, val_blk, r1 - r0, A.cols)
-                ops.spmm_csr_compute(t[0], t[1], t[2], d["dY"][r0:r1], A.cols, r1 - r0, out=dB_d, accumulate=not first)
-                first = False
+                if per_block_bwd:
+                    t = ops.csr_transpose(crow_blk, col_blk, val_blk, r1 - r0, A.cols)
+                    ops.spmm_csr_compute(t[0], t[1], t[2], d["dY"][r0:r1], A.cols, r1 - r0, out=dB_d, accumulate=not first)
+                    first = False
+        if not per_block_bwd:   # 16-bit outputs: one pass over the whole A^T, a single rounding
+            ops.spmm_csr_grad_b_transient_compute(d["crow"], d["col"], d["val"], d["dY"], A.rows, A.cols, out=dB_d)
         ev_b = torch.cuda.Event()
         ev_b.record(cur)
         with torch.cuda.stream(s_out):

@@ -122,7 +122,9 @@ typedef struct ofspmm_opts {
                              kernel on another stream (a collective, the peer pull) gets SMs while
                              this one runs                                                          */
   int32_t variant;        /* OFSPMM_VARIANT_AUTO or a code from ofspmm_choose_variant               */
-  int32_t reserved;
+  int32_t reserve_ctas_per_sm; /* persistent grid of (occupancy - r) CTAs per SM: every SM keeps r CTA
+                             slots (128 threads, <= 64 registers each) free for the 128-thread
+                             exchange kernels that overlap this product (pull / combine / signal)   */
   const void* plan;       /* device plan from ofspmm_plan_build for THIS (crow, variant); NULL: the
                              partition is recomputed inside the call                                */
   size_t plan_bytes;
@@ -277,6 +279,37 @@ OFSPMM_API int ofspmm_scatter_add_rows(void* dst, int64_t ld_dst, const void* sr
                                        int64_t count, int64_t n, int dense_dtype, int max_ctas,
                                        ofspmm_stream_t stream);
 
+/* ---- Flag-synchronised multi-peer exchange: one launch for all peers, inter-rank ordering inside
+ * the kernel.  Each rank owns a signal pad in symmetric memory; after publishing its data for
+ * epoch e it writes e into its slot of every peer's pad (ofspmm_signal_peers, st.release.sys); a
+ * consumer block spins on the flag of the segment it is about to read (ld.acquire.sys).  The
+ * caller double-buffers the published data by epoch parity, so no "done reading" handshake exists.
+ * ONE rank per GPU: kernels of different ranks wait on one another.
+ *   pull:    dst[seg.dst_row + i, :] = seg.src[seg.list[i], :]          for every segment, in order
+ *   combine: acc[r, :] += seg.src[seg.inv[r], :]  where seg.inv[r] >= 0, segments in the given
+ *            (= rank) order: a fixed summation order; acc is fp32 (rounded once by the caller for
+ *            16-bit operands, ofspmm_cast_from_f32). */
+typedef struct ofspmm_pull_seg {
+  const void* src;   /* peer-mapped base of the owner's published shard                         */
+  const void* list;  /* device: rows wanted, relative to src (idx_dtype)                          */
+  const void* flag;  /* device, uint64: THIS rank's pad slot the owner writes its epoch to        */
+  int64_t count;
+  int64_t dst_row;
+} ofspmm_pull_seg;
+typedef struct ofspmm_combine_seg {
+  const void* src;   /* peer-mapped first row of the peer's partial rows for this rank's shard    */
+  const void* inv;   /* device int32[rows]: this rank's row -> row of src, or -1                   */
+  const void* flag;
+} ofspmm_combine_seg;
+OFSPMM_API int ofspmm_signal_peers(void* const* peer_slots, int n, uint64_t epoch, ofspmm_stream_t stream);
+OFSPMM_API int ofspmm_pull_rows_multi(void* dst, int64_t ld_dst, int64_t ld_src, const ofspmm_pull_seg* segs,
+                                      int nseg, uint64_t epoch, int64_t n, int dense_dtype, int idx_dtype,
+                                      int max_ctas, ofspmm_stream_t stream);
+OFSPMM_API int ofspmm_combine_rows_multi(float* acc, int64_t ld_acc, int64_t ld_src,
+                                         const ofspmm_combine_seg* segs, int nseg, uint64_t epoch,
+                                         int64_t rows, int64_t n, int src_dtype, int max_ctas,
+                                         ofspmm_stream_t stream);
+
 /* fp32-accumulator forms for 16-bit operands: the owner of a dB shard adds the peers' bf16 partial
  * rows into an fp32 buffer and rounds once at the end (ofspmm_cast_from_f32), instead of rounding
  * to bf16 after every rank's contribution. */
@@ -285,6 +318,28 @@ OFSPMM_API int ofspmm_scatter_add_rows_f32(float* dst, int64_t ld_dst, const voi
                                            int64_t count, int64_t n, int src_dtype, int max_ctas,
                                            ofspmm_stream_t stream);
 OFSPMM_API int ofspmm_cast_from_f32(const float* src, void* dst, int64_t count, int dst_dtype,
+                                    ofspmm_stream_t stream);
+
+/* ---- Graph construction on the device: the step before the path.
+ * COO -> CSR: `row`, `col` int64 edge endpoints, `val` fp32 (NULL: all ones), nnz_in entries in any
+ * order with duplicates.  Duplicates are merged in edge-list order — coalesce 0: sum (Graph500 /
+ * scipy convention), 1: max, 2: first — and entries outside rows x cols are dropped.  Outputs:
+ * crow[rows+1], col_out / val_out sized for nnz_in (only the first counts[0] entries are written),
+ * columns sorted and unique within a row; counts[0] = nnz of the CSR, counts[1] = dropped entries
+ * (device int64[2], may be NULL).  The caller reads counts[0] after synchronising. */
+OFSPMM_API size_t ofspmm_coo_to_csr_workspace_bytes(int64_t nnz_in, int64_t rows, int64_t cols);
+OFSPMM_API int ofspmm_coo_to_csr(const int64_t* row, const int64_t* col, const float* val, int64_t nnz_in,
+                                 int64_t rows, int64_t cols, int coalesce, int idx_dtype, void* crow,
+                                 void* col_out, float* val_out, int64_t* counts, void* workspace,
+                                 size_t workspace_bytes, ofspmm_stream_t stream);
+/* row_of_nnz[p] = row of stored entry p (CSR -> COO rows). */
+OFSPMM_API int ofspmm_csr_expand_rows(const void* crow, int idx_dtype, int64_t rows, int64_t* row_of_nnz,
+                                      ofspmm_stream_t stream);
+/* In-place normalisation of fp32 values with D = diag(row sums of |A|): mode 0: D^-1/2 A D^-1/2
+ * (square A, the GCN propagation matrix), mode 1: D^-1 A.  dinv_rows: `rows` floats of scratch
+ * (holds the per-row scale afterwards). */
+OFSPMM_API int ofspmm_csr_normalize(const void* crow, const void* col, float* val, int idx_dtype,
+                                    int64_t rows, int64_t cols, int mode, float* dinv_rows,
                                     ofspmm_stream_t stream);
 
 /* ---- Host-buffer convenience entry (what a CPU-tensor caller / the e2e benchmark uses): copies

@@ -25,7 +25,8 @@ EXPORTS = (
     "ofspmm_fwd_ex_workspace_bytes", "ofspmm_fwd_ex", "ofspmm_plan_bytes", "ofspmm_plan_build",
     "ofspmm_choose_variant", "ofspmm_bwd_b_cached_workspace_bytes", "ofspmm_bwd_b_cached", "ofspmm_sddmm_ex",
     "ofspmm_gather_rows", "ofspmm_scatter_add_rows", "ofspmm_permute_values", "ofspmm_scatter_add_rows_f32",
-    "ofspmm_cast_from_f32",
+    "ofspmm_cast_from_f32", "ofspmm_coo_to_csr_workspace_bytes", "ofspmm_coo_to_csr", "ofspmm_csr_expand_rows",
+    "ofspmm_csr_normalize", "ofspmm_signal_peers", "ofspmm_pull_rows_multi", "ofspmm_combine_rows_multi",
 )
 
 # ofspmm_opts.flags / variant codes (include/ofspmm.h)
@@ -51,10 +52,21 @@ class CsrStruct(ctypes.Structure):
                 ("idx_dtype", ctypes.c_int32), ("val_dtype", ctypes.c_int32)]
 
 
+class PullSeg(ctypes.Structure):
+    """struct ofspmm_pull_seg."""
+    _fields_ = [("src", ctypes.c_void_p), ("list", ctypes.c_void_p), ("flag", ctypes.c_void_p),
+                ("count", ctypes.c_int64), ("dst_row", ctypes.c_int64)]
+
+
+class CombineSeg(ctypes.Structure):
+    """struct ofspmm_combine_seg."""
+    _fields_ = [("src", ctypes.c_void_p), ("inv", ctypes.c_void_p), ("flag", ctypes.c_void_p)]
+
+
 class OptsStruct(ctypes.Structure):
     """struct ofspmm_opts (include/ofspmm.h)."""
     _fields_ = [("flags", ctypes.c_uint32), ("tasks_per_warp", ctypes.c_int32), ("variant", ctypes.c_int32),
-                ("reserved", ctypes.c_int32), ("plan", ctypes.c_void_p), ("plan_bytes", ctypes.c_size_t),
+                ("reserve_ctas_per_sm", ctypes.c_int32), ("plan", ctypes.c_void_p), ("plan_bytes", ctypes.c_size_t),
                 ("bias", ctypes.c_void_p), ("acc32", ctypes.c_void_p)]
 
 
@@ -136,6 +148,20 @@ def lib() -> ctypes.CDLL:
     L.ofspmm_scatter_add_rows_f32.restype = i32
     L.ofspmm_cast_from_f32.argtypes = [vp, vp, i64, i32, vp]
     L.ofspmm_cast_from_f32.restype = i32
+    L.ofspmm_coo_to_csr_workspace_bytes.argtypes = [i64, i64, i64]
+    L.ofspmm_coo_to_csr_workspace_bytes.restype = sz
+    L.ofspmm_coo_to_csr.argtypes = [vp, vp, vp, i64, i64, i64, i32, i32, vp, vp, vp, vp, vp, sz, vp]
+    L.ofspmm_coo_to_csr.restype = i32
+    L.ofspmm_csr_expand_rows.argtypes = [vp, i32, i64, vp, vp]
+    L.ofspmm_csr_expand_rows.restype = i32
+    L.ofspmm_csr_normalize.argtypes = [vp, vp, vp, i32, i64, i64, i32, vp, vp]
+    L.ofspmm_csr_normalize.restype = i32
+    L.ofspmm_signal_peers.argtypes = [ctypes.POINTER(ctypes.c_void_p), i32, ctypes.c_uint64, vp]
+    L.ofspmm_signal_peers.restype = i32
+    L.ofspmm_pull_rows_multi.argtypes = [vp, i64, i64, ctypes.POINTER(PullSeg), i32, ctypes.c_uint64, i64, i32, i32, i32, vp]
+    L.ofspmm_pull_rows_multi.restype = i32
+    L.ofspmm_combine_rows_multi.argtypes = [vp, i64, i64, ctypes.POINTER(CombineSeg), i32, ctypes.c_uint64, i64, i64, i32, i32, vp]
+    L.ofspmm_combine_rows_multi.restype = i32
     L.ofspmm_permute_values.argtypes = [vp, i32, vp, i32, i64, vp, vp]
     L.ofspmm_permute_values.restype = i32
     L.ofspmm_gather_rows.argtypes = [vp, i64, vp, i64, vp, i32, i64, i64, i64, i32, i32, vp]

@@ -90,6 +90,7 @@ FwdLaunch make_launch(const ofspmm_opts* opts, int64_t rows, int64_t nnz, int64_
   FwdLaunch L;
   L.variant = resolve_variant(opts ? opts->variant : OFSPMM_VARIANT_AUTO, rows, nnz, n, dense_dtype);
   L.tasks_per_warp = opts && opts->tasks_per_warp > 0 ? opts->tasks_per_warp : 0;
+  L.reserve_ctas = opts && opts->reserve_ctas_per_sm > 0 ? opts->reserve_ctas_per_sm : 0;
   const uint32_t fl = opts ? opts->flags : 0u;
   // task order: dynamic (drawn from a counter) unless the caller pins the static interleave
   L.dynamic = OFSPMM_DEFAULT_DYNAMIC_ORDER ? (fl & OFSPMM_ORDER_STATIC) == 0 : (fl & OFSPMM_ORDER_DYNAMIC) != 0;
@@ -347,6 +348,39 @@ int ofspmm_bwd_b_cached(const ofspmm_csr* A, const void* t_crow, const void* t_c
   return run_fwd(&At, dY, n, dB, n, n, dense_dtype, opts, w + tv_bytes, workspace_bytes - tv_bytes, stream);
 }
 
+size_t ofspmm_coo_to_csr_workspace_bytes(int64_t nnz_in, int64_t rows, int64_t cols) {
+  if (nnz_in < 0 || rows < 0 || cols < 0) return 0;
+  return coo_to_csr_workspace_bytes(nnz_in, rows, cols);
+}
+
+int ofspmm_coo_to_csr(const int64_t* row, const int64_t* col, const float* val, int64_t nnz_in, int64_t rows, int64_t cols,
+                      int coalesce, int idx_dtype, void* crow, void* col_out, float* val_out, int64_t* counts,
+                      void* workspace, size_t workspace_bytes, ofspmm_stream_t stream) {
+  if (nnz_in < 0 || rows < 0 || cols < 0 || coalesce < 0 || coalesce > 2) return OFSPMM_ERR_INVALID_ARG;
+  if (crow == nullptr || (nnz_in > 0 && (row == nullptr || col == nullptr || col_out == nullptr || val_out == nullptr)))
+    return OFSPMM_ERR_INVALID_ARG;
+  if (!idx_ok(idx_dtype)) return OFSPMM_ERR_UNSUPPORTED_DTYPE;
+  if (nnz_in >= (int64_t{1} << 31) - 1) return OFSPMM_ERR_TOO_LARGE;
+  if (rows > 0 && cols > 0 && rows > ((int64_t{1} << 62) / cols)) return OFSPMM_ERR_TOO_LARGE;   // row*cols+col must fit
+  return launch_coo_to_csr(row, col, val, nnz_in, rows, cols, coalesce, idx_dtype, crow, col_out, val_out, counts, workspace,
+                           workspace_bytes, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int ofspmm_csr_expand_rows(const void* crow, int idx_dtype, int64_t rows, int64_t* row_of_nnz, ofspmm_stream_t stream) {
+  if (rows < 0 || crow == nullptr || (rows > 0 && row_of_nnz == nullptr)) return OFSPMM_ERR_INVALID_ARG;
+  if (!idx_ok(idx_dtype)) return OFSPMM_ERR_UNSUPPORTED_DTYPE;
+  return launch_expand_rows(crow, idx_dtype, rows, row_of_nnz, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int ofspmm_csr_normalize(const void* crow, const void* col, float* val, int idx_dtype, int64_t rows, int64_t cols, int mode,
+                         float* dinv_rows, ofspmm_stream_t stream) {
+  if (rows < 0 || cols < 0 || crow == nullptr || (mode != 0 && mode != 1)) return OFSPMM_ERR_INVALID_ARG;
+  if (rows > 0 && dinv_rows == nullptr) return OFSPMM_ERR_WORKSPACE;
+  if (mode == 0 && rows != cols) return OFSPMM_ERR_INVALID_ARG;   // D^-1/2 A D^-1/2 needs a square matrix
+  if (!idx_ok(idx_dtype)) return OFSPMM_ERR_UNSUPPORTED_DTYPE;
+  return launch_csr_normalize(crow, col, val, idx_dtype, rows, cols, mode, dinv_rows, reinterpret_cast<cudaStream_t>(stream));
+}
+
 int ofspmm_permute_values(const void* val, int val_dtype, const void* perm, int idx_dtype, int64_t nnz, void* out,
                           ofspmm_stream_t stream) {
   if (nnz < 0) return OFSPMM_ERR_INVALID_ARG;
@@ -363,6 +397,31 @@ int ofspmm_gather_rows(void* dst, int64_t ld_dst, const void* src, int64_t ld_sr
   if (list != nullptr && !idx_ok(idx_dtype)) return OFSPMM_ERR_UNSUPPORTED_DTYPE;
   return launch_gather_rows(dst, ld_dst, src, ld_src, list, list ? idx_dtype : OFSPMM_DTYPE_INT32, idx_offset, count, n,
                             dense_dtype, max_ctas, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int ofspmm_signal_peers(void* const* peer_slots, int n, uint64_t epoch, ofspmm_stream_t stream) {
+  if (n < 0 || (n > 0 && peer_slots == nullptr)) return OFSPMM_ERR_INVALID_ARG;
+  for (int i = 0; i < n; ++i)
+    if (peer_slots[i] == nullptr) return OFSPMM_ERR_INVALID_ARG;
+  return launch_signal_peers(peer_slots, n, epoch, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int ofspmm_pull_rows_multi(void* dst, int64_t ld_dst, int64_t ld_src, const ofspmm_pull_seg* segs, int nseg,
+                           uint64_t epoch, int64_t n, int dense_dtype, int idx_dtype, int max_ctas,
+                           ofspmm_stream_t stream) {
+  if (n < 0 || ld_dst < n || ld_src < n || nseg < 0 || (nseg > 0 && (segs == nullptr || dst == nullptr)))
+    return OFSPMM_ERR_INVALID_ARG;
+  return launch_pull_rows_multi(dst, ld_dst, ld_src, segs, nseg, epoch, n, dense_dtype, idx_dtype, max_ctas,
+                                reinterpret_cast<cudaStream_t>(stream));
+}
+
+int ofspmm_combine_rows_multi(float* acc, int64_t ld_acc, int64_t ld_src, const ofspmm_combine_seg* segs, int nseg,
+                              uint64_t epoch, int64_t rows, int64_t n, int src_dtype, int max_ctas,
+                              ofspmm_stream_t stream) {
+  if (n < 0 || rows < 0 || ld_acc < n || ld_src < n || nseg < 0 || (nseg > 0 && (segs == nullptr || acc == nullptr)))
+    return OFSPMM_ERR_INVALID_ARG;
+  return launch_combine_rows_multi(acc, ld_acc, ld_src, segs, nseg, epoch, rows, n, src_dtype, max_ctas,
+                                   reinterpret_cast<cudaStream_t>(stream));
 }
 
 int ofspmm_scatter_add_rows_f32(float* dst, int64_t ld_dst, const void* src, int64_t ld_src, const void* list,

@@ -191,6 +191,138 @@ __global__ void cast_rows_from_f32_kernel(const float* __restrict__ in, DT* __re
     out[i] = from_float<DT>(in[i]);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Flag-synchronised multi-peer kernels: ONE launch pulls from (or combines the partials of) every
+// peer, and the inter-rank ordering lives inside the kernel — each source segment is guarded by an
+// epoch flag its owner writes into THIS rank's signal pad (st.release.sys over NVLink) after its
+// data is complete; a block spins (ld.acquire.sys + nanosleep) on the flag of the segment it is
+// about to read.  No host barrier, no collective, no per-peer launch: at 8 ranks a forward is
+// publish + signal + pull + two products, whatever the number of peers.  Buffers are double
+// buffered by epoch parity by the caller, so no "done reading" handshake is needed (dist.py).
+// One rank per GPU only: kernels of different ranks wait on one another (B200_PROFILING.md).
+
+struct PullSeg {
+  const char* src;          // peer buffer (row 0 of the peer's published shard)
+  const void* list;         // rows wanted from it (device, IdxT), relative to `src`
+  const unsigned long long* flag;   // this rank's pad slot the owner of `src` writes its epoch to
+  long long count;          // rows
+  long long dst_row;        // first destination row of the segment
+};
+constexpr int kMaxSegs = 16;
+struct PullArgs {
+  PullSeg seg[kMaxSegs];
+  int nseg;
+};
+
+__device__ __forceinline__ void wait_flag(const unsigned long long* flag, unsigned long long epoch) {
+  if (threadIdx.x == 0) {
+    unsigned long long v;
+    for (;;) {
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flag) : "memory");
+      if (v >= epoch) break;
+      __nanosleep(200);
+    }
+  }
+  __syncthreads();
+}
+
+constexpr int kPullThreads = 128;   // fits the CTA slot the overlapped product leaves free per SM
+
+template <typename IdxT>
+__global__ void __launch_bounds__(kPullThreads) pull_rows_multi_kernel(char* __restrict__ dst, long long dst_stride,
+                                                                      long long src_stride, const PullArgs a,
+                                                                      unsigned long long epoch, int units) {
+  for (int s = 0; s < a.nseg; ++s) {
+    const PullSeg sg = a.seg[s];
+    if (sg.count == 0) continue;
+    wait_flag(sg.flag, epoch);
+    const IdxT* list = static_cast<const IdxT*>(sg.list);
+    const long long total = sg.count * units;
+    const long long stride = static_cast<long long>(gridDim.x) * kPullThreads;
+    long long u = static_cast<long long>(blockIdx.x) * kPullThreads + threadIdx.x;
+    for (; u + (kUnroll - 1) * stride < total; u += kUnroll * stride) {
+      uint4 v[kUnroll];
+      long long drow[kUnroll];
+      int c[kUnroll];
+#pragma unroll
+      for (int k = 0; k < kUnroll; ++k) {
+        const long long uu = u + k * stride;
+        drow[k] = uu / units;
+        c[k] = static_cast<int>(uu - drow[k] * units);
+        v[k] = ld_peer16(sg.src + static_cast<long long>(list[drow[k]]) * src_stride + c[k] * 16);
+      }
+#pragma unroll
+      for (int k = 0; k < kUnroll; ++k)
+        *reinterpret_cast<uint4*>(dst + (sg.dst_row + drow[k]) * dst_stride + c[k] * 16) = v[k];
+    }
+    for (; u < total; u += stride) {
+      const long long r = u / units;
+      const int c = static_cast<int>(u - r * units);
+      *reinterpret_cast<uint4*>(dst + (sg.dst_row + r) * dst_stride + c * 16) =
+          ld_peer16(sg.src + static_cast<long long>(list[r]) * src_stride + c * 16);
+    }
+  }
+}
+
+struct CombineSeg {
+  const char* src;          // peer partial rows for this rank's shard (first row of the segment)
+  const int* inv;           // this rank's rows -> index into the segment, or -1 (device, int32[rows])
+  const unsigned long long* flag;
+};
+struct CombineArgs {
+  CombineSeg seg[kMaxSegs];
+  int nseg;
+};
+
+// acc[row, :] += sum over peers (in the order of `a.seg`, i.e. ascending rank: a fixed summation
+// order) of the peer's partial row, for the rows the peer holds.  One 16-byte unit of the source
+// dtype per thread; AccT = float for bf16 sources (rounded once by the caller), = source for fp32.
+template <typename SrcT>
+__global__ void __launch_bounds__(kPullThreads) combine_rows_multi_kernel(float* __restrict__ acc, long long ld_acc,
+                                                                         long long src_stride, const CombineArgs a,
+                                                                         unsigned long long epoch, long long rows, int units) {
+  constexpr int kPer = 16 / sizeof(SrcT);   // values per 16-byte unit: 4 fp32 or 8 bf16
+  for (int s = 0; s < a.nseg; ++s) {
+    const CombineSeg sg = a.seg[s];
+    wait_flag(sg.flag, epoch);
+    const long long total = rows * units;
+    const long long stride = static_cast<long long>(gridDim.x) * kPullThreads;
+    for (long long u = static_cast<long long>(blockIdx.x) * kPullThreads + threadIdx.x; u < total; u += stride) {
+      const long long r = u / units;
+      const int j = sg.inv[r];
+      if (j < 0) continue;
+      const int c = static_cast<int>(u - r * units);
+      const uint4 v = ld_peer16(sg.src + static_cast<long long>(j) * src_stride + c * 16);
+      float* d = acc + r * ld_acc + c * kPer;
+      if constexpr (sizeof(SrcT) == 4) {
+        float4 x = *reinterpret_cast<float4*>(d);
+        x.x += __uint_as_float(v.x); x.y += __uint_as_float(v.y); x.z += __uint_as_float(v.z); x.w += __uint_as_float(v.w);
+        *reinterpret_cast<float4*>(d) = x;
+      } else {
+        float4 x = reinterpret_cast<float4*>(d)[0], y = reinterpret_cast<float4*>(d)[1];
+        x.x += __uint_as_float(v.x << 16); x.y += __uint_as_float(v.x & 0xffff0000u);
+        x.z += __uint_as_float(v.y << 16); x.w += __uint_as_float(v.y & 0xffff0000u);
+        y.x += __uint_as_float(v.z << 16); y.y += __uint_as_float(v.z & 0xffff0000u);
+        y.z += __uint_as_float(v.w << 16); y.w += __uint_as_float(v.w & 0xffff0000u);
+        reinterpret_cast<float4*>(d)[0] = x;
+        reinterpret_cast<float4*>(d)[1] = y;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+struct SignalArgs {
+  unsigned long long* slot[kMaxSegs];   // per peer: where this rank's epoch goes in the peer's pad
+  int n;
+};
+// After everything earlier on the stream (the publish of this rank's data): tell every peer.
+__global__ void signal_peers_kernel(const SignalArgs a, unsigned long long epoch) {
+  __threadfence_system();
+  const int i = threadIdx.x;
+  if (i < a.n) asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(a.slot[i]), "l"(epoch) : "memory");
+}
+
 template <typename IdxT, typename ValT>
 __global__ void gather_vals_kernel(const ValT* __restrict__ val, const IdxT* __restrict__ perm, long long nnz,
                                    ValT* __restrict__ out) {
@@ -305,6 +437,90 @@ int launch_cast_from_f32(const float* src, void* dst, int64_t count, int dst_dty
   } else {
     return OFSPMM_ERR_UNSUPPORTED_DTYPE;
   }
+  count_launch();
+  OFSPMM_CUDA_OK(cudaGetLastError());
+  return OFSPMM_OK;
+}
+
+int launch_signal_peers(void* const* slots, int n, unsigned long long epoch, cudaStream_t stream) {
+  if (n < 0 || n > kMaxSegs) return OFSPMM_ERR_INVALID_ARG;
+  if (n == 0) return OFSPMM_OK;
+  SignalArgs a;
+  a.n = n;
+  for (int i = 0; i < n; ++i) a.slot[i] = static_cast<unsigned long long*>(slots[i]);
+  signal_peers_kernel<<<1, 32, 0, stream>>>(a, epoch);
+  count_launch();
+  OFSPMM_CUDA_OK(cudaGetLastError());
+  return OFSPMM_OK;
+}
+
+int launch_pull_rows_multi(void* dst, int64_t ld_dst, int64_t ld_src, const ofspmm_pull_seg* segs, int nseg,
+                           unsigned long long epoch, int64_t n, int dense_dtype, int idx_dtype, int max_ctas,
+                           cudaStream_t stream) {
+  if (nseg < 0 || nseg > kMaxSegs) return OFSPMM_ERR_INVALID_ARG;
+  const size_t es = dense_dtype == OFSPMM_DTYPE_FLOAT ? 4 : 2;
+  if (dense_dtype != OFSPMM_DTYPE_FLOAT && dense_dtype != OFSPMM_DTYPE_BFLOAT16) return OFSPMM_ERR_UNSUPPORTED_DTYPE;
+  if ((n * es) % 16 != 0 || (ld_dst * es) % 16 != 0 || (ld_src * es) % 16 != 0 || (reinterpret_cast<uintptr_t>(dst) & 15))
+    return OFSPMM_ERR_INVALID_ARG;   // the multi-peer path moves whole 16-byte units
+  PullArgs a;
+  a.nseg = nseg;
+  long long rows = 0;
+  for (int i = 0; i < nseg; ++i) {
+    if (segs[i].count < 0 || (segs[i].count > 0 && (segs[i].src == nullptr || segs[i].list == nullptr || segs[i].flag == nullptr)))
+      return OFSPMM_ERR_INVALID_ARG;
+    if (reinterpret_cast<uintptr_t>(segs[i].src) & 15) return OFSPMM_ERR_INVALID_ARG;
+    a.seg[i].src = static_cast<const char*>(segs[i].src);
+    a.seg[i].list = segs[i].list;
+    a.seg[i].flag = static_cast<const unsigned long long*>(segs[i].flag);
+    a.seg[i].count = segs[i].count;
+    a.seg[i].dst_row = segs[i].dst_row;
+    rows += segs[i].count;
+  }
+  if (rows == 0 || n == 0) return OFSPMM_OK;
+  DevInfo dev;
+  if (int rc = get_dev_info(&dev)) return rc;
+  const int units = static_cast<int>(n * es / 16);
+  int grid = max_ctas > 0 ? max_ctas : dev.sms;
+  const long long need = (rows * units + kPullThreads * kUnroll - 1) / (kPullThreads * kUnroll);
+  if (grid > need) grid = static_cast<int>(need < 1 ? 1 : need);
+  if (idx_dtype == OFSPMM_DTYPE_INT32)
+    pull_rows_multi_kernel<int32_t><<<grid, kPullThreads, 0, stream>>>(static_cast<char*>(dst), ld_dst * es, ld_src * es, a, epoch, units);
+  else if (idx_dtype == OFSPMM_DTYPE_INT64)
+    pull_rows_multi_kernel<int64_t><<<grid, kPullThreads, 0, stream>>>(static_cast<char*>(dst), ld_dst * es, ld_src * es, a, epoch, units);
+  else
+    return OFSPMM_ERR_UNSUPPORTED_DTYPE;
+  count_launch();
+  OFSPMM_CUDA_OK(cudaGetLastError());
+  return OFSPMM_OK;
+}
+
+int launch_combine_rows_multi(float* acc, int64_t ld_acc, int64_t ld_src, const ofspmm_combine_seg* segs, int nseg,
+                              unsigned long long epoch, int64_t rows, int64_t n, int src_dtype, int max_ctas,
+                              cudaStream_t stream) {
+  if (nseg < 0 || nseg > kMaxSegs) return OFSPMM_ERR_INVALID_ARG;
+  if (src_dtype != OFSPMM_DTYPE_FLOAT && src_dtype != OFSPMM_DTYPE_BFLOAT16) return OFSPMM_ERR_UNSUPPORTED_DTYPE;
+  const size_t es = src_dtype == OFSPMM_DTYPE_FLOAT ? 4 : 2;
+  if ((n * es) % 16 != 0 || (ld_src * es) % 16 != 0 || ld_acc % 8 != 0 || (reinterpret_cast<uintptr_t>(acc) & 31))
+    return OFSPMM_ERR_INVALID_ARG;
+  if (nseg == 0 || rows == 0 || n == 0) return OFSPMM_OK;
+  CombineArgs a;
+  a.nseg = nseg;
+  for (int i = 0; i < nseg; ++i) {
+    if (segs[i].src == nullptr || segs[i].inv == nullptr || segs[i].flag == nullptr) return OFSPMM_ERR_INVALID_ARG;
+    a.seg[i].src = static_cast<const char*>(segs[i].src);
+    a.seg[i].inv = static_cast<const int*>(segs[i].inv);
+    a.seg[i].flag = static_cast<const unsigned long long*>(segs[i].flag);
+  }
+  DevInfo dev;
+  if (int rc = get_dev_info(&dev)) return rc;
+  const int units = static_cast<int>(n * es / 16);
+  int grid = max_ctas > 0 ? max_ctas : dev.sms * 4;
+  const long long need = (rows * units + kPullThreads - 1) / kPullThreads;
+  if (grid > need) grid = static_cast<int>(need < 1 ? 1 : need);
+  if (src_dtype == OFSPMM_DTYPE_FLOAT)
+    combine_rows_multi_kernel<float><<<grid, kPullThreads, 0, stream>>>(acc, ld_acc, ld_src * es, a, epoch, rows, units);
+  else
+    combine_rows_multi_kernel<__nv_bfloat16><<<grid, kPullThreads, 0, stream>>>(acc, ld_acc, ld_src * es, a, epoch, rows, units);
   count_launch();
   OFSPMM_CUDA_OK(cudaGetLastError());
   return OFSPMM_OK;

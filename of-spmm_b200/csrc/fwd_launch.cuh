@@ -31,7 +31,9 @@ int launch_full(FwdParams p, int panels, const FwdLaunch& L, cudaStream_t stream
   // persistent grid: a whole number of CTAs per SM (148 SMs on B200), never more than the tasks
   const int64_t ctas_needed = (static_cast<int64_t>(p.P) + WARPS - 1) / WARPS;
   const int64_t ctas_all = (static_cast<int64_t>(p.P) * panels + WARPS - 1) / WARPS;
-  const int64_t resident = static_cast<int64_t>(dev.sms) * occ;
+  // reserve_ctas: leave that many CTA slots per SM to the exchange kernels of the multi-GPU path
+  const int occ_used = L.reserve_ctas > 0 ? (occ - L.reserve_ctas > 1 ? occ - L.reserve_ctas : 1) : occ;
+  const int64_t resident = static_cast<int64_t>(dev.sms) * occ_used;
   int64_t gx64 = ctas_all < resident ? ctas_all : resident;
   // tasks_per_warp = k > 0 (ofspmm_opts): a non-persistent grid whose CTAs retire after k tasks
   // per warp, so kernels of another stream (NCCL collectives, the peer-pull kernel of the

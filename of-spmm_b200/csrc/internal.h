@@ -44,6 +44,7 @@ int encode_variant(const FwdVariant& v);
 struct FwdLaunch {
   FwdVariant variant;
   int tasks_per_warp;  // 0 = persistent grid
+  int reserve_ctas;    // CTA slots per SM a persistent grid leaves free for overlapping exchange kernels
   bool dynamic;        // tasks drawn from a global counter (persistent grid only)
   unsigned flags;      // kFwd* epilogue bits
   const void* bias;
@@ -92,6 +93,13 @@ size_t transpose_workspace_bytes(int64_t rows, int64_t cols, int64_t nnz, int id
 int launch_transpose(const ofspmm_csr* A, void* t_crow, void* t_col, void* t_val, void* t_perm,
                      void* ws, size_t ws_bytes, cudaStream_t stream);
 const char* fwd_variant_name(int64_t n, int dense_dtype, bool aligned);
+size_t coo_to_csr_workspace_bytes(int64_t n, int64_t rows, int64_t cols);
+int launch_coo_to_csr(const int64_t* row, const int64_t* col, const float* val, int64_t n, int64_t rows, int64_t cols,
+                      int mode, int idx_dtype, void* crow, void* col_out, float* val_out, int64_t* counts, void* ws,
+                      size_t ws_bytes, cudaStream_t stream);
+int launch_expand_rows(const void* crow, int idx_dtype, int64_t rows, int64_t* out, cudaStream_t stream);
+int launch_csr_normalize(const void* crow, const void* col, float* val, int idx_dtype, int64_t rows, int64_t cols, int mode,
+                         float* dinv, cudaStream_t stream);
 int launch_gather_vals(const void* val, int val_dtype, const void* perm, int idx_dtype, int64_t nnz,
                        void* out, cudaStream_t stream);
 int launch_gather_rows(void* dst, int64_t ld_dst, const void* src, int64_t ld_src, const void* list,
@@ -100,6 +108,13 @@ int launch_gather_rows(void* dst, int64_t ld_dst, const void* src, int64_t ld_sr
 int launch_scatter_add_rows_f32(float* dst, int64_t ld_dst, const void* src, int64_t ld_src, const void* list,
                                 int idx_dtype, int64_t idx_offset, int64_t count, int64_t n, int src_dtype,
                                 int max_ctas, cudaStream_t stream);
+int launch_signal_peers(void* const* slots, int n, unsigned long long epoch, cudaStream_t stream);
+int launch_pull_rows_multi(void* dst, int64_t ld_dst, int64_t ld_src, const ofspmm_pull_seg* segs, int nseg,
+                           unsigned long long epoch, int64_t n, int dense_dtype, int idx_dtype, int max_ctas,
+                           cudaStream_t stream);
+int launch_combine_rows_multi(float* acc, int64_t ld_acc, int64_t ld_src, const ofspmm_combine_seg* segs, int nseg,
+                              unsigned long long epoch, int64_t rows, int64_t n, int src_dtype, int max_ctas,
+                              cudaStream_t stream);
 int launch_cast_from_f32(const float* src, void* dst, int64_t count, int dst_dtype, cudaStream_t stream);
 int launch_scatter_add_rows(void* dst, int64_t ld_dst, const void* src, int64_t ld_src, const void* list,
                             int idx_dtype, int64_t idx_offset, int64_t count, int64_t n, int dense_dtype,

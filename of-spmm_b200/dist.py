@@ -60,14 +60,14 @@ class CudaCompute:
         return ops.SpmmPlan(crow, col, rows, cols, n, dtype, transpose=True)
 
     def spmm(self, A: CsrMatrix, b, out, plan=None, accumulate=False, tasks_per_warp=0, bias=None, relu=False,
-             acc32=None, acc32_in=False, acc32_out=False):
+             acc32=None, acc32_in=False, acc32_out=False, reserve_ctas=0):
         return ops.spmm_csr_compute(A.crow, A.col, A.val, b, A.rows, A.cols, out=out, plan=plan, accumulate=accumulate,
                                     tasks_per_warp=tasks_per_warp, bias=bias, relu=relu, acc32=acc32, acc32_in=acc32_in,
-                                    acc32_out=acc32_out)
+                                    acc32_out=acc32_out, reserve_ctas=reserve_ctas)
 
-    def spmm_t(self, A: CsrMatrix, dy, out, plan=None, tasks_per_warp=0, acc32_out=None):
+    def spmm_t(self, A: CsrMatrix, dy, out, plan=None, tasks_per_warp=0, acc32_out=None, reserve_ctas=0):
         return ops.spmm_csr_grad_b_compute(A.crow, A.col, A.val, dy, A.rows, A.cols, out=out, plan=plan,
-                                           tasks_per_warp=tasks_per_warp, acc32_out=acc32_out)
+                                           tasks_per_warp=tasks_per_warp, acc32_out=acc32_out, reserve_ctas=reserve_ctas)
 
     def sddmm(self, A: CsrMatrix, dy, b, plan=None):
         return ops.sddmm_csr_compute(A.crow, A.col, dy, b, A.rows, A.cols, A.val.dtype, plan=plan)
@@ -100,6 +100,21 @@ class SymmTransport:
         self.bufs: Dict[str, Tuple[torch.Tensor, list]] = {}
         self._bar = symm.empty((64,), dtype=torch.float32, device=device)
         self._hbar = symm.rendezvous(self._bar, self.gname)
+        # signal pad of the flag-synchronised kernels: pad[row, src_rank] = last epoch src_rank published
+        self.pad_rows = 64
+        self.pad = symm.empty((self.pad_rows, world), dtype=torch.int64, device=device)
+        hpad = symm.rendezvous(self.pad, self.gname)
+        self.pad.zero_()
+        torch.cuda.synchronize(device)
+        dist.barrier(group=group)                     # nobody signals before every pad is zeroed
+        self.peer_pad = [hpad.get_buffer(r, (self.pad_rows, world), torch.int64) for r in range(world)]
+
+    def my_flag_ptr(self, row: int, src_rank: int) -> int:
+        return self.pad.data_ptr() + (row * self.world + src_rank) * 8
+
+    def peer_flag_ptr(self, peer: int, row: int) -> int:
+        """Where THIS rank's epoch goes in `peer`'s pad."""
+        return self.peer_pad[peer].data_ptr() + (row * self.world + self.rank) * 8
 
     def alloc(self, name: str, rows: int, n: int, dtype) -> torch.Tensor:
         t = self._symm.empty((rows, n), dtype=dtype, device=self.device)
@@ -286,8 +301,13 @@ class ShardedSpmm:
 
         # ---- published buffers and what every peer holds for this rank's shard
         self._c = torch.empty((m, n), dtype=dtype, device=device)
+        self.fused = world > 1 and transport == "symm"
         if world > 1:
-            self.B_pubs = [self.T.alloc(f"B{k}", self.shard, n, dtype) for k in range(slots)]
+            # published buffers are double buffered by epoch parity: a rank overwrites parity p at
+            # epoch e only after its own pull / combine of epoch e-1 completed, which required every
+            # peer's signal of e-1, which each peer issues after it finished reading epoch e-2 (= p)
+            self.B_pubs2 = [[self.T.alloc(f"B{k}.{par}", self.shard, n, dtype) for par in (0, 1)] for k in range(slots)]
+            self.B_pubs = [pair[0] for pair in self.B_pubs2]
             tbl = [torch.zeros_like(seg_table) for _ in range(world)]
             dev_tbl = seg_table.to(device)
             gl = [torch.zeros_like(dev_tbl) for _ in range(world)]
@@ -297,15 +317,21 @@ class ShardedSpmm:
             dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=group)
             for sc in self.sub[1:]:
                 for k in range(slots):
-                    self.T.alloc(f"{sc.dBc_name}.{k}", int(mx), n, dtype)
+                    for par in (0, 1):
+                        self.T.alloc(f"{sc.dBc_name}.{k}.{par}", int(mx), n, dtype)
             recv = _exchange_lists(send_lists, rank, world, group)
             # (peer r, its bucket name, offset, count, rows of MY shard it holds partials for)
             self.incoming = [(r, f"dBc{int(tbl[r][rank][0])}", int(tbl[r][rank][1]), int(tbl[r][rank][2]), recv[r])
                              for r in range(world) if r != rank]
         else:
             self.B_pubs = [torch.zeros((self.shard, n), dtype=dtype, device=device) for _ in range(slots)]
+            self.B_pubs2 = [[b, b] for b in self.B_pubs]
             self.incoming = []
         self.B_pub = self.B_pubs[0]
+        self._fwd_epoch = [0] * slots
+        self._bwd_epoch = [0] * slots
+        if self.fused:
+            self._build_fused_tables()
         self._dbs = [torch.zeros((self.shard, n), dtype=dtype, device=device) for _ in range(slots)]
         # 16-bit operands on several ranks: running sums of the accumulate passes (forward) and of the
         # ranks' partials (backward) stay in fp32 and are rounded once — same error as a single pass
@@ -333,42 +359,110 @@ class ShardedSpmm:
         for sc in self.sub:
             sc.A.val.copy_(val_blk[sc.pos])
 
+    # ------------------------------------------------------------------ fused (flag-synchronised) exchange
+    def _build_fused_tables(self) -> None:
+        """Everything the one-launch exchange kernels need, as ctypes arrays built once: where to
+        write this rank's epoch in every peer's pad, the pull segments per (bucket, slot, parity)
+        and the combine segments per (slot, parity) in ascending rank order."""
+        import ctypes
+
+        from . import _lib
+        T, W, es = self.T, self.world, (4 if self.dtype == torch.float32 else 2)
+        assert 2 * self.slots <= T.pad_rows and W <= 16
+        peers = [r for r in range(W) if r != self.rank]
+        self._sig = {}
+        for kind in (0, 1):                       # 0: forward (B published), 1: backward (partials published)
+            for k in range(self.slots):
+                arr = (ctypes.c_void_p * len(peers))(*[T.peer_flag_ptr(r, 2 * k + kind) for r in peers])
+                self._sig[(kind, k)] = arr
+        self._pull = {}
+        for g, sc in enumerate(self.sub[1:], 1):
+            for k in range(self.slots):
+                for par in (0, 1):
+                    segs = (_lib.PullSeg * len(sc.segs))()
+                    for i, (s_, off, cnt, ids) in enumerate(sc.segs):
+                        segs[i] = _lib.PullSeg(T.peer(f"B{k}.{par}", s_).data_ptr(), ids.data_ptr() if cnt else None,
+                                               T.my_flag_ptr(2 * k, s_), cnt, off)
+                    self._pull[(g, k, par)] = segs
+        # inverse maps: my shard row -> row of peer r's partial segment (or -1)
+        self._inv = {}
+        for r, name, off, cnt, ids in self.incoming:
+            inv = torch.full((self.shard,), -1, dtype=torch.int32, device=self.device)
+            if cnt:
+                inv[ids.long()] = torch.arange(cnt, dtype=torch.int32, device=self.device)
+            self._inv[r] = inv
+        self._comb = {}
+        for k in range(self.slots):
+            for par in (0, 1):
+                inc = [x for x in self.incoming if x[3] > 0]
+                segs = (_lib.CombineSeg * max(1, len(inc)))()
+                for i, (r, name, off, cnt, ids) in enumerate(inc):
+                    segs[i] = _lib.CombineSeg(T.peer(f"{name}.{k}.{par}", r).data_ptr() + off * self.n * es,
+                                              self._inv[r].data_ptr(), T.my_flag_ptr(2 * k + 1, r))
+                self._comb[(k, par)] = (segs, len(inc))
+
+    def _signal(self, kind: int, slot: int, epoch: int) -> None:
+        from . import _lib
+        arr = self._sig[(kind, slot)]
+        ops.check(_lib.lib().ofspmm_signal_peers(arr, len(arr), epoch, torch.cuda.current_stream().cuda_stream), "signal_peers")
+
     # ------------------------------------------------------------------ forward
     def forward(self, B_shard: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
                 bias: Optional[torch.Tensor] = None, relu: bool = False, slot: int = 0) -> torch.Tensor:
-        """C_blk[m, n] = A_blk · B (B given as this rank's shard; None: ``self.B_pubs[slot]`` was filled
-        in place).  ``bias`` / ``relu`` are fused into the last accumulate pass."""
+        """C_blk[m, n] = A_blk · B, B given as this rank's shard.  ``bias`` / ``relu`` are fused into
+        the last accumulate pass."""
         st, cp, C = self.st, self.cp, (out if out is not None else self._c)
-        B_pub, bname = self.B_pubs[slot], f"B{slot}"
+        self._fwd_epoch[slot] += 1
+        epoch = self._fwd_epoch[slot]
+        par = epoch & 1
+        B_pub = self.B_pubs2[slot][par]
+        self.B_pubs[slot] = B_pub                     # what sddmm() of this step reads
+        if slot == 0:
+            self.B_pub = B_pub
         cur = st.cur()
-        st.wait(cur, self._ev_pulled[slot])           # peers finished pulling the previous step's rows
-        if B_shard is not None and B_shard.data_ptr() != B_pub.data_ptr():
-            B_pub[: B_shard.shape[0]].copy_(B_shard)
         last = len(self.sub) - 1
         ev_g = []
-        if self.world > 1:
+        ev_in = st.record() if self.world > 1 else None   # the pulled-row buffers of the previous step are free
+        if B_shard is not None and B_shard.data_ptr() != B_pub.data_ptr():
+            B_pub[: B_shard.shape[0]].copy_(B_shard)
+        if self.fused:
+            from . import _lib
+            self._signal(0, slot, epoch)              # my shard for this epoch is complete: tell every peer
+            dd, ii = ops._DENSE[self.dtype], _lib.DTYPE_INT32
+            with st.on_comm():
+                st.wait(st.comm, ev_in)
+                for g, sc in enumerate(self.sub[1:], 1):
+                    segs = self._pull[(g, slot, par)]
+                    # ONE launch for all owners of this bucket; each segment waits for its owner's flag
+                    ops.check(_lib.lib().ofspmm_pull_rows_multi(sc.Bc[slot].data_ptr(), self.n, self.n, segs, len(segs), epoch,
+                                                               self.n, dd, ii, self.pull_ctas, st.comm.cuda_stream),
+                              "pull_rows_multi")
+                    ev_g.append(st.record(st.comm))
+        elif self.world > 1:                          # host-logic emulation (gloo): barriers + all-gather
+            st.wait(cur, self._ev_pulled[slot])
             ev_pub = st.record()
             with st.on_comm():
                 st.wait(st.comm, ev_pub)
-                self.T.barrier(0)                     # every rank has published its shard
-                self.T.refresh(bname)
+                self.T.barrier(0)
+                self.T.refresh(f"B{slot}.{par}")
                 for sc in self.sub[1:]:
                     for s, off, cnt, ids in sc.segs:
                         if cnt:
-                            cp.gather_rows(sc.Bc[slot][off:off + cnt], self.T.peer(bname, s), ids, max_ctas=self.pull_ctas)
+                            cp.gather_rows(sc.Bc[slot][off:off + cnt], self.T.peer(f"B{slot}.{par}", s), ids, max_ctas=self.pull_ctas)
                     ev_g.append(st.record(st.comm))
-                self.T.barrier(1)                     # every rank is done reading the published shards
+                self.T.barrier(1)
                 self._ev_pulled[slot] = st.record(st.comm)
         ep = dict(bias=bias, relu=relu)
         wide = self._wide and last > 0       # bf16: fp32 running sums between the passes
         s0 = self.sub[0]
-        cp.spmm(s0.A, B_pub[: s0.A.cols], C, plan=s0.plan, tasks_per_warp=self.tpw, **(ep if last == 0 else {}),
+        # products that overlap the exchange leave one CTA slot per SM to its 128-thread kernels
+        ov = dict(reserve_ctas=1) if self.fused else dict(tasks_per_warp=self.tpw)
+        cp.spmm(s0.A, B_pub[: s0.A.cols], C, plan=s0.plan, **(ov if last > 0 else {}), **(ep if last == 0 else {}),
                 **(dict(acc32=self._acc32, acc32_out=True) if wide else {}))
         for g, sc in enumerate(self.sub[1:], 1):
             st.wait(cur, ev_g[g - 1])
             acc = dict(acc32=self._acc32, acc32_in=True, acc32_out=g < last) if wide else dict(accumulate=True)
-            cp.spmm(sc.A, sc.Bc[slot], C, plan=sc.plan, tasks_per_warp=self.tpw if g < last else 0,
-                    **acc, **(ep if g == last else {}))
+            cp.spmm(sc.A, sc.Bc[slot], C, plan=sc.plan, **(ov if g < last else {}), **acc, **(ep if g == last else {}))
         return C
 
     # ------------------------------------------------------------------ backward wrt B
@@ -379,11 +473,18 @@ class ShardedSpmm:
         cur = st.cur()
         dY_blk = dY_blk.contiguous()
         db = self._dbs[slot]
-        st.wait(cur, self._ev_consumed[slot])         # peers finished reading the previous partials
+        self._bwd_epoch[slot] += 1
+        epoch = self._bwd_epoch[slot]
+        par = epoch & 1
+        ov = dict(reserve_ctas=1) if self.fused else dict(tasks_per_warp=self.tpw)
+        if not self.fused:
+            st.wait(cur, self._ev_consumed[slot])     # emulation: peers finished reading the previous partials
         for sc in self.sub[1:]:                       # remote partials first: peers are waiting for them
-            pub = self.T.bufs[f"{sc.dBc_name}.{slot}"][0]
-            cp.spmm_t(sc.A, dY_blk, pub[: sc.A.cols], plan=sc.plan, tasks_per_warp=self.tpw)
-        ev_rem = st.record()
+            pub = self.T.bufs[f"{sc.dBc_name}.{slot}.{par}"][0]
+            cp.spmm_t(sc.A, dY_blk, pub[: sc.A.cols], plan=sc.plan, **ov)
+        if self.fused:
+            self._signal(1, slot, epoch)              # my partials for this epoch are complete
+        ev_rem = st.record() if self.world > 1 else None
         s0 = self.sub[0]
         acc = self._db32 if self._wide else db           # bf16: the ranks' partials are summed in fp32
         if self._wide:
@@ -392,18 +493,29 @@ class ShardedSpmm:
             cp.spmm_t(s0.A, dY_blk, db[: s0.A.cols], plan=s0.plan)
         if self.world == 1:
             return db
+        if self.fused:
+            from . import _lib
+            segs, nseg = self._comb[(slot, par)]
+            if nseg:
+                # ONE launch adds every peer's partial rows, in rank order, each guarded by its flag
+                ops.check(_lib.lib().ofspmm_combine_rows_multi(acc.data_ptr(), self.n, self.n, segs, nseg, epoch, self.shard,
+                                                              self.n, ops._DENSE[self.dtype], 0, cur.cuda_stream),
+                          "combine_rows_multi")
+            if self._wide:
+                cp.cast_from_f32(db, self._db32)      # one rounding of the complete sum
+            return db
         ev_loc = st.record()
         with st.on_comm():
             st.wait(st.comm, ev_rem)
             self.T.barrier(2)                         # every rank's remote partials are complete
             for sc in self.sub[1:]:
-                self.T.refresh(f"{sc.dBc_name}.{slot}")
+                self.T.refresh(f"{sc.dBc_name}.{slot}.{par}")
             st.wait(st.comm, ev_loc)
             for r, name, off, cnt, ids in self.incoming:   # ascending rank order: deterministic sum
                 if cnt:
-                    cp.scatter_add_rows(acc, self.T.peer(f"{name}.{slot}", r)[off:off + cnt], ids, max_ctas=0)
+                    cp.scatter_add_rows(acc, self.T.peer(f"{name}.{slot}.{par}", r)[off:off + cnt], ids, max_ctas=0)
             if self._wide:
-                cp.cast_from_f32(db, self._db32)      # one rounding of the complete sum
+                cp.cast_from_f32(db, self._db32)
             self.T.barrier(3)                         # every rank is done reading the partials
             self._ev_consumed[slot] = st.record(st.comm)
         st.wait(cur, self._ev_consumed[slot])

@@ -2,9 +2,12 @@
 the CSR arrays the op consumes, and persisting it.
 
 * ``coo_to_csr``           edge list (row, col[, val]) → CSR, duplicates coalesced, columns sorted
-                            within a row — device-agnostic torch (sort + segment ops; runs on the GPU
-                            for the 10⁸-edge graphs of BASELINE.json, on the CPU in the tests).
-* ``add_self_loops`` / ``sym_normalize`` / ``row_normalize``   the GCN preprocessing steps.
+                            within a row.  CUDA tensors go through the library's device kernels
+                            (``ofspmm_coo_to_csr``: radix sort + hand-written coalesce / offsets
+                            kernels, csrc/build.cu); CPU tensors (file ingestion, host tests) use the
+                            equivalent torch sort + segment ops.
+* ``add_self_loops`` / ``sym_normalize`` / ``row_normalize``   the GCN preprocessing steps
+                            (``ofspmm_csr_expand_rows`` / ``ofspmm_csr_normalize`` on the device).
 * ``save_csr_npz`` / ``load_csr_npz``   on-disk interchange in the *scipy.sparse.save_npz* layout
                             (keys ``data, indices, indptr, shape, format``), so a real Reddit /
                             ogbn-products adjacency exported with SciPy, DGL or PyG drops in where
@@ -13,7 +16,7 @@ the CSR arrays the op consumes, and persisting it.
                             python/oneflow/framework/check_point_v2.py:109-153.)
 * ``load_edge_list``       whitespace / comma separated ``src dst [weight]`` text → CSR.
 
-One-off construction utilities, not on the per-step path: plain torch / numpy, no custom kernels.
+One-off construction utilities, not on the per-step path.
 """
 from __future__ import annotations
 
@@ -23,6 +26,46 @@ import numpy as np
 import torch
 
 from .graphs import CsrMatrix
+
+_COALESCE = {"sum": 0, "max": 1, "first": 2}
+
+
+def _device_coo_to_csr(row, col, val, M: int, K: int, coalesce: str, index_dtype) -> CsrMatrix:
+    """CUDA path: every step on the device through the C ABI; one D2H read of the two counters."""
+    import ctypes
+
+    from . import _lib
+    from .ops import _INDEX, _ptr, _stream_ptr, check
+    L = _lib.lib()
+    n = int(row.numel())
+    dev = row.device
+    row, col = row.contiguous(), col.contiguous()
+    val = None if val is None else val.to(torch.float32).contiguous()
+    crow = torch.empty(M + 1, dtype=index_dtype, device=dev)
+    col_out = torch.empty(max(n, 1), dtype=index_dtype, device=dev)
+    val_out = torch.empty(max(n, 1), dtype=torch.float32, device=dev)
+    counts = torch.zeros(2, dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        nbytes = L.ofspmm_coo_to_csr_workspace_bytes(n, M, K)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        check(L.ofspmm_coo_to_csr(_ptr(row), _ptr(col), _ptr(val), n, M, K, _COALESCE[coalesce], _INDEX[index_dtype],
+                                  crow.data_ptr(), col_out.data_ptr(), val_out.data_ptr(), counts.data_ptr(),
+                                  ws.data_ptr(), nbytes, _stream_ptr(row)), "coo_to_csr")
+    nnz, dropped = (int(x) for x in counts.cpu())
+    if dropped:
+        raise ValueError(f"{dropped} edge(s) outside the {M} x {K} matrix")
+    return CsrMatrix(crow, col_out[:nnz].clone(), val_out[:nnz].clone(), M, K)
+
+
+def _device_normalize(A: CsrMatrix, mode: int) -> CsrMatrix:
+    from . import _lib
+    from .ops import _INDEX, _ptr, _stream_ptr, check
+    val = A.val.detach().to(torch.float32).clone()
+    dinv = torch.empty(max(A.rows, 1), dtype=torch.float32, device=val.device)
+    with torch.cuda.device(val.device):
+        check(_lib.lib().ofspmm_csr_normalize(_ptr(A.crow), _ptr(A.col), _ptr(val), _INDEX[A.crow.dtype], A.rows, A.cols, mode,
+                                              dinv.data_ptr(), _stream_ptr(val)), "csr_normalize")
+    return CsrMatrix(A.crow, A.col, val.to(A.val.dtype), A.rows, A.cols)
 
 
 def coo_to_csr(row: torch.Tensor, col: torch.Tensor, val: Optional[torch.Tensor], shape: Tuple[int, int],
@@ -34,6 +77,12 @@ def coo_to_csr(row: torch.Tensor, col: torch.Tensor, val: Optional[torch.Tensor]
     row, col = row.to(torch.int64).flatten(), col.to(torch.int64).flatten()
     if row.numel() != col.numel() or (val is not None and val.numel() != row.numel()):
         raise ValueError("row, col and val must have the same number of entries")
+    if coalesce not in _COALESCE:
+        raise ValueError(f"unknown coalesce mode {coalesce!r}")
+    if row.is_cuda:
+        if row.numel() >= 2 ** 31 - 1:
+            raise ValueError("nnz does not fit the library's 32-bit row offsets")
+        return _device_coo_to_csr(row, col, None if val is None else val.flatten(), M, K, coalesce, index_dtype)
     if row.numel() and (int(row.min()) < 0 or int(row.max()) >= M or int(col.min()) < 0 or int(col.max()) >= K):
         raise ValueError(f"edge index outside the {M} x {K} matrix")
     dev = row.device
@@ -64,6 +113,14 @@ def coo_to_csr(row: torch.Tensor, col: torch.Tensor, val: Optional[torch.Tensor]
 
 
 def csr_to_coo(A: CsrMatrix) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    if A.crow.is_cuda:
+        from . import _lib
+        from .ops import _INDEX, _ptr, _stream_ptr, check
+        rows = torch.empty(A.nnz, dtype=torch.int64, device=A.crow.device)
+        with torch.cuda.device(A.crow.device):
+            check(_lib.lib().ofspmm_csr_expand_rows(_ptr(A.crow), _INDEX[A.crow.dtype], A.rows, _ptr(rows),
+                                                    _stream_ptr(A.crow)), "csr_expand_rows")
+        return rows, A.col.to(torch.int64), A.val
     rows = torch.repeat_interleave(torch.arange(A.rows, device=A.crow.device), A.row_lengths())
     return rows, A.col.to(torch.int64), A.val
 
@@ -82,6 +139,10 @@ def add_self_loops(A: CsrMatrix, weight: float = 1.0) -> CsrMatrix:
 
 def sym_normalize(A: CsrMatrix) -> CsrMatrix:
     """D^-1/2 · A · D^-1/2 with D = diag(row sums of |A|) — the GCN propagation matrix."""
+    if A.crow.is_cuda:
+        if A.rows != A.cols:
+            raise ValueError("symmetric normalisation needs a square matrix")
+        return _device_normalize(A, 0)
     r, c, v = csr_to_coo(A)
     deg = torch.zeros(A.rows, dtype=torch.float32, device=r.device).index_add_(0, r, v.abs().float())
     dinv = torch.where(deg > 0, deg.rsqrt(), torch.zeros_like(deg))
@@ -90,6 +151,8 @@ def sym_normalize(A: CsrMatrix) -> CsrMatrix:
 
 def row_normalize(A: CsrMatrix) -> CsrMatrix:
     """D^-1 · A (mean aggregation)."""
+    if A.crow.is_cuda:
+        return _device_normalize(A, 1)
     r, _, v = csr_to_coo(A)
     deg = torch.zeros(A.rows, dtype=torch.float32, device=r.device).index_add_(0, r, v.abs().float())
     dinv = torch.where(deg > 0, 1.0 / deg, torch.zeros_like(deg))

@@ -180,8 +180,8 @@ class SpmmPlan:
 
 
 def _opts(flags: int = 0, tasks_per_warp: int = 0, variant: int = 0, part: Optional[torch.Tensor] = None,
-          bias: Optional[torch.Tensor] = None, acc32: Optional[torch.Tensor] = None) -> OptsStruct:
-    return OptsStruct(flags, tasks_per_warp, variant, 0, part.data_ptr() if part is not None else None,
+          bias: Optional[torch.Tensor] = None, acc32: Optional[torch.Tensor] = None, reserve_ctas: int = 0) -> OptsStruct:
+    return OptsStruct(flags, tasks_per_warp, variant, reserve_ctas, part.data_ptr() if part is not None else None,
                       part.numel() if part is not None else 0, bias.data_ptr() if bias is not None else None,
                       acc32.data_ptr() if acc32 is not None else None)
 
@@ -200,7 +200,8 @@ def spmm_csr_compute(a_crow, a_col, a_val, b, a_rows: int, a_cols: int,
                      out: Optional[torch.Tensor] = None, *, plan: Optional[SpmmPlan] = None,
                      accumulate: bool = False, bias: Optional[torch.Tensor] = None, relu: bool = False,
                      tasks_per_warp: int = 0, variant: Optional[int] = None, order: Optional[str] = None,
-                     acc32: Optional[torch.Tensor] = None, acc32_in: bool = False, acc32_out: bool = False) -> torch.Tensor:
+                     acc32: Optional[torch.Tensor] = None, acc32_in: bool = False, acc32_out: bool = False,
+                     reserve_ctas: int = 0) -> torch.Tensor:
     """SpmmCsrKernel::Compute — out[a_rows, n] = A · b  (``accumulate``: out += A · b; ``bias`` /
     ``relu``: epilogue fused into the store, applied to the complete row sum).
 
@@ -234,7 +235,7 @@ def spmm_csr_compute(a_crow, a_col, a_val, b, a_rows: int, a_cols: int,
         ws, wsp = _workspace(nbytes, b.device)
         ldb = b.stride(0) if b.shape[0] > 1 else max(n, 1)
         ldc = out.stride(0) if out.shape[0] > 1 else max(n, 1)
-        o = _opts(flags, tasks_per_warp, v, part, bias, acc32 if (acc32_in or acc32_out) else None)
+        o = _opts(flags, tasks_per_warp, v, part, bias, acc32 if (acc32_in or acc32_out) else None, reserve_ctas)
         rc = L.ofspmm_fwd_ex(ctypes.byref(A), _ptr(b), ldb, _ptr(out), ldc, n, _DENSE[dt], ctypes.byref(o), wsp, nbytes,
                              _stream_ptr(b))
         check(rc, "spmm_csr")
@@ -245,7 +246,7 @@ def spmm_csr_grad_b_compute(a_crow, a_col, a_val, dy, a_rows: int, a_cols: int,
                             transposed: Optional[Tuple[torch.Tensor, torch.Tensor, torch.Tensor]] = None,
                             out: Optional[torch.Tensor] = None, *, plan: Optional[SpmmPlan] = None,
                             atomic: bool = False, tasks_per_warp: int = 0, regather: bool = False,
-                            acc32_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                            acc32_out: Optional[torch.Tensor] = None, reserve_ctas: int = 0) -> torch.Tensor:
     """SpmmCsrGradBKernel::Compute — db[a_cols, n] = A^T · dy.  Routes, in order of preference:
 
       * ``plan`` with a transposed structure → forward kernel on the cached structure of A^T; the
@@ -288,7 +289,7 @@ def spmm_csr_grad_b_compute(a_crow, a_col, a_val, dy, a_rows: int, a_cols: int,
                 # acc32_out: the fp32 sums go to that buffer instead of `out` (16-bit products whose
                 # partial results are combined across ranks in fp32)
                 fl = _acc32_flags(acc32_out, False, acc32_out is not None, a_cols, n, dt)
-                o = _opts(fl, tasks_per_warp, plan.t_variant, plan.t_part, None, acc32_out)
+                o = _opts(fl, tasks_per_warp, plan.t_variant, plan.t_part, None, acc32_out, reserve_ctas)
                 check(L.ofspmm_fwd_ex(ctypes.byref(At), _ptr(dy), n, _ptr(out), n, n, _DENSE[dt], ctypes.byref(o), wsp, nbytes,
                                       _stream_ptr(dy)), "spmm_csr_grad_b(cached structure + values)")
         return out

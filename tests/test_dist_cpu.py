@@ -34,7 +34,7 @@ class OracleCompute:
         return None
 
     def spmm(self, A, b, out, plan=None, accumulate=False, tasks_per_warp=0, bias=None, relu=False,
-             acc32=None, acc32_in=False, acc32_out=False):
+             acc32=None, acc32_in=False, acc32_out=False, reserve_ctas=0):
         from oracle import oracle as O
         assert not (acc32_in or acc32_out), "fp32 running sums are a 16-bit feature; the CPU stand-in is fp32"
         res = torch.from_numpy(O.spmm_f32(A.crow.numpy(), A.col.numpy(), A.val.numpy(), b.contiguous().numpy(), A.cols))
@@ -47,7 +47,7 @@ class OracleCompute:
         out.copy_(res)
         return out
 
-    def spmm_t(self, A, dy, out, plan=None, tasks_per_warp=0, acc32_out=None):
+    def spmm_t(self, A, dy, out, plan=None, tasks_per_warp=0, acc32_out=None, reserve_ctas=0):
         from oracle import oracle as O
         out.copy_(torch.from_numpy(O.spmm_t_f32(A.crow.numpy(), A.col.numpy(), A.val.numpy(), dy.contiguous().numpy(), A.cols)))
         return out

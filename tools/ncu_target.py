@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--workload", default="cfg2_reddit_n128_fp32")
     ap.add_argument("--op", default="fwd", choices=["fwd", "bwd_t", "atomic", "sddmm"])
     ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--plan", action="store_true", help="forward with a cached plan (no partition kernel in the call)")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     spec = bench.WORKLOADS[args.workload]
@@ -34,12 +35,13 @@ def main():
     C = torch.empty((A.rows, n), dtype=dtype, device=dev)
     dB = torch.empty((A.cols, n), dtype=dtype, device=dev)
     if args.op == "fwd":
-        fn = lambda: ops.spmm_csr_compute(A.crow, A.col, A.val, B, A.rows, A.cols, out=C)
+        plan = ops.SpmmPlan(A.crow, A.col, A.rows, A.cols, n, dtype) if args.plan else None
+        fn = lambda: ops.spmm_csr_compute(A.crow, A.col, A.val, B, A.rows, A.cols, out=C, plan=plan)
     elif args.op == "bwd_t":
         tr = ops.csr_transpose(A.crow, A.col, A.val, A.rows, A.cols)
         fn = lambda: ops.spmm_csr_grad_b_compute(A.crow, A.col, A.val, dY, A.rows, A.cols, transposed=tr, out=dB)
     elif args.op == "atomic":
-        fn = lambda: ops.spmm_csr_grad_b_compute(A.crow, A.col, A.val, dY, A.rows, A.cols, out=dB)
+        fn = lambda: ops.spmm_csr_grad_b_compute(A.crow, A.col, A.val, dY, A.rows, A.cols, out=dB, atomic=True)
     else:
         dv = torch.empty(A.nnz, dtype=torch.float32, device=dev)
         fn = lambda: ops.sddmm_csr_compute(A.crow, A.col, dY, B, A.rows, A.cols, out=dv)

@@ -67,7 +67,8 @@ def main():
         report("bwd_b transpose-route", *timed(lambda: ops.spmm_csr_grad_b_compute(A.crow, A.col, A.val, dY, A.rows, A.cols, transposed=tr, out=dB), args.reps))
         del tr
     if "atomic" not in args.skip:
-        report("bwd_b atomic-route", *timed(lambda: ops.spmm_csr_grad_b_compute(A.crow, A.col, A.val, dY, A.rows, A.cols, out=dB), args.reps))
+        report("bwd_b atomic-route", *timed(lambda: ops.spmm_csr_grad_b_compute(A.crow, A.col, A.val, dY, A.rows, A.cols, out=dB, atomic=True), args.reps))
+        report("bwd_b transient-route", *timed(lambda: ops.spmm_csr_grad_b_compute(A.crow, A.col, A.val, dY, A.rows, A.cols, out=dB), args.reps))
     if "sddmm" not in args.skip:
         dv = torch.empty(A.nnz, dtype=torch.float32, device=dev)
         report("sddmm", *timed(lambda: ops.sddmm_csr_compute(A.crow, A.col, dY, B, A.rows, A.cols, out=dv), args.reps))
