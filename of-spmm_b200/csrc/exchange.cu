@@ -228,6 +228,98 @@ __device__ __forceinline__ void wait_flag(const unsigned long long* flag, unsign
 
 constexpr int kPullThreads = 128;   // fits the CTA slot the overlapped product leaves free per SM
 
+// TMA pull: one warp per CTA drives a ring of kStages shared-memory stages.  Every wanted row is one
+// cp.async.bulk (global -> shared) straight from the owner's HBM over NVLink, completion counted on
+// the stage's mbarrier; a landed stage leaves as ONE bulk store (shared -> global; destination rows
+// are consecutive).  The loads of the next kAhead batches are in flight while a batch is waited
+// for: 3 x 16 KB per CTA, ~7 MB chip-wide — the bytes in flight NVLink's ~3 us round trip needs at
+// 700+ GB/s — for 32 threads and a handful of registers per SM, so the product it overlaps keeps
+// its occupancy.  Stage reuse: load #i refills the stage of load #i-kStages, whose store is at
+// least two commits old when at most kAhead = kStages-2 loads run ahead; waiting until at most one
+// store group is pending therefore guarantees that store has finished reading the stage.
+constexpr int kStages = 5;
+constexpr int kAhead = kStages - 2;
+constexpr int kStageBytes = 16 * 1024;
+
+__device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+
+template <typename IdxT>
+__global__ void __launch_bounds__(32) pull_rows_tma_kernel(char* __restrict__ dst, long long dst_stride, long long src_stride,
+                                                          const PullArgs a, unsigned long long epoch, uint32_t row_bytes) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+  const int lane = threadIdx.x;
+  const int rows_per_stage = kStageBytes / row_bytes;
+  if (lane == 0)
+    for (int i = 0; i < kStages; ++i) mbar_init(&bars[i], 1);
+  fence_mbar_init();
+  __syncwarp();
+  const uint64_t pol = l2_policy_evict_first();
+  uint32_t phase_bits = 0;     // bit i = parity to wait for on stage i
+  long long issued = 0, done = 0;   // batches this CTA has issued / retired, over all segments (ring position)
+  for (int s = 0; s < a.nseg; ++s) {
+    const PullSeg sg = a.seg[s];
+    if (sg.count == 0) continue;
+    if (lane == 0) {
+      unsigned long long v;
+      for (;;) {
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(sg.flag) : "memory");
+        if (v >= epoch) break;
+        __nanosleep(200);
+      }
+    }
+    __syncwarp();
+    const IdxT* list = static_cast<const IdxT*>(sg.list);
+    const long long nb = (sg.count + rows_per_stage - 1) / rows_per_stage;      // batches of the segment
+    const long long mine = blockIdx.x < nb ? (nb - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    auto issue = [&](long long k) {   // k-th batch of this CTA in this segment
+      const long long batch = blockIdx.x + k * gridDim.x;
+      const int st = static_cast<int>(issued % kStages);
+      const long long r0 = batch * rows_per_stage;
+      const int cnt = static_cast<int>(sg.count - r0 < rows_per_stage ? sg.count - r0 : rows_per_stage);
+      if (issued >= kStages) {       // the store that last used this stage must have finished reading it
+        if (lane == 0) bulk_wait_read<1>();
+        __syncwarp();
+      }
+      if (lane == 0) mbar_arrive_expect_tx(&bars[st], static_cast<uint32_t>(cnt) * row_bytes);
+      __syncwarp();
+      for (int r = lane; r < cnt; r += 32)
+        tma_bulk_g2s(smem + st * kStageBytes + r * row_bytes, sg.src + static_cast<long long>(list[r0 + r]) * src_stride, row_bytes,
+                     &bars[st], pol);
+      ++issued;
+    };
+    long long k_issue = 0;
+    for (; k_issue < mine && k_issue < kAhead; ++k_issue) issue(k_issue);
+    for (long long k = 0; k < mine; ++k) {
+      if (k_issue < mine) issue(k_issue++);
+      const int st = static_cast<int>(done % kStages);
+      mbar_wait(&bars[st], (phase_bits >> st) & 1u);
+      phase_bits ^= 1u << st;
+      const long long batch = blockIdx.x + k * gridDim.x;
+      const long long r0 = batch * rows_per_stage;
+      const int cnt = static_cast<int>(sg.count - r0 < rows_per_stage ? sg.count - r0 : rows_per_stage);
+      if (lane == 0) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        bulk_s2g(dst + (sg.dst_row + r0) * dst_stride, smem + st * kStageBytes, static_cast<uint32_t>(cnt) * row_bytes);
+        bulk_commit();
+      }
+      __syncwarp();
+      ++done;
+    }
+  }
+  if (lane == 0) bulk_wait_read<0>();
+  __syncwarp();
+}
+
+// Register fallback (rows that are not packed / too wide for a stage): 16-byte loads, kUnroll in flight.
 template <typename IdxT>
 __global__ void __launch_bounds__(kPullThreads) pull_rows_multi_kernel(char* __restrict__ dst, long long dst_stride,
                                                                       long long src_stride, const PullArgs a,
@@ -278,35 +370,54 @@ struct CombineArgs {
 // order) of the peer's partial row, for the rows the peer holds.  One 16-byte unit of the source
 // dtype per thread; AccT = float for bf16 sources (rounded once by the caller), = source for fp32.
 template <typename SrcT>
+__device__ __forceinline__ void add_unit(float* d, const uint4& v) {
+  if constexpr (sizeof(SrcT) == 4) {
+    float4 x = *reinterpret_cast<float4*>(d);
+    x.x += __uint_as_float(v.x); x.y += __uint_as_float(v.y); x.z += __uint_as_float(v.z); x.w += __uint_as_float(v.w);
+    *reinterpret_cast<float4*>(d) = x;
+  } else {
+    float4 x = reinterpret_cast<float4*>(d)[0], y = reinterpret_cast<float4*>(d)[1];
+    x.x += __uint_as_float(v.x << 16); x.y += __uint_as_float(v.x & 0xffff0000u);
+    x.z += __uint_as_float(v.y << 16); x.w += __uint_as_float(v.y & 0xffff0000u);
+    y.x += __uint_as_float(v.z << 16); y.y += __uint_as_float(v.z & 0xffff0000u);
+    y.z += __uint_as_float(v.w << 16); y.w += __uint_as_float(v.w & 0xffff0000u);
+    reinterpret_cast<float4*>(d)[0] = x;
+    reinterpret_cast<float4*>(d)[1] = y;
+  }
+}
+
+// The unit -> thread mapping is the same for every segment, so one thread adds all peers'
+// contributions to its units, in segment order; kUnroll peer loads in flight per thread.
+template <typename SrcT>
 __global__ void __launch_bounds__(kPullThreads) combine_rows_multi_kernel(float* __restrict__ acc, long long ld_acc,
                                                                          long long src_stride, const CombineArgs a,
                                                                          unsigned long long epoch, long long rows, int units) {
   constexpr int kPer = 16 / sizeof(SrcT);   // values per 16-byte unit: 4 fp32 or 8 bf16
+  const long long total = rows * units;
+  const long long stride = static_cast<long long>(gridDim.x) * kPullThreads;
   for (int s = 0; s < a.nseg; ++s) {
     const CombineSeg sg = a.seg[s];
     wait_flag(sg.flag, epoch);
-    const long long total = rows * units;
-    const long long stride = static_cast<long long>(gridDim.x) * kPullThreads;
-    for (long long u = static_cast<long long>(blockIdx.x) * kPullThreads + threadIdx.x; u < total; u += stride) {
-      const long long r = u / units;
-      const int j = sg.inv[r];
-      if (j < 0) continue;
-      const int c = static_cast<int>(u - r * units);
-      const uint4 v = ld_peer16(sg.src + static_cast<long long>(j) * src_stride + c * 16);
-      float* d = acc + r * ld_acc + c * kPer;
-      if constexpr (sizeof(SrcT) == 4) {
-        float4 x = *reinterpret_cast<float4*>(d);
-        x.x += __uint_as_float(v.x); x.y += __uint_as_float(v.y); x.z += __uint_as_float(v.z); x.w += __uint_as_float(v.w);
-        *reinterpret_cast<float4*>(d) = x;
-      } else {
-        float4 x = reinterpret_cast<float4*>(d)[0], y = reinterpret_cast<float4*>(d)[1];
-        x.x += __uint_as_float(v.x << 16); x.y += __uint_as_float(v.x & 0xffff0000u);
-        x.z += __uint_as_float(v.y << 16); x.w += __uint_as_float(v.y & 0xffff0000u);
-        y.x += __uint_as_float(v.z << 16); y.y += __uint_as_float(v.z & 0xffff0000u);
-        y.z += __uint_as_float(v.w << 16); y.w += __uint_as_float(v.w & 0xffff0000u);
-        reinterpret_cast<float4*>(d)[0] = x;
-        reinterpret_cast<float4*>(d)[1] = y;
+    for (long long u0 = static_cast<long long>(blockIdx.x) * kPullThreads + threadIdx.x; u0 < total; u0 += kUnroll * stride) {
+      uint4 v[kUnroll];
+      float* d[kUnroll];
+#pragma unroll
+      for (int k = 0; k < kUnroll; ++k) {
+        const long long u = u0 + k * stride;
+        d[k] = nullptr;
+        if (u < total) {
+          const long long r = u / units;
+          const int j = sg.inv[r];
+          if (j >= 0) {
+            const int c = static_cast<int>(u - r * units);
+            v[k] = ld_peer16(sg.src + static_cast<long long>(j) * src_stride + c * 16);
+            d[k] = acc + r * ld_acc + c * kPer;
+          }
+        }
       }
+#pragma unroll
+      for (int k = 0; k < kUnroll; ++k)
+        if (d[k] != nullptr) add_unit<SrcT>(d[k], v[k]);
     }
     __syncthreads();
   }
@@ -480,15 +591,41 @@ int launch_pull_rows_multi(void* dst, int64_t ld_dst, int64_t ld_src, const ofsp
   DevInfo dev;
   if (int rc = get_dev_info(&dev)) return rc;
   const int units = static_cast<int>(n * es / 16);
-  int grid = max_ctas > 0 ? max_ctas : dev.sms;
-  const long long need = (rows * units + kPullThreads * kUnroll - 1) / (kPullThreads * kUnroll);
-  if (grid > need) grid = static_cast<int>(need < 1 ? 1 : need);
-  if (idx_dtype == OFSPMM_DTYPE_INT32)
-    pull_rows_multi_kernel<int32_t><<<grid, kPullThreads, 0, stream>>>(static_cast<char*>(dst), ld_dst * es, ld_src * es, a, epoch, units);
-  else if (idx_dtype == OFSPMM_DTYPE_INT64)
-    pull_rows_multi_kernel<int64_t><<<grid, kPullThreads, 0, stream>>>(static_cast<char*>(dst), ld_dst * es, ld_src * es, a, epoch, units);
-  else
-    return OFSPMM_ERR_UNSUPPORTED_DTYPE;
+  const size_t row_bytes = static_cast<size_t>(n) * es;
+  if (idx_dtype != OFSPMM_DTYPE_INT32 && idx_dtype != OFSPMM_DTYPE_INT64) return OFSPMM_ERR_UNSUPPORTED_DTYPE;
+  if (ld_dst == n && row_bytes <= static_cast<size_t>(kStageBytes)) {
+    // TMA path: destination rows packed (one bulk store per stage), a row fits a stage
+    const int rows_per_stage = static_cast<int>(kStageBytes / row_bytes);
+    const size_t smem = static_cast<size_t>(kStages) * kStageBytes + kStages * sizeof(uint64_t);
+    int grid = max_ctas > 0 ? max_ctas : dev.sms * 2;
+    const long long need = (rows + rows_per_stage - 1) / rows_per_stage;
+    if (grid > need) grid = static_cast<int>(need < 1 ? 1 : need);
+    if (idx_dtype == OFSPMM_DTYPE_INT32) {
+      static KernelLaunchCache cache;
+      if (cache.get(dev.ordinal) == 0) {
+        OFSPMM_CUDA_OK(cudaFuncSetAttribute(pull_rows_tma_kernel<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        cache.set(dev.ordinal, 1);
+      }
+      pull_rows_tma_kernel<int32_t><<<grid, 32, smem, stream>>>(static_cast<char*>(dst), ld_dst * es, ld_src * es, a, epoch,
+                                                               static_cast<uint32_t>(row_bytes));
+    } else {
+      static KernelLaunchCache cache;
+      if (cache.get(dev.ordinal) == 0) {
+        OFSPMM_CUDA_OK(cudaFuncSetAttribute(pull_rows_tma_kernel<int64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        cache.set(dev.ordinal, 1);
+      }
+      pull_rows_tma_kernel<int64_t><<<grid, 32, smem, stream>>>(static_cast<char*>(dst), ld_dst * es, ld_src * es, a, epoch,
+                                                               static_cast<uint32_t>(row_bytes));
+    }
+  } else {
+    int grid = max_ctas > 0 ? max_ctas : dev.sms * 2;
+    const long long need = (rows * units + kPullThreads * kUnroll - 1) / (kPullThreads * kUnroll);
+    if (grid > need) grid = static_cast<int>(need < 1 ? 1 : need);
+    if (idx_dtype == OFSPMM_DTYPE_INT32)
+      pull_rows_multi_kernel<int32_t><<<grid, kPullThreads, 0, stream>>>(static_cast<char*>(dst), ld_dst * es, ld_src * es, a, epoch, units);
+    else
+      pull_rows_multi_kernel<int64_t><<<grid, kPullThreads, 0, stream>>>(static_cast<char*>(dst), ld_dst * es, ld_src * es, a, epoch, units);
+  }
   count_launch();
   OFSPMM_CUDA_OK(cudaGetLastError());
   return OFSPMM_OK;
@@ -514,8 +651,8 @@ int launch_combine_rows_multi(float* acc, int64_t ld_acc, int64_t ld_src, const 
   DevInfo dev;
   if (int rc = get_dev_info(&dev)) return rc;
   const int units = static_cast<int>(n * es / 16);
-  int grid = max_ctas > 0 ? max_ctas : dev.sms * 4;
-  const long long need = (rows * units + kPullThreads - 1) / kPullThreads;
+  int grid = max_ctas > 0 ? max_ctas : dev.sms * 8;
+  const long long need = (rows * units + kPullThreads * kUnroll - 1) / (kPullThreads * kUnroll);
   if (grid > need) grid = static_cast<int>(need < 1 ? 1 : need);
   if (src_dtype == OFSPMM_DTYPE_FLOAT)
     combine_rows_multi_kernel<float><<<grid, kPullThreads, 0, stream>>>(acc, ld_acc, ld_src * es, a, epoch, rows, units);

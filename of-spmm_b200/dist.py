@@ -61,11 +61,20 @@ class CudaCompute:
 
     def spmm(self, A: CsrMatrix, b, out, plan=None, accumulate=False, tasks_per_warp=0, bias=None, relu=False,
              acc32=None, acc32_in=False, acc32_out=False, reserve_ctas=0):
+        if plan is not None:      # hot path of the sharded step: one ctypes call, everything else prepared
+            L = ops._lib
+            flags = (L.FWD_ACCUMULATE if accumulate else 0) | (L.FWD_BIAS if bias is not None else 0) | \
+                    (L.FWD_RELU if relu else 0) | (L.FWD_ACC32_IN if acc32_in else 0) | (L.FWD_ACC32_OUT if acc32_out else 0)
+            return plan.prepared()(A.val, b, out, flags, bias, acc32 if (acc32_in or acc32_out) else None, reserve_ctas,
+                                   tasks_per_warp)
         return ops.spmm_csr_compute(A.crow, A.col, A.val, b, A.rows, A.cols, out=out, plan=plan, accumulate=accumulate,
                                     tasks_per_warp=tasks_per_warp, bias=bias, relu=relu, acc32=acc32, acc32_in=acc32_in,
                                     acc32_out=acc32_out, reserve_ctas=reserve_ctas)
 
     def spmm_t(self, A: CsrMatrix, dy, out, plan=None, tasks_per_warp=0, acc32_out=None, reserve_ctas=0):
+        if plan is not None and plan.t_crow is not None:
+            flags = ops._lib.FWD_ACC32_OUT if acc32_out is not None else 0
+            return plan.prepared(True)(plan.transposed_values(A.val), dy, out, flags, None, acc32_out, reserve_ctas, tasks_per_warp)
         return ops.spmm_csr_grad_b_compute(A.crow, A.col, A.val, dy, A.rows, A.cols, out=out, plan=plan,
                                            tasks_per_warp=tasks_per_warp, acc32_out=acc32_out, reserve_ctas=reserve_ctas)
 

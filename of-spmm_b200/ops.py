@@ -173,10 +173,57 @@ class SpmmPlan:
             self._t_val, self._t_val_key = out, key
         return self._t_val
 
+    def prepared(self, transposed: bool = False) -> "_Prepared":
+        """Low-host-overhead launcher of A·B (or, ``transposed``, of A^T·dY on the cached structure)."""
+        key = "_prep_t" if transposed else "_prep"
+        p = getattr(self, key, None)
+        if p is None:
+            if transposed:
+                p = _Prepared(self.t_crow, self.t_col, self.cols, self.rows, self.n, self.dtype, self.t_variant, self.t_part)
+            else:
+                p = _Prepared(self.a_crow, self.a_col, self.rows, self.cols, self.n, self.dtype, self.variant, self.part)
+            setattr(self, key, p)
+        return p
+
     def variant_name(self, transposed: bool = False) -> str:
         v = self.t_variant if transposed else self.variant
         r, c = (self.cols, self.rows) if transposed else (self.rows, self.cols)
         return _lib.lib().ofspmm_variant_name(v, r, self.nnz, self.n, _DENSE[self.dtype]).decode()
+
+
+class _Prepared:
+    """One forward-shaped product with everything that does not change between calls resolved once
+    (CSR struct, variant, task partition, a persistent workspace, the opts struct): a call is a
+    single ctypes call, ~10 us of host time instead of ~50 — which matters once 8 GPUs have cut the
+    device time of a step to ~1 ms.  Built lazily by ``SpmmPlan.prepared``; never shared between
+    streams that could run concurrently (it owns its workspace)."""
+
+    def __init__(self, crow, col, rows: int, cols: int, n: int, dtype, variant: int, part: torch.Tensor):
+        L = _lib.lib()
+        self.L, self.n, self.rows, self.cols, self.dd = L, int(n), rows, cols, _DENSE[dtype]
+        self.keep = (crow, col, part)
+        self.A = CsrStruct(rows, cols, int(col.numel()), _ptr(crow), _ptr(col), None, _INDEX[crow.dtype], _lib.DTYPE_FLOAT)
+        self.variant = variant
+        with torch.cuda.device(crow.device):
+            self.ws_bytes = L.ofspmm_fwd_ex_workspace_bytes(rows, cols, self.A.nnz, self.n, self.dd, variant)
+            self.ws = torch.empty(max(self.ws_bytes, 16), dtype=torch.uint8, device=crow.device)
+        self.opts = OptsStruct(0, 0, variant, 0, part.data_ptr(), part.numel(), None, None)
+        self._byref_A, self._byref_o = ctypes.byref(self.A), ctypes.byref(self.opts)
+
+    def __call__(self, val: torch.Tensor, b: torch.Tensor, out: torch.Tensor, flags: int = 0, bias=None, acc32=None,
+                 reserve_ctas: int = 0, tasks_per_warp: int = 0) -> torch.Tensor:
+        A, o = self.A, self.opts
+        A.val = val.data_ptr() if val.numel() else None
+        A.val_dtype = _DENSE[val.dtype]
+        o.flags, o.tasks_per_warp, o.reserve_ctas_per_sm = flags, tasks_per_warp, reserve_ctas
+        o.bias = bias.data_ptr() if bias is not None else None
+        o.acc32 = acc32.data_ptr() if acc32 is not None else None
+        ldb = b.stride(0) if b.shape[0] > 1 else self.n
+        ldc = out.stride(0) if out.shape[0] > 1 else self.n
+        check(self.L.ofspmm_fwd_ex(self._byref_A, b.data_ptr() if b.numel() else None, ldb, out.data_ptr(), ldc, self.n, self.dd,
+                                   self._byref_o, self.ws.data_ptr(), self.ws_bytes,
+                                   torch.cuda.current_stream(out.device).cuda_stream), "spmm_csr(prepared)")
+        return out
 
 
 def _opts(flags: int = 0, tasks_per_warp: int = 0, variant: int = 0, part: Optional[torch.Tensor] = None,

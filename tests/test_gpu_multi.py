@@ -105,7 +105,11 @@ def _worker(rank, world, port, cases, q):
     except Exception:
         import traceback
         q.put(("error", rank, traceback.format_exc()))
+        q.close()
+        q.join_thread()
         os._exit(1)
+    q.close()
+    q.join_thread()                                   # the result must reach the parent before the hard exit
     os._exit(0)
 
 
@@ -180,7 +184,11 @@ def _gcn_worker(rank, world, port, q):
     except Exception:
         import traceback
         q.put(("error", rank, traceback.format_exc()))
+        q.close()
+        q.join_thread()
         os._exit(1)
+    q.close()
+    q.join_thread()                                   # the result must reach the parent before the hard exit
     os._exit(0)
 
 

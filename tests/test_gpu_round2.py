@@ -430,3 +430,54 @@ def test_scatter_add_rows_into_fp32_then_cast_once():
     out = torch.empty((K, n), dtype=torch.bfloat16, device=DEV)
     ops.cast_from_f32(out, acc)
     assert torch.equal(out, want.to(torch.bfloat16))
+
+
+# ------------------------------------------------------------------ flag-synchronised multi-peer kernels, one GPU
+
+@pytest.mark.parametrize("dtype,n", [(torch.float32, 128), (torch.bfloat16, 256), (torch.float32, 20)])
+def test_multi_peer_pull_and_combine_kernels_bit_exact(dtype, n):
+    """ofspmm_signal_peers / ofspmm_pull_rows_multi (TMA ring when rows are packed) /
+    ofspmm_combine_rows_multi with the 'peers' being buffers on the same GPU: the flags are written by
+    the signal kernel earlier on the same stream, so no kernel ever waits on a concurrently running
+    one.  Checked against torch indexing, bit for bit; the cross-GPU use is in tests/test_gpu_multi.py."""
+    L = _lib.lib()
+    g = torch.Generator().manual_seed(n)
+    peers, shard = 3, 4000
+    if (n * (4 if dtype == torch.float32 else 2)) % 16 != 0:
+        pytest.skip("multi-peer kernels move whole 16-byte units")
+    pad = torch.zeros((4, peers), dtype=torch.int64, device=DEV)
+    stream = torch.cuda.current_stream().cuda_stream
+    epoch = 7
+    slots = (ctypes.c_void_p * peers)(*[pad.data_ptr() + (0 * peers + r) * 8 for r in range(peers)])
+    assert L.ofspmm_signal_peers(slots, peers, epoch, stream) == 0
+    srcs = [torch.randn(shard, n, generator=g).to(dtype).to(DEV) for _ in range(peers)]
+    lists = [torch.randperm(shard, generator=g)[: 700 + 311 * r].sort().values.int().to(DEV) for r in range(peers)]
+    total = sum(int(l.numel()) for l in lists)
+    dst = torch.full((total, n), 3.0, dtype=dtype, device=DEV)
+    segs = (_lib.PullSeg * peers)()
+    off = 0
+    for r in range(peers):
+        segs[r] = _lib.PullSeg(srcs[r].data_ptr(), lists[r].data_ptr(), pad.data_ptr() + r * 8, int(lists[r].numel()), off)
+        off += int(lists[r].numel())
+    dd = 2 if dtype == torch.float32 else 11
+    for ctas in (0, 3):
+        dst.fill_(3.0)
+        assert L.ofspmm_pull_rows_multi(dst.data_ptr(), n, n, segs, peers, epoch, n, dd, 5, ctas, stream) == 0
+        torch.cuda.synchronize()
+        assert torch.equal(dst, torch.cat([srcs[r][lists[r].long()] for r in range(peers)]))
+    # combine: acc[row] += partial rows of every "peer", in segment order, fp32 accumulator
+    acc = torch.randn(shard, n, generator=g).to(DEV)
+    want = acc.clone()
+    parts, invs = [], []
+    csegs = (_lib.CombineSeg * peers)()
+    for r in range(peers):
+        part = torch.randn(int(lists[r].numel()), n, generator=g).to(dtype).to(DEV)
+        inv = torch.full((shard,), -1, dtype=torch.int32, device=DEV)
+        inv[lists[r].long()] = torch.arange(lists[r].numel(), dtype=torch.int32, device=DEV)
+        parts.append(part)
+        invs.append(inv)
+        csegs[r] = _lib.CombineSeg(part.data_ptr(), inv.data_ptr(), pad.data_ptr() + r * 8)
+        want[lists[r].long()] += part.float()
+    assert L.ofspmm_combine_rows_multi(acc.data_ptr(), n, n, csegs, peers, epoch, shard, n, dd, 0, stream) == 0
+    torch.cuda.synchronize()
+    assert torch.equal(acc, want)
