@@ -637,7 +637,10 @@ int launch_combine_rows_multi(float* acc, int64_t ld_acc, int64_t ld_src, const 
   if (nseg < 0 || nseg > kMaxSegs) return OFSPMM_ERR_INVALID_ARG;
   if (src_dtype != OFSPMM_DTYPE_FLOAT && src_dtype != OFSPMM_DTYPE_BFLOAT16) return OFSPMM_ERR_UNSUPPORTED_DTYPE;
   const size_t es = src_dtype == OFSPMM_DTYPE_FLOAT ? 4 : 2;
-  if ((n * es) % 16 != 0 || (ld_src * es) % 16 != 0 || ld_acc % 8 != 0 || (reinterpret_cast<uintptr_t>(acc) & 31))
+  // one 16-byte source unit = 4 fp32 (16 B of fp32 accumulator) or 8 bf16 (32 B of accumulator)
+  const size_t acc_unit = src_dtype == OFSPMM_DTYPE_FLOAT ? 16 : 32;
+  if ((n * es) % 16 != 0 || (ld_src * es) % 16 != 0 || (ld_acc * 4) % acc_unit != 0 ||
+      (reinterpret_cast<uintptr_t>(acc) & (acc_unit - 1)))
     return OFSPMM_ERR_INVALID_ARG;
   if (nseg == 0 || rows == 0 || n == 0) return OFSPMM_OK;
   CombineArgs a;
