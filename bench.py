@@ -232,11 +232,12 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------
 # verification of the timed outputs against the oracle (sampled rows, any size)
 
-def verify_sample(A, B_full, dY_full, C_blk, r0, r1, dB_shard, s0, s1, dtype, nsample=256, seed=7, relu=False,
+def verify_sample(A, B_full, dY_full, C_blk, r0, r1, dB_shard, shard_ids, dtype, nsample=256, seed=7, relu=False,
                   only_c=False):
     """>= nsample rows of C and of dB taken from the buffers the timed loop wrote, against the fp64
     oracle on exactly those rows (SURVEY.md §8c tolerances).  A / B_full / dY_full are the whole
-    operands on this rank's device; C_blk = rows [r0, r1) of C, dB_shard = rows [s0, s1) of dB."""
+    operands on this rank's device; C_blk = rows [r0, r1) of C; row i of dB_shard is row shard_ids[i]
+    of dB (global ids, ascending — contiguous or block-cyclic ownership)."""
     import numpy as np
     import torch
     from oracle import oracle as O
@@ -269,7 +270,9 @@ def verify_sample(A, B_full, dY_full, C_blk, r0, r1, dB_shard, s0, s1, dtype, ns
         res["ok"] = res["C_ok"]
         return res
     # ---- dB rows (= columns of A): every non-zero of the sampled columns, over the whole matrix
-    cols_s = torch.unique(torch.randint(s0, max(s0 + 1, s1), (nsample,), generator=g)).to(A.crow.device)
+    shard_ids = shard_ids.to(A.crow.device).long()
+    pick = torch.unique(torch.randint(0, max(1, shard_ids.numel()), (nsample,), generator=g)).to(A.crow.device)
+    cols_s = shard_ids[pick]                                   # ascending, like shard_ids
     hit = torch.isin(A.col, cols_s.to(A.col.dtype))
     p = torch.nonzero(hit).flatten()
     r_of = torch.searchsorted(A.crow.long(), p, right=True) - 1
@@ -283,7 +286,7 @@ def verify_sample(A, B_full, dY_full, C_blk, r0, r1, dB_shard, s0, s1, dtype, ns
     tval = A.val[p].float().cpu().numpy()
     want = O.spmm_f64(tcrow, inv.cpu().numpy(), tval, dYh, max(1, urow.numel()))
     amax = O.spmm_absmax(tcrow, inv.cpu().numpy(), tval, dYh, max(1, urow.numel()))
-    got = dB_shard[(cols_s - s0)].float().cpu().numpy().astype(np.float64)
+    got = dB_shard[pick].float().cpu().numpy().astype(np.float64)
     # bf16 on several ranks: each rank's partial column sum is rounded to bf16 for transport
     tol = (O.fp32_tolerance(want, amax, np.diff(tcrow)) + 2.0 ** -20 * np.abs(want)) if f32 else \
         (1e-2 * np.abs(want) + 2.0 ** -7 * amax * (1 + np.sqrt(np.diff(tcrow)))[:, None])
@@ -446,6 +449,8 @@ def main():
     ap.add_argument("--buckets", type=int, default=1, help="N>1, pull: remote column buckets (accumulate passes)")
     ap.add_argument("--tasks-per-warp", type=int, default=4, help="N>1: CTAs of the overlapped products retire after k tasks")
     ap.add_argument("--pull-ctas", type=int, default=64, help="N>1, pull: grid cap of the peer-pull kernels")
+    ap.add_argument("--layout", default="auto", choices=["auto", "block", "cyclic"],
+                    help="N>1, pull: ownership of B / dB rows (auto = block-cyclic when contiguous blocks would skew the egress)")
     args = ap.parse_args()
     args.warmup = max(3, args.warmup)
     if args.impl == "reference":
@@ -489,13 +494,16 @@ def main():
         dmod = __import__("importlib").import_module("of-spmm_b200.dist")
         if args.scheme == "pull":
             runner = dmod.ShardedSpmm(A, n, dtype, rank, world, dev, buckets=args.buckets,
-                                      tasks_per_warp=args.tasks_per_warp, pull_ctas=args.pull_ctas)
+                                      tasks_per_warp=args.tasks_per_warp, pull_ctas=args.pull_ctas, shard_layout=args.layout)
             xb = runner.exchange_bytes()
+            detail["shard_layout"] = runner.layout + (f" (blocks of {runner.cyc} rows dealt round-robin)" if runner.layout == "cyclic" else "")
             detail["exchange"] = {"pulled_bytes_per_product_rank0": xb["pulled"], "all_gather_bytes_per_product": xb["all_gather"],
                                   "local_nnz_fraction_rank0": round(xb["local_nnz_fraction"], 4)}
             parallelism = (f"row-block x{world} (nnz-balanced whole rows), B/dB row-sharded; needed-rows exchange over peer "
                            f"memory (comm={runner.comm}): local columns compute while {args.buckets} remote bucket(s) are pulled "
-                           f"with ofspmm_gather_rows, then accumulate passes; dB partials pulled + added in rank order")
+                           f"by one flag-synchronised TMA kernel (ofspmm_pull_rows_multi), then accumulate passes; dB partials "
+                           f"published, then combined in rank order by one kernel (ofspmm_combine_rows_multi); the two "
+                           f"products are interleaved in ShardedSpmm.step")
         else:
             runner = dmod.AllGatherSpmm(A, n, dtype, rank, world, dev, tasks_per_warp=args.tasks_per_warp or 2)
             parallelism = (f"row-block x{world}, round-1 scheme: ncclAllGather(B) overlapped with A^T*dY, ncclReduceScatter(dB) "
@@ -504,7 +512,7 @@ def main():
         step = lambda: runner.step(B_in, dY_in)
         fwd_only = lambda: runner.forward(B_in)
         plan_ms = None
-        r0, r1, s0, s1 = runner.r0, runner.r1, runner.lo, runner.hi
+        r0, r1, shard_ids = runner.r0, runner.r1, runner.shard_ids
         outputs = lambda: (runner._c, runner._db)
     else:
         t0 = time.perf_counter()
@@ -524,7 +532,7 @@ def main():
         detail["variant"] = {"forward": plan.variant_name(), "backward (forward kernel on A^T)": plan.variant_name(True),
                              "chosen_from": "row-length histogram (ofspmm_row_hist -> ofspmm_choose_variant), plan built once",
                              "row_hist_log2": [int(x) for x in plan.hist.tolist()[:24]]}
-        r0, r1, s0, s1 = 0, A.rows, 0, A.cols
+        r0, r1, shard_ids = 0, A.rows, torch.arange(A.cols, device=dev)
         outputs = lambda: (C, dB)
 
     def barrier():
@@ -554,7 +562,7 @@ def main():
     verified = None
     if not args.no_verify:
         c_out, db_out = outputs()
-        verified = verify_sample(A, B, dY, c_out, r0, r1, db_out, s0, s1, dtype)
+        verified = verify_sample(A, B, dY, c_out, r0, r1, db_out, shard_ids, dtype)
     # dominant kernel (forward): its own CUDA-event loop right after, same residency / clocks
     for _ in range(2):
         fwd_only()
@@ -596,7 +604,7 @@ def main():
     if not args.no_e2e and world == 1:
         e2e, C_h, dB_h = _e2e_pipelined(args, ofs, ops, A, B, dY, n, dtype, dev, flops_step)
         if not args.no_verify:   # what came back to the host is checked too
-            ve = verify_sample(A, B, dY, C_h.to(dev), 0, A.rows, dB_h.to(dev), 0, A.cols, dtype, seed=9)
+            ve = verify_sample(A, B, dY, C_h.to(dev), 0, A.rows, dB_h.to(dev), torch.arange(A.cols, device=dev), dtype, seed=9)
             e2e["verified"] = ve["ok"]
         del C_h, dB_h
         if dtype == torch.float32:

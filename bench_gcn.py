@@ -105,7 +105,7 @@ def main(args):
     if not args.no_verify:
         Z1_full = X @ model.W1
         h1 = sh.forward(model.local_rows(Z1_full), out=model._h1, relu=True, slot=0)[:m].clone()
-        v1 = bench.verify_sample(A, Z1_full, None, h1, sh.r0, sh.r1, None, 0, 0, torch.float32, relu=True, only_c=True)
+        v1 = bench.verify_sample(A, Z1_full, None, h1, sh.r0, sh.r1, None, None, torch.float32, relu=True, only_c=True)
         # layer 2 needs H1 of every rank: all ranks hold the same graph and weights, so recompute the sampled rows' inputs
         verified = {"H1_rows": v1["C_rows"], "H1_ok": v1["C_ok"], "loss": float(loss)}
         verified["ok"] = bool(v1["C_ok"]) and bool(torch.isfinite(loss))

@@ -219,11 +219,17 @@ class ShardedSpmm:
 
     def __init__(self, A: CsrMatrix, n: int, dtype: torch.dtype, rank: int, world: int, device, *,
                  buckets: int = 1, tasks_per_warp: int = 4, pull_ctas: int = 64, group=None,
-                 compute=None, transport: Optional[str] = None, shard_like_rows: bool = False, slots: int = 1):
+                 compute=None, transport: Optional[str] = None, shard_like_rows: bool = False, slots: int = 1,
+                 shard_layout: str = "auto", cyclic_block: int = 256):
         """``shard_like_rows`` (square A): shard B / dB by the SAME boundaries as the row blocks, so
         the output block of one product is the input shard of the next (GCN layers chain without a
-        re-shard); default: equal shards of ceil(K/world) rows.  ``slots``: independent sets of
-        exchange buffers over the one shared structure (one per layer of a model)."""
+        re-shard).  Otherwise ``shard_layout`` decides which rank owns which row of B / dB:
+        "block" = contiguous equal blocks of ceil(K/world) rows; "cyclic" = blocks of ``cyclic_block``
+        rows dealt round-robin, which spreads the hub columns of a skewed graph (R-MAT keeps them at
+        the low ids) over all owners — with contiguous blocks one rank would have to serve most of
+        what every other rank pulls, and its NVLink egress becomes the bottleneck; "auto" measures
+        that egress skew once and picks.  ``slots``: independent sets of exchange buffers over the
+        one shared structure (one per layer of a model)."""
         assert A.rows >= world, "fewer rows than ranks"
         self.rank, self.world, self.device, self.group = rank, world, device, group
         self.n, self.dtype = n, dtype
@@ -240,15 +246,37 @@ class ShardedSpmm:
         if shard_like_rows:
             assert A.rows == A.cols, "shard_like_rows needs a square matrix"
             self.col_bounds = [int(b) for b in self.bounds]
+            shard_layout = "block"
         else:
             eq = shard_rows_count(A.cols, world)
             self.col_bounds = [min(A.cols, s * eq) for s in range(world)] + [A.cols]
-        self.lo, self.hi = self.col_bounds[rank], self.col_bounds[rank + 1]
-        self.shard = max(1, max(self.col_bounds[s + 1] - self.col_bounds[s] for s in range(world))) if shard_like_rows \
-            else shard_rows_count(A.cols, world)                     # rows of every shard buffer (padded)
-        self.kp = self.shard * world
+        self.cyc = max(1, int(cyclic_block))
         self.slots = slots
         m = blk.rows
+        col = blk.col.long()
+        valid = (col >= 0) & (col < A.cols)
+        touched = torch.unique(col[valid])
+        if shard_layout == "auto":
+            # rows every OTHER rank would pull from each owner under contiguous blocks; the busiest
+            # owner's egress bounds the exchange
+            self.layout = "block"
+            own_blk, _ = self._owner_local(touched)
+            demand = torch.bincount(own_blk[own_blk != rank], minlength=world).to(torch.float64)
+            if world > 1:
+                dist.all_reduce(demand, group=group)
+            skew = float(demand.max() / demand.mean().clamp(min=1.0))
+            shard_layout = "cyclic" if (world > 2 and skew > 1.5) else "block"
+            self.egress_skew_block = skew
+        self.layout = shard_layout
+        ids_all = torch.arange(A.cols, device=col.device)
+        own_all, _ = self._owner_local(ids_all)
+        counts = torch.bincount(own_all, minlength=world)
+        self.shard_ids = ids_all[own_all == rank]                     # global ids of my shard rows, in local order
+        self.own = int(self.shard_ids.numel())
+        self.shard = max(1, int(counts.max()))                       # rows of every shard buffer (padded)
+        self.kp = self.shard * world
+        self.lo, self.hi = (self.col_bounds[rank], self.col_bounds[rank + 1]) if self.layout == "block" else (None, None)
+        del ids_all, own_all
         if transport is None:
             nccl = world > 1 and dist.is_initialized() and dist.get_backend(group) == "nccl"
             transport = "symm" if nccl else "gather"
@@ -259,31 +287,28 @@ class ShardedSpmm:
         nb = max(1, min(buckets, world - 1)) if world > 1 else 0
         ring = [(rank + d) % world for d in range(1, world)]
         chunk = [ring[(i * len(ring)) // nb:((i + 1) * len(ring)) // nb] for i in range(nb)] if nb else []
-        col = blk.col.long()
         lens = blk.row_lengths()
         rows_of = torch.repeat_interleave(torch.arange(m, device=col.device), lens)
-        cb = torch.tensor(self.col_bounds, dtype=torch.int64, device=col.device)
-        valid = (col >= 0) & (col < A.cols)
-        owner = (torch.searchsorted(cb, col.clamp(0, max(A.cols - 1, 0)), right=True) - 1).clamp(0, world - 1)
+        owner, _ = self._owner_local(col.clamp(0, max(A.cols - 1, 0)))
         gid_of_shard = torch.zeros(world + 1, dtype=torch.int64, device=col.device)
         for g, shards in enumerate(chunk, 1):
             for s in shards:
                 gid_of_shard[s] = g
         gid = torch.where(valid, gid_of_shard[owner.clamp(0, world)], torch.zeros_like(owner))  # skipped entries: bucket 0
-        touched = torch.unique(col[valid])
-        t_owner = (torch.searchsorted(cb, touched, right=True) - 1).clamp(0, world - 1)
+        t_owner, t_local = self._owner_local(touched)
         remap = torch.full((A.cols + 1,), -1, dtype=torch.int64, device=col.device)
-        remap[self.lo:self.hi] = torch.arange(self.hi - self.lo, device=col.device)
+        remap[self.shard_ids] = torch.arange(self.own, device=col.device)
         self.sub: List[_SubCsr] = []
         seg_table = torch.zeros((world, 3), dtype=torch.int64)       # [owner s] -> (bucket, offset, count) on this rank
         send_lists: List[torch.Tensor] = [torch.empty(0, dtype=torch.int32, device=col.device) for _ in range(world)]
-        metas = [(0, [(rank, 0, self.hi - self.lo, None)], self.hi - self.lo)]
+        metas = [(0, [(rank, 0, self.own, None)], self.own)]
         for g, shards in enumerate(chunk, 1):
             off, segs = 0, []
             for s in shards:
-                lst = touched[t_owner == s]
+                sel = t_owner == s
+                lst = touched[sel]
                 remap[lst] = off + torch.arange(lst.numel(), device=col.device)
-                local_ids = (lst - self.col_bounds[s]).to(torch.int32)
+                local_ids = t_local[sel].to(torch.int32)                 # rows of the owner's shard (its local order)
                 segs.append((s, off, int(lst.numel()), local_ids))
                 seg_table[s] = torch.tensor([g, off, int(lst.numel())])
                 send_lists[s] = local_ids
@@ -298,7 +323,7 @@ class ShardedSpmm:
             crow[1:] = torch.cumsum(cnt, 0)
             sc = _SubCsr()
             sc.A = CsrMatrix(crow.to(blk.crow.dtype), new_col[pos].to(blk.col.dtype), blk.val[pos].contiguous(), m,
-                             max(ncols if g > 0 else self.hi - self.lo, 1))
+                             max(ncols if g > 0 else self.own, 1))
             sc.pos, sc.segs, sc.ncols = pos, segs, ncols
             sc.plan = self.cp.plan(sc.A.crow, sc.A.col, m, sc.A.cols, n, dtype) if getattr(self.cp, "is_cuda", False) else None
             sc.Bc = [torch.zeros((max(ncols, 1), n), dtype=dtype, device=device) for _ in range(slots)] if g > 0 else None
@@ -355,9 +380,18 @@ class ShardedSpmm:
     def shard_rows(self, B_full: torch.Tensor) -> torch.Tensor:
         """This rank's row shard of a K×n dense operand (zero-padded to the shard buffer size)."""
         out = torch.zeros((self.shard, self.n), dtype=B_full.dtype, device=B_full.device)
-        if self.hi > self.lo:
-            out[: self.hi - self.lo] = B_full[self.lo:self.hi]
+        if self.own:
+            out[: self.own] = B_full[self.shard_ids.to(B_full.device)]
         return out
+
+    def _owner_local(self, cols: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        """(owner rank, row inside the owner's shard) of global B-row ids under this layout."""
+        if getattr(self, "layout", "block") == "cyclic":
+            q = torch.div(cols, self.cyc, rounding_mode="floor")
+            return q % self.world, torch.div(q, self.world, rounding_mode="floor") * self.cyc + cols % self.cyc
+        cb = torch.tensor(self.col_bounds, dtype=torch.int64, device=cols.device)
+        owner = (torch.searchsorted(cb, cols, right=True) - 1).clamp(0, self.world - 1)
+        return owner, cols - cb[owner]
 
     def shard_rows_out(self, dY_full: torch.Tensor) -> torch.Tensor:
         """The rows of an M×n tensor that belong to this rank's row block of A."""
@@ -415,12 +449,10 @@ class ShardedSpmm:
         arr = self._sig[(kind, slot)]
         ops.check(_lib.lib().ofspmm_signal_peers(arr, len(arr), epoch, torch.cuda.current_stream().cuda_stream), "signal_peers")
 
-    # ------------------------------------------------------------------ forward
-    def forward(self, B_shard: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
-                bias: Optional[torch.Tensor] = None, relu: bool = False, slot: int = 0) -> torch.Tensor:
-        """C_blk[m, n] = A_blk · B, B given as this rank's shard.  ``bias`` / ``relu`` are fused into
-        the last accumulate pass."""
-        st, cp, C = self.st, self.cp, (out if out is not None else self._c)
+    # ------------------------------------------------------------------ forward, in phases
+    def _fwd_begin(self, B_shard, slot):
+        """Publish this rank's shard for a new epoch, tell the peers, start pulling theirs."""
+        st, cp = self.st, self.cp
         self._fwd_epoch[slot] += 1
         epoch = self._fwd_epoch[slot]
         par = epoch & 1
@@ -429,7 +461,6 @@ class ShardedSpmm:
         if slot == 0:
             self.B_pub = B_pub
         cur = st.cur()
-        last = len(self.sub) - 1
         ev_g = []
         ev_in = st.record() if self.world > 1 else None   # the pulled-row buffers of the previous step are free
         if B_shard is not None and B_shard.data_ptr() != B_pub.data_ptr():
@@ -461,47 +492,68 @@ class ShardedSpmm:
                     ev_g.append(st.record(st.comm))
                 self.T.barrier(1)
                 self._ev_pulled[slot] = st.record(st.comm)
-        ep = dict(bias=bias, relu=relu)
+        return B_pub, ev_g
+
+    def _overlap_opts(self):
+        # products that overlap the exchange leave one CTA slot per SM to its small kernels
+        return dict(reserve_ctas=1) if self.fused else dict(tasks_per_warp=self.tpw)
+
+    def _fwd_local(self, B_pub, C, ep):
+        last = len(self.sub) - 1
         wide = self._wide and last > 0       # bf16: fp32 running sums between the passes
         s0 = self.sub[0]
-        # products that overlap the exchange leave one CTA slot per SM to its 128-thread kernels
-        ov = dict(reserve_ctas=1) if self.fused else dict(tasks_per_warp=self.tpw)
-        cp.spmm(s0.A, B_pub[: s0.A.cols], C, plan=s0.plan, **(ov if last > 0 else {}), **(ep if last == 0 else {}),
-                **(dict(acc32=self._acc32, acc32_out=True) if wide else {}))
+        self.cp.spmm(s0.A, B_pub[: s0.A.cols], C, plan=s0.plan, **(self._overlap_opts() if last > 0 else {}),
+                     **(ep if last == 0 else {}), **(dict(acc32=self._acc32, acc32_out=True) if wide else {}))
+
+    def _fwd_remote(self, ev_g, C, ep, slot):
+        st, cur, last = self.st, self.st.cur(), len(self.sub) - 1
+        wide = self._wide and last > 0
         for g, sc in enumerate(self.sub[1:], 1):
             st.wait(cur, ev_g[g - 1])
             acc = dict(acc32=self._acc32, acc32_in=True, acc32_out=g < last) if wide else dict(accumulate=True)
-            cp.spmm(sc.A, sc.Bc[slot], C, plan=sc.plan, **(ov if g < last else {}), **acc, **(ep if g == last else {}))
+            self.cp.spmm(sc.A, sc.Bc[slot], C, plan=sc.plan, **(self._overlap_opts() if g < last else {}), **acc,
+                         **(ep if g == last else {}))
+
+    def forward(self, B_shard: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
+                bias: Optional[torch.Tensor] = None, relu: bool = False, slot: int = 0) -> torch.Tensor:
+        """C_blk[m, n] = A_blk · B, B given as this rank's shard.  ``bias`` / ``relu`` are fused into
+        the last accumulate pass."""
+        C = out if out is not None else self._c
+        ep = dict(bias=bias, relu=relu)
+        B_pub, ev_g = self._fwd_begin(B_shard, slot)
+        self._fwd_local(B_pub, C, ep)
+        self._fwd_remote(ev_g, C, ep, slot)
         return C
 
-    # ------------------------------------------------------------------ backward wrt B
-    def backward(self, dY_blk: torch.Tensor, slot: int = 0) -> torch.Tensor:
-        """dB_shard[shard, n] = rows of A^T·dY owned by this rank, summed over ranks in rank order
-        (rows past this rank's shard size stay zero)."""
+    # ------------------------------------------------------------------ backward wrt B, in phases
+    def _bwd_remote(self, dY_blk, slot):
+        """The partial rows other ranks own, published and signalled first: peers are waiting for them."""
         st, cp = self.st, self.cp
         cur = st.cur()
-        dY_blk = dY_blk.contiguous()
-        db = self._dbs[slot]
         self._bwd_epoch[slot] += 1
         epoch = self._bwd_epoch[slot]
         par = epoch & 1
-        ov = dict(reserve_ctas=1) if self.fused else dict(tasks_per_warp=self.tpw)
         if not self.fused:
             st.wait(cur, self._ev_consumed[slot])     # emulation: peers finished reading the previous partials
-        for sc in self.sub[1:]:                       # remote partials first: peers are waiting for them
+        for sc in self.sub[1:]:
             pub = self.T.bufs[f"{sc.dBc_name}.{slot}.{par}"][0]
-            cp.spmm_t(sc.A, dY_blk, pub[: sc.A.cols], plan=sc.plan, **ov)
+            cp.spmm_t(sc.A, dY_blk, pub[: sc.A.cols], plan=sc.plan, **self._overlap_opts())
         if self.fused:
             self._signal(1, slot, epoch)              # my partials for this epoch are complete
         ev_rem = st.record() if self.world > 1 else None
-        s0 = self.sub[0]
-        acc = self._db32 if self._wide else db           # bf16: the ranks' partials are summed in fp32
-        if self._wide:
-            cp.spmm_t(s0.A, dY_blk, db[: s0.A.cols], plan=s0.plan, acc32_out=self._db32[: s0.A.cols])
+        return epoch, par, ev_rem
+
+    def _bwd_local(self, dY_blk, slot):
+        s0, db = self.sub[0], self._dbs[slot]
+        if self._wide:                                # bf16: the ranks' partials are summed in fp32
+            self.cp.spmm_t(s0.A, dY_blk, db[: s0.A.cols], plan=s0.plan, acc32_out=self._db32[: s0.A.cols])
         else:
-            cp.spmm_t(s0.A, dY_blk, db[: s0.A.cols], plan=s0.plan)
-        if self.world == 1:
-            return db
+            self.cp.spmm_t(s0.A, dY_blk, db[: s0.A.cols], plan=s0.plan)
+
+    def _bwd_combine(self, epoch, par, ev_rem, slot):
+        st, cp, db = self.st, self.cp, self._dbs[slot]
+        cur = st.cur()
+        acc = self._db32 if self._wide else db
         if self.fused:
             from . import _lib
             segs, nseg = self._comb[(slot, par)]
@@ -530,6 +582,16 @@ class ShardedSpmm:
         st.wait(cur, self._ev_consumed[slot])
         return db
 
+    def backward(self, dY_blk: torch.Tensor, slot: int = 0) -> torch.Tensor:
+        """dB_shard[shard, n] = rows of A^T·dY owned by this rank, summed over ranks in rank order
+        (rows past this rank's shard size stay zero)."""
+        dY_blk = dY_blk.contiguous()
+        epoch, par, ev_rem = self._bwd_remote(dY_blk, slot)
+        self._bwd_local(dY_blk, slot)
+        if self.world == 1:
+            return self._dbs[slot]
+        return self._bwd_combine(epoch, par, ev_rem, slot)
+
     # ------------------------------------------------------------------ SDDMM value gradient
     def sddmm(self, dY_blk: torch.Tensor, slot: int = 0) -> torch.Tensor:
         """dval of this rank's block, against the B rows the last ``forward`` of this slot holds
@@ -543,14 +605,28 @@ class ShardedSpmm:
         return dval
 
     def step(self, B_shard: torch.Tensor, dY_blk: torch.Tensor):
-        """One benchmark step: C_blk = A_blk·B and dB_shard = (A^T·dY)[own shard]."""
-        return self.forward(B_shard), self.backward(dY_blk)
+        """One benchmark step: C_blk = A_blk·B and dB_shard = (A^T·dY)[own shard] — two independent
+        products, interleaved so that every exchange has the longest possible head start: publish B
+        and the remote partials of dB first (both signalled to the peers at once), compute the two
+        local parts while the pulls fly, then the remote forward pass and the combine, whose inputs
+        have long arrived."""
+        if self.world == 1:
+            return self.forward(B_shard), self.backward(dY_blk)
+        dY_blk = dY_blk.contiguous()
+        C, ep = self._c, dict(bias=None, relu=False)
+        B_pub, ev_g = self._fwd_begin(B_shard, 0)
+        epoch, par, ev_rem = self._bwd_remote(dY_blk, 0)
+        self._fwd_local(B_pub, C, ep)
+        self._bwd_local(dY_blk, 0)
+        self._fwd_remote(ev_g, C, ep, 0)
+        db = self._bwd_combine(epoch, par, ev_rem, 0)
+        return C, db
 
     def exchange_bytes(self) -> Dict[str, float]:
         """Bytes this rank receives per product, next to what a full all-gather would move."""
         s = 4 if self.dtype == torch.float32 else 2
         return {"pulled": float(self.pulled_rows) * self.n * s,
-                "all_gather": float(self.cols - (self.hi - self.lo)) * self.n * s,
+                "all_gather": float(self.cols - self.own) * self.n * s,
                 "local_nnz_fraction": self.local_fraction}
 
 
@@ -575,6 +651,8 @@ class AllGatherSpmm:
         self.shard = shard_rows_count(A.cols, world)
         self.kp = self.shard * world
         self.lo, self.hi = min(A.cols, rank * self.shard), min(A.cols, (rank + 1) * self.shard)
+        self.shard_ids = torch.arange(self.lo, self.hi, device=A.crow.device)
+        self.own = self.hi - self.lo
         blk = self.A_blk
         self.plan = self.cp.plan(blk.crow, blk.col, blk.rows, blk.cols, n, dtype) if getattr(self.cp, "is_cuda", False) else None
         self._b_full = torch.empty((self.kp, n), dtype=dtype, device=device)

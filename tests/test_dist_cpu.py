@@ -65,7 +65,7 @@ class OracleCompute:
         return dst
 
 
-def _worker(rank, world, port, n, scheme, buckets, q):
+def _worker(rank, world, port, n, scheme, buckets, layout, q):
     sys.path.insert(0, ROOT)
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -79,13 +79,17 @@ def _worker(rank, world, port, n, scheme, buckets, q):
         dY = ofs.graphs.upstream_grad(A.rows, n, 6)
         bias = torch.linspace(-1, 1, n)
         if scheme == "pull":
-            sh = dmod.ShardedSpmm(A, n, torch.float32, rank, world, "cpu", buckets=buckets, compute=OracleCompute())
+            sh = dmod.ShardedSpmm(A, n, torch.float32, rank, world, "cpu", buckets=buckets, compute=OracleCompute(),
+                                  shard_layout=layout, cyclic_block=16)
         else:
             sh = dmod.AllGatherSpmm(A, n, torch.float32, rank, world, "cpu", compute=OracleCompute())
         out = {}
         for it in range(2):                             # twice: the publish / consume hand-shake repeats
             C_blk, dB_shard = sh.step(sh.shard_rows(B), sh.shard_rows_out(dY))
         out["C"], out["dB"] = C_blk.clone().numpy(), dB_shard.clone().numpy()
+        # forward and backward called separately must agree with the interleaved step
+        C2, dB2 = sh.forward(sh.shard_rows(B)).clone(), sh.backward(sh.shard_rows_out(dY)).clone()
+        out["sep_equals_step"] = bool(torch.equal(C2, torch.from_numpy(out["C"]))) and bool(torch.equal(dB2, torch.from_numpy(out["dB"])))
         if scheme == "pull":
             out["dval"] = sh.sddmm(sh.shard_rows_out(dY)).numpy()
             out["C_ep"] = sh.forward(sh.shard_rows(B), bias=bias, relu=True).clone().numpy()
@@ -94,6 +98,7 @@ def _worker(rank, world, port, n, scheme, buckets, q):
             # new edge values, same structure
             sh.update_values(sh.A_blk.val * -2.0)
             out["C_scaled"] = sh.forward(sh.shard_rows(B)).clone().numpy()
+        out["shard_ids"], out["layout"] = sh.shard_ids.numpy(), getattr(sh, "layout", "block")
         q.put((rank, sh.bounds, sh.r0, sh.r1, sh.shard, out))
         dist.barrier()
         dist.destroy_process_group()
@@ -103,16 +108,17 @@ def _worker(rank, world, port, n, scheme, buckets, q):
         os._exit(1)
 
 
-@pytest.mark.parametrize("world,n,scheme,buckets", [(2, 16, "pull", 1), (3, 12, "pull", 1), (3, 8, "pull", 2),
-                                                    (2, 12, "allgather", 1)])
-def test_sharded_spmm_gloo(world, n, scheme, buckets):
+@pytest.mark.parametrize("world,n,scheme,buckets,layout", [(2, 16, "pull", 1, "auto"), (3, 12, "pull", 1, "block"),
+                                                           (3, 8, "pull", 2, "cyclic"), (4, 8, "pull", 1, "auto"),
+                                                           (2, 12, "allgather", 1, "block")])
+def test_sharded_spmm_gloo(world, n, scheme, buckets, layout):
     sys.path.insert(0, ROOT)
     import ofspmm_b200 as ofs
     from oracle import oracle as O
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, n, scheme, buckets, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n, scheme, buckets, layout, q)) for r in range(world)]
     for p in procs:
         p.start()
     results = []
@@ -144,10 +150,21 @@ def test_sharded_spmm_gloo(world, n, scheme, buckets):
     assert C.shape == C_ref.shape
     np.testing.assert_allclose(C, C_ref, rtol=1e-4, atol=1e-4)
     shard = results[0][4]
-    dB = np.concatenate([r[5]["dB"] for r in results], axis=0)
-    assert dB.shape[0] == shard * world >= A.cols
-    np.testing.assert_allclose(dB[: A.cols], dB_ref, rtol=1e-4, atol=1e-4)
-    assert np.all(dB[A.cols:] == 0)                            # padding rows stay zero
+    dB = np.full((A.cols, n), np.nan)
+    owned = 0
+    for r in results:                                         # row i of a shard is row shard_ids[i] of dB
+        ids = r[5]["shard_ids"]
+        assert r[5]["dB"].shape[0] == shard and len(ids) <= shard
+        dB[ids] = r[5]["dB"][: len(ids)]
+        assert np.all(r[5]["dB"][len(ids):] == 0)            # padding rows stay zero
+        owned += len(ids)
+    assert owned == A.cols and not np.isnan(dB).any()         # every row of dB has exactly one owner
+    np.testing.assert_allclose(dB, dB_ref, rtol=1e-4, atol=1e-4)
+    if layout == "cyclic":
+        assert all(r[5]["layout"] == "cyclic" for r in results)
+        assert results[0][5]["shard_ids"][:17].tolist() == list(range(16)) + [16 * world]   # blocks of 16 dealt round-robin
+    assert all(r[5]["sep_equals_step"] for r in results)      # forward(); backward() == the interleaved step(), bit for bit
+    assert len({r[5]["layout"] for r in results}) == 1        # "auto" is a collective decision: all ranks agree
     if scheme != "pull":
         return
     dval = np.concatenate([r[5]["dval"] for r in results])

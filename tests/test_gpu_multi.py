@@ -64,22 +64,22 @@ def _worker(rank, world, port, cases, q):
             for _ in range(3):                                   # repeated steps: publish / consume hand-shake
                 C_blk, dB_sh = sh.step(Bs, dYs)
             torch.cuda.synchronize()
-            r0, r1, s0, s1 = sh.r0, sh.r1, sh.lo, sh.hi
+            r0, r1, sid = sh.r0, sh.r1, sh.shard_ids.cpu().numpy()
             lens = np.diff(crow)[r0:r1]
             got_c = C_blk.float().cpu().numpy().astype(np.float64)
             got_db = dB_sh.float().cpu().numpy().astype(np.float64)
             if dt == "fp32":
                 # the pull scheme adds one rounding per accumulate pass / per contributing rank
                 tol_c = O.fp32_tolerance(C64[r0:r1], amax[r0:r1], lens) + 2.0 ** -22 * np.abs(C64[r0:r1]) * (buckets + 1)
-                tol_db = O.fp32_tolerance(dB64[s0:s1], amax_t[s0:s1], cnt[s0:s1]) + 2.0 ** -22 * np.abs(dB64[s0:s1]) * world
+                tol_db = O.fp32_tolerance(dB64[sid], amax_t[sid], cnt[sid]) + 2.0 ** -22 * np.abs(dB64[sid]) * world
             else:
                 # bf16: C is rounded once (fp32 running sums between the passes).  dB: every rank's partial
                 # column sum travels as bf16 (one rounding of a sum of up to cnt terms each), the total
                 # is accumulated in fp32 and rounded once more
                 tol_c = 1e-2 * np.abs(C64[r0:r1]) + 2.0 ** -8 * amax[r0:r1]
-                tol_db = 1e-2 * np.abs(dB64[s0:s1]) + 2.0 ** -8 * amax_t[s0:s1] * (1 + np.sqrt(cnt[s0:s1]))[:, None]
+                tol_db = 1e-2 * np.abs(dB64[sid]) + 2.0 ** -8 * amax_t[sid] * (1 + np.sqrt(cnt[sid]))[:, None]
             ok_c = bool((np.abs(got_c - C64[r0:r1]) <= tol_c + 1e-30).all())
-            ok_db = bool((np.abs(got_db[: s1 - s0] - dB64[s0:s1]) <= tol_db + 1e-30).all()) and bool((got_db[s1 - s0:] == 0).all())
+            ok_db = bool((np.abs(got_db[: len(sid)] - dB64[sid]) <= tol_db + 1e-30).all()) and bool((got_db[len(sid):] == 0).all())
             ok_dv = ok_det = ok_ep = True
             if scheme == "pull":
                 p0, p1 = int(crow[r0]), int(crow[r1])
