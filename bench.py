@@ -449,6 +449,9 @@ def main():
     ap.add_argument("--buckets", type=int, default=1, help="N>1, pull: remote column buckets (accumulate passes)")
     ap.add_argument("--tasks-per-warp", type=int, default=4, help="N>1: CTAs of the overlapped products retire after k tasks")
     ap.add_argument("--pull-ctas", type=int, default=64, help="N>1, pull: grid cap of the peer-pull kernels")
+    ap.add_argument("--no-interleave", action="store_true", help="N>1, pull: step = forward(); backward() back to back")
+    ap.add_argument("--combine-ctas", type=int, default=0,
+                    help="N>1, pull: >0 runs the dB combine beside the last forward pass with that many CTAs")
     ap.add_argument("--layout", default="auto", choices=["auto", "block", "cyclic"],
                     help="N>1, pull: ownership of B / dB rows (auto = block-cyclic when contiguous blocks would skew the egress)")
     args = ap.parse_args()
@@ -494,8 +497,11 @@ def main():
         dmod = __import__("importlib").import_module("of-spmm_b200.dist")
         if args.scheme == "pull":
             runner = dmod.ShardedSpmm(A, n, dtype, rank, world, dev, buckets=args.buckets,
-                                      tasks_per_warp=args.tasks_per_warp, pull_ctas=args.pull_ctas, shard_layout=args.layout)
+                                      tasks_per_warp=args.tasks_per_warp, pull_ctas=args.pull_ctas, shard_layout=args.layout,
+                                      interleave=not args.no_interleave, combine_ctas=args.combine_ctas)
             xb = runner.exchange_bytes()
+            detail["step_order"] = ("interleaved" + (f", combine beside the last forward pass ({args.combine_ctas} CTAs)"
+                                                     if args.combine_ctas else "")) if runner.interleave else "forward(); backward()"
             detail["shard_layout"] = runner.layout + (f" (blocks of {runner.cyc} rows dealt round-robin)" if runner.layout == "cyclic" else "")
             detail["exchange"] = {"pulled_bytes_per_product_rank0": xb["pulled"], "all_gather_bytes_per_product": xb["all_gather"],
                                   "local_nnz_fraction_rank0": round(xb["local_nnz_fraction"], 4)}

@@ -220,7 +220,7 @@ class ShardedSpmm:
     def __init__(self, A: CsrMatrix, n: int, dtype: torch.dtype, rank: int, world: int, device, *,
                  buckets: int = 1, tasks_per_warp: int = 4, pull_ctas: int = 64, group=None,
                  compute=None, transport: Optional[str] = None, shard_like_rows: bool = False, slots: int = 1,
-                 shard_layout: str = "auto", cyclic_block: int = 256):
+                 shard_layout: str = "auto", cyclic_block: int = 256, interleave: bool = True, combine_ctas: int = 0):
         """``shard_like_rows`` (square A): shard B / dB by the SAME boundaries as the row blocks, so
         the output block of one product is the input shard of the next (GCN layers chain without a
         re-shard).  Otherwise ``shard_layout`` decides which rank owns which row of B / dB:
@@ -238,6 +238,9 @@ class ShardedSpmm:
         self.st = _Streams(device)
         self.tpw = tasks_per_warp if world > 1 else 0
         self.pull_ctas = pull_ctas
+        # step(): interleave the two products; combine_ctas > 0 also runs the combine beside the last
+        # forward pass, on the communication stream, with that many CTAs
+        self.interleave, self.combine_ctas = interleave, combine_ctas
         # nnz-balanced whole-row blocks (device partitioner when the graph is on the GPU)
         self.bounds = ops.row_blocks(A.crow, A.nnz, world).cpu().tolist()
         self.r0, self.r1 = int(self.bounds[rank]), int(self.bounds[rank + 1])
@@ -505,13 +508,15 @@ class ShardedSpmm:
         self.cp.spmm(s0.A, B_pub[: s0.A.cols], C, plan=s0.plan, **(self._overlap_opts() if last > 0 else {}),
                      **(ep if last == 0 else {}), **(dict(acc32=self._acc32, acc32_out=True) if wide else {}))
 
-    def _fwd_remote(self, ev_g, C, ep, slot):
+    def _fwd_remote(self, ev_g, C, ep, slot, shared=False):
+        """``shared``: something else (the combine of an interleaved step) runs beside the last pass
+        too, so it also leaves a CTA slot per SM."""
         st, cur, last = self.st, self.st.cur(), len(self.sub) - 1
         wide = self._wide and last > 0
         for g, sc in enumerate(self.sub[1:], 1):
             st.wait(cur, ev_g[g - 1])
             acc = dict(acc32=self._acc32, acc32_in=True, acc32_out=g < last) if wide else dict(accumulate=True)
-            self.cp.spmm(sc.A, sc.Bc[slot], C, plan=sc.plan, **(self._overlap_opts() if g < last else {}), **acc,
+            self.cp.spmm(sc.A, sc.Bc[slot], C, plan=sc.plan, **(self._overlap_opts() if (g < last or shared) else {}), **acc,
                          **(ep if g == last else {}))
 
     def forward(self, B_shard: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
@@ -550,7 +555,7 @@ class ShardedSpmm:
         else:
             self.cp.spmm_t(s0.A, dY_blk, db[: s0.A.cols], plan=s0.plan)
 
-    def _bwd_combine(self, epoch, par, ev_rem, slot):
+    def _bwd_combine(self, epoch, par, ev_rem, slot, max_ctas=0):
         st, cp, db = self.st, self.cp, self._dbs[slot]
         cur = st.cur()
         acc = self._db32 if self._wide else db
@@ -560,7 +565,7 @@ class ShardedSpmm:
             if nseg:
                 # ONE launch adds every peer's partial rows, in rank order, each guarded by its flag
                 ops.check(_lib.lib().ofspmm_combine_rows_multi(acc.data_ptr(), self.n, self.n, segs, nseg, epoch, self.shard,
-                                                              self.n, ops._DENSE[self.dtype], 0, cur.cuda_stream),
+                                                              self.n, ops._DENSE[self.dtype], max_ctas, cur.cuda_stream),
                           "combine_rows_multi")
             if self._wide:
                 cp.cast_from_f32(db, self._db32)      # one rounding of the complete sum
@@ -610,14 +615,25 @@ class ShardedSpmm:
         and the remote partials of dB first (both signalled to the peers at once), compute the two
         local parts while the pulls fly, then the remote forward pass and the combine, whose inputs
         have long arrived."""
-        if self.world == 1:
+        if self.world == 1 or not self.interleave:
             return self.forward(B_shard), self.backward(dY_blk)
+        st = self.st
         dY_blk = dY_blk.contiguous()
         C, ep = self._c, dict(bias=None, relu=False)
         B_pub, ev_g = self._fwd_begin(B_shard, 0)
         epoch, par, ev_rem = self._bwd_remote(dY_blk, 0)
         self._fwd_local(B_pub, C, ep)
         self._bwd_local(dY_blk, 0)
+        if self.fused and self.combine_ctas > 0:
+            # the combine (peer reads over NVLink, latency bound) runs beside the remote forward pass
+            ev_loc = st.record()
+            with st.on_comm():
+                st.wait(st.comm, ev_loc)
+                db = self._bwd_combine(epoch, par, ev_rem, 0, max_ctas=self.combine_ctas)
+                ev_done = st.record(st.comm)
+            self._fwd_remote(ev_g, C, ep, 0, shared=True)
+            st.wait(st.cur(), ev_done)
+            return C, db
         self._fwd_remote(ev_g, C, ep, 0)
         db = self._bwd_combine(epoch, par, ev_rem, 0)
         return C, db

@@ -27,7 +27,7 @@ def _free_port():
 
 def _worker(rank, world, port, cases, q):
     import threading
-    threading.Timer(240.0, lambda: os._exit(3)).start()           # never hang the box
+    threading.Timer(400.0, lambda: os._exit(3)).start()           # never hang the box
     sys.path.insert(0, ROOT)
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -41,7 +41,8 @@ def _worker(rank, world, port, cases, q):
         from oracle import oracle as O
         dmod = importlib.import_module("of-spmm_b200.dist")
         report = []
-        for (graph, n, dt, scheme, buckets, tpw) in cases:
+        for (graph, n, dt, scheme, buckets, tpw, *more) in cases:
+            kw = more[0] if more else {}
             dtype = torch.float32 if dt == "fp32" else torch.bfloat16
             A = {"rmat": lambda: ofs.graphs.rmat_csr(13, 16, seed=4),
                  "reddit": lambda: ofs.graphs.reddit_like(64, seed=2),
@@ -57,7 +58,7 @@ def _worker(rank, world, port, cases, q):
             dv64, aabs = O.sddmm_f64(crow, col, dYf, Bf)
             Ad = A.to(dev)
             if scheme == "pull":
-                sh = dmod.ShardedSpmm(Ad, n, dtype, rank, world, dev, buckets=buckets, tasks_per_warp=tpw)
+                sh = dmod.ShardedSpmm(Ad, n, dtype, rank, world, dev, buckets=buckets, tasks_per_warp=tpw, **kw)
             else:
                 sh = dmod.AllGatherSpmm(Ad, n, dtype, rank, world, dev, tasks_per_warp=tpw)
             Bs, dYs = sh.shard_rows(B.to(dev)), sh.shard_rows_out(dY.to(dev))
@@ -90,13 +91,20 @@ def _worker(rank, world, port, cases, q):
                 # deterministic: a repeated step returns the same bits
                 c2, d2 = sh.step(Bs, dYs)
                 ok_det = bool(torch.equal(c2, C_blk)) and bool(torch.equal(d2, dB_sh))
+                # ... and so do the two products called one after the other (the step interleaves them)
+                c1, d1 = C_blk.clone(), dB_sh.clone()
+                c3 = sh.forward(Bs).clone()
+                d3 = sh.backward(dYs)
+                ok_det = ok_det and bool(torch.equal(c3, c1)) and bool(torch.equal(d3, d1))
+                if "shard_layout" in kw:
+                    ok_det = ok_det and sh.layout == kw["shard_layout"]
                 # fused epilogue on the last accumulate pass
                 bias = torch.linspace(-1, 1, n).to(dtype).to(dev)
                 ce = sh.forward(Bs, bias=bias, relu=True).float().cpu().numpy().astype(np.float64)
                 ref_e = np.maximum(C64[r0:r1] + bias.float().cpu().numpy().astype(np.float64)[None, :], 0)
                 ok_ep = bool((np.abs(ce - ref_e) <= tol_c + 2.0 ** (-22 if dt == "fp32" else -7) * (np.abs(ref_e) + 1) + 1e-30).all())
                 torch.cuda.synchronize()
-            report.append(dict(case=(graph, n, dt, scheme, buckets, tpw), C=ok_c, dB=ok_db, dval=ok_dv, det=ok_det, ep=ok_ep,
+            report.append(dict(case=(graph, n, dt, scheme, buckets, tpw, kw), C=ok_c, dB=ok_db, dval=ok_dv, det=ok_det, ep=ok_ep,
                                comm=sh.comm))
             del sh
         q.put((rank, report))
@@ -118,6 +126,10 @@ CASES = [
     ("rmat", 128, "fp32", "pull", 1, 0),
     ("reddit", 128, "fp32", "pull", 2, 2),
     ("products", 256, "bf16", "pull", 1, 4),
+    ("rmat", 128, "fp32", "pull", 1, 4, dict(shard_layout="cyclic", cyclic_block=64)),           # hub rows dealt round-robin
+    ("products", 256, "bf16", "pull", 1, 4, dict(shard_layout="cyclic", cyclic_block=32, combine_ctas=64)),
+    ("rmat", 128, "fp32", "pull", 2, 2, dict(combine_ctas=148)),      # combine beside the last forward pass
+    ("reddit", 128, "fp32", "pull", 1, 0, dict(interleave=False)),    # step = forward(); backward()
     ("rmat", 64, "fp32", "allgather", 1, 2),
     ("reddit", 128, "fp32", "allgather", 1, 0),
 ]
@@ -136,7 +148,7 @@ def test_sharded_spmm_nccl_vs_oracle(world):
         p.start()
     results = []
     for _ in range(world):
-        r = q.get(timeout=300)
+        r = q.get(timeout=420)
         if r[0] == "error":
             for p in procs:
                 p.kill()
