@@ -113,6 +113,9 @@ enum {
   OFSPMM_VARIANT_ITEMS64 = 1,  /* 64 merge items per warp task (small problems: 4x more warps)      */
   OFSPMM_VARIANT_ROWPAR = 2,   /* sub-warp per row instead of nnz-parallel groups (short rows x
                                   narrow dense operand)                                              */
+  OFSPMM_VARIANT_ROWS = 4,     /* whole rows per lane group, ONE launch, no partition / carries /
+                                  fix-up: small problems whose longest row is short (needs int32
+                                  indices and 16-byte dense rows of <= 512 bytes, else ITEMS64)      */
   OFSPMM_VARIANT_EXPLICIT = 0x100
 };
 

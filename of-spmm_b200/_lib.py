@@ -31,7 +31,7 @@ EXPORTS = (
 
 # ofspmm_opts.flags / variant codes (include/ofspmm.h)
 FWD_ACCUMULATE, FWD_BIAS, FWD_RELU, ORDER_DYNAMIC, ORDER_STATIC, FWD_ACC32_IN, FWD_ACC32_OUT = 1, 2, 4, 8, 16, 32, 64
-VARIANT_AUTO, VARIANT_ITEMS64, VARIANT_ROWPAR, VARIANT_EXPLICIT = 0, 1, 2, 0x100
+VARIANT_AUTO, VARIANT_ITEMS64, VARIANT_ROWPAR, VARIANT_ROWS, VARIANT_EXPLICIT = 0, 1, 2, 4, 0x100
 
 
 class OfspmmLibraryError(ImportError):

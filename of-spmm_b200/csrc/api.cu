@@ -133,6 +133,8 @@ int run_fwd(const ofspmm_csr* A, const void* B, int64_t ldb, void* C, int64_t ld
     // a plan built for another task size is a caller bug, not something to paper over
     if (opts->plan_bytes != plan_bytes_for(A->rows, A->nnz, L.variant.items)) return OFSPMM_ERR_INVALID_ARG;
     part = opts->plan;
+  } else if (rows_kernel_applies(A, B, ldb, C, ldc, n, dense_dtype, L)) {
+    part = nullptr;  // the whole-row kernel reads crow directly: no task list
   } else if (int rc = launch_task_partition(A->crow, A->idx_dtype, A->rows, A->nnz, P, L.variant.items,
                                             w + W.part_off, stream)) {
     return rc;
@@ -187,7 +189,22 @@ int ofspmm_plan_build(const void* crow, int idx_dtype, int64_t rows, int64_t nnz
 
 int ofspmm_choose_variant(const int64_t* hist32_host, int64_t rows, int64_t nnz, int64_t n, int dense_dtype) {
   FwdVariant v = resolve_variant(OFSPMM_VARIANT_AUTO, rows, nnz, n, dense_dtype);
-  if (hist32_host == nullptr || rows <= 0 || nnz <= 0 || v.items == kSmallTaskItems) return encode_variant(v);
+  if (hist32_host == nullptr || rows <= 0 || nnz <= 0) return encode_variant(v);
+  if (v.items == kSmallTaskItems) {
+    // Small problem (fewer 256-item tasks than resident warps): launch, staging and carry
+    // latencies dominate.  If no row reaches 512 non-zeros (histogram buckets >= 10 empty) and one
+    // lane group per row yields at least 8 warps per SM, the whole-row kernel does the product in
+    // ONE launch (cfg1: 34.6 -> see profiles/r2_cfg1_latency.md); otherwise 64-item tasks.
+    const int64_t vecw = dense_dtype == OFSPMM_DTYPE_BFLOAT16 ? 8 : 4;
+    int64_t long_rows = 0;
+    for (int b = 10; b < 32; ++b) long_rows += hist32_host[b];
+    if (n > 0 && n % vecw == 0 && n / vecw <= 32 && long_rows == 0) {
+      const int64_t lpr = n / vecw <= 8 ? 8 : (n / vecw <= 16 ? 16 : 32);
+      const int64_t warps = (rows * lpr + 31) / 32;
+      if (warps >= 148 * 8) return encode_variant(resolve_variant(OFSPMM_VARIANT_EXPLICIT | OFSPMM_VARIANT_ROWS, rows, nnz, n, dense_dtype));
+    }
+    return encode_variant(v);
+  }
   // Row-parallel groups (each 8 / 16-lane group owns whole rows, 4 / 2 rows in flight per warp)
   // against nnz-parallel groups (every group works on every row): measured on B200 at N = 32 / 64
   // fp32, the row-parallel layout wins 10-20 % on R-MAT (median row length 0-1, 90 % of the rows
@@ -611,9 +628,15 @@ const char* ofspmm_variant_name(int variant, int64_t rows, int64_t nnz, int64_t 
   // "<schedule family>/<lane layout>": family from the variant, layout from the dense width
   static thread_local char buf[160];
   const FwdVariant v = resolve_variant(variant, rows, nnz, n, dense_dtype);
-  const char* fam = v.items == kSmallTaskItems ? "merge_path(64-item tasks)"
+  const char* fam = v.whole_rows               ? "whole_rows(one launch, no merge path)"
+                    : v.items == kSmallTaskItems ? "merge_path(64-item tasks)"
                     : v.row_parallel           ? "merge_path(256-item tasks, row-parallel groups)"
                                                : "merge_path(256-item tasks)";
+  if (v.whole_rows) {
+    const int64_t nvec = n / (dense_dtype == OFSPMM_DTYPE_BFLOAT16 ? 8 : 4);
+    snprintf(buf, sizeof(buf), "%s/group-per-row(%d lanes x 16B, 4 gathers in flight)", fam, nvec <= 8 ? 8 : (nvec <= 16 ? 16 : 32));
+    return buf;
+  }
   snprintf(buf, sizeof(buf), "%s/%s", fam, fwd_variant_name(n, dense_dtype, true));
   return buf;
 }

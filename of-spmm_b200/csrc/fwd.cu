@@ -8,6 +8,7 @@ namespace ofspmm {
 int launch_family_base(const FwdParams&, int, int, int, bool, const FwdLaunch&, cudaStream_t);
 int launch_family_small(const FwdParams&, int, int, int, bool, const FwdLaunch&, cudaStream_t);
 int launch_family_rowpar(const FwdParams&, int, int, int, bool, const FwdLaunch&, cudaStream_t);
+int launch_family_rows(const FwdParams&, int, int, cudaStream_t);
 
 namespace {
 
@@ -20,15 +21,26 @@ bool rowpar_supported(int64_t n, int dense_dtype) {
   return n % v == 0 && n / v <= 16;
 }
 
+// Dense widths the whole-row family has kernels for: 16-byte vectors, at most 32 of them.
+bool rows_supported(int64_t n, int dense_dtype) {
+  const int64_t v = vec_width(dense_dtype);
+  return n > 0 && n % v == 0 && n / v <= 32;
+}
+
 }  // namespace
 
 // AUTO (no histogram available): decided from the host-known sizes only — fewer 256-item tasks
 // than resident warps -> 64-item tasks.  With the row-length histogram on the host,
 // ofspmm_choose_variant() may also pick the row-parallel layout (api.cu).
 FwdVariant resolve_variant(int variant, int64_t rows, int64_t nnz, int64_t n, int dense_dtype) {
-  FwdVariant v{kTaskItems, false};
+  FwdVariant v{kTaskItems, false, false};
   if (variant & OFSPMM_VARIANT_EXPLICIT) {
-    if (variant & OFSPMM_VARIANT_ITEMS64) v.items = kSmallTaskItems;
+    if (variant & OFSPMM_VARIANT_ROWS) {
+      // sized like the 64-item family, which is also what runs when a launch cannot use the
+      // whole-row kernel (int64 indices, unaligned or strided-odd rows)
+      v.items = kSmallTaskItems;
+      v.whole_rows = rows_supported(n, dense_dtype);
+    } else if (variant & OFSPMM_VARIANT_ITEMS64) v.items = kSmallTaskItems;
     else if ((variant & OFSPMM_VARIANT_ROWPAR) && rowpar_supported(n, dense_dtype)) v.row_parallel = true;
     return v;
   }
@@ -38,7 +50,8 @@ FwdVariant resolve_variant(int variant, int64_t rows, int64_t nnz, int64_t n, in
 
 int encode_variant(const FwdVariant& v) {
   int code = OFSPMM_VARIANT_EXPLICIT;
-  if (v.items == kSmallTaskItems) code |= OFSPMM_VARIANT_ITEMS64;
+  if (v.whole_rows) code |= OFSPMM_VARIANT_ROWS;
+  else if (v.items == kSmallTaskItems) code |= OFSPMM_VARIANT_ITEMS64;
   if (v.row_parallel) code |= OFSPMM_VARIANT_ROWPAR;
   return code;
 }
@@ -59,6 +72,17 @@ int launch_task_partition(const void* crow, int idx_dtype, int64_t rows, int64_t
   count_launch();
   OFSPMM_CUDA_OK(cudaGetLastError());
   return OFSPMM_OK;
+}
+
+// The whole-row kernel needs what resolve_variant cannot see: the pointers' alignment, the
+// strides and the index dtype of THIS call.
+bool rows_kernel_applies(const ofspmm_csr* A, const void* B, int64_t ldb, const void* C, int64_t ldc, int64_t n,
+                         int dense_dtype, const FwdLaunch& L) {
+  if (!L.variant.whole_rows || A->idx_dtype != OFSPMM_DTYPE_INT32 || !rows_supported(n, dense_dtype)) return false;
+  const int64_t v = vec_width(dense_dtype);
+  const uintptr_t bits = reinterpret_cast<uintptr_t>(B) | reinterpret_cast<uintptr_t>(C) |
+                         ((L.flags & kFwdBias) ? reinterpret_cast<uintptr_t>(L.bias) : 0);
+  return (bits & 15) == 0 && ldb % v == 0 && ldc % v == 0;
 }
 
 int launch_fwd(const ofspmm_csr* A, const void* B, int64_t ldb, void* C, int64_t ldc, int64_t n,
@@ -89,6 +113,10 @@ int launch_fwd(const ofspmm_csr* A, const void* B, int64_t ldb, void* C, int64_t
   const bool aligned = ((reinterpret_cast<uintptr_t>(B) | reinterpret_cast<uintptr_t>(C) |
                          ((L.flags & kFwdBias) ? reinterpret_cast<uintptr_t>(L.bias) : 0)) & 15) == 0;
   const bool vec_rows = aligned && n % v == 0 && ldb % v == 0 && ldc % v == 0;
+  if (rows_kernel_applies(A, B, ldb, C, ldc, n, dense_dtype, L)) {
+    p.counter = nullptr;
+    return launch_family_rows(p, dense_dtype, A->val_dtype, stream);
+  }
   if (L.variant.items == kSmallTaskItems)
     return launch_family_small(p, A->idx_dtype, dense_dtype, A->val_dtype, aligned, L, stream);
   if (L.variant.row_parallel && vec_rows && rowpar_supported(n, dense_dtype))

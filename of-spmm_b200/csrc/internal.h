@@ -36,8 +36,12 @@ inline int64_t num_tasks(int64_t rows, int64_t nnz, int items = kTaskItems) {
 struct FwdVariant {
   int items;          // merge items per warp task: kTaskItems or kSmallTaskItems
   bool row_parallel;  // sub-warp per row (short rows, narrow dense operand) instead of nnz-parallel
+  bool whole_rows;    // spmm_rows_kernel: one launch, no merge path (items = kSmallTaskItems for sizing)
 };
 FwdVariant resolve_variant(int variant, int64_t rows, int64_t nnz, int64_t n, int dense_dtype);
+struct FwdLaunch;
+bool rows_kernel_applies(const ofspmm_csr* A, const void* B, int64_t ldb, const void* C, int64_t ldc, int64_t n,
+                         int dense_dtype, const FwdLaunch& L);
 int encode_variant(const FwdVariant& v);
 
 // Per-launch options the C ABI passes down (ofspmm_opts).

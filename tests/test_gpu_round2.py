@@ -40,7 +40,7 @@ def _oracle_fwd(A, B):
 # ------------------------------------------------------------------ variants, plans, task order
 
 @pytest.mark.parametrize("N", [16, 32, 64, 128, 256])
-@pytest.mark.parametrize("variant", [X, X | _lib.VARIANT_ITEMS64, X | _lib.VARIANT_ROWPAR])
+@pytest.mark.parametrize("variant", [X, X | _lib.VARIANT_ITEMS64, X | _lib.VARIANT_ROWPAR, X | _lib.VARIANT_ROWS])
 @pytest.mark.parametrize("graph", ["rmat", "reddit"])
 def test_forward_explicit_variants(N, variant, graph):
     """Every kernel family on every lane layout against the fp64 oracle (a family that has no
@@ -106,17 +106,108 @@ def test_cached_structure_backward_sees_value_updates():
     _fp32_ok(_np(got), ref, amax, cnt, "cached-structure dB after in-place value update")
 
 
-def test_small_problem_uses_small_tasks_and_is_fast_enough():
-    """BASELINE configs[0] (4096^2, 1 %, N=64): AUTO picks 64-item tasks; result vs oracle."""
+def test_small_problem_variants():
+    """BASELINE configs[0] (4096^2, 1 %, N=64): without the histogram AUTO picks 64-item tasks; the
+    plan (histogram: no row reaches 512 non-zeros) picks the one-launch whole-row kernel, for the
+    product and for the product on A^T; results vs the oracle, launches counted."""
     A = graphs.uniform_csr(4096, 4096, 0.01, seed=1)
     name = _lib.lib().ofspmm_fwd_variant(A.rows, A.nnz, 64, 2).decode()
     assert "64-item" in name, name
     B = graphs.dense_operand(A.cols, 64, 1)
+    dY = graphs.upstream_grad(A.rows, 64, 2)
     C64, amax, lens = _oracle_fwd(A, B)
     Ad = A.to(DEV)
-    plan = ops.SpmmPlan(Ad.crow, Ad.col, A.rows, A.cols, 64)
+    plan = ops.SpmmPlan(Ad.crow, Ad.col, A.rows, A.cols, 64, transpose=True)
+    assert plan.variant == X | _lib.VARIANT_ROWS and plan.t_variant == X | _lib.VARIANT_ROWS, (plan.variant, plan.t_variant)
+    assert "whole_rows" in plan.variant_name()
+    n0 = _lib.lib().ofspmm_launch_count()
     got = ops.spmm_csr_compute(Ad.crow, Ad.col, Ad.val, B.to(DEV), A.rows, A.cols, plan=plan)
-    _fp32_ok(_np(got), C64, amax, lens, "cfg1 planned")
+    assert _lib.lib().ofspmm_launch_count() - n0 == 1            # no partition, no fix-up
+    _fp32_ok(_np(got), C64, amax, lens, "cfg1 planned (whole rows)")
+    small = ops.spmm_csr_compute(Ad.crow, Ad.col, Ad.val, B.to(DEV), A.rows, A.cols, variant=X | _lib.VARIANT_ITEMS64)
+    _fp32_ok(_np(small), C64, amax, lens, "cfg1 64-item tasks")
+    dB64 = O.spmm_t_f64(A.crow.numpy(), A.col.numpy(), A.val.numpy(), dY.numpy(), A.cols)
+    amax_t, cnt = O.spmm_t_absmax(A.crow.numpy(), A.col.numpy(), A.val.numpy(), dY.numpy(), A.cols)
+    dB = ops.spmm_csr_grad_b_compute(Ad.crow, Ad.col, Ad.val, dY.to(DEV), A.rows, A.cols, plan=plan)
+    _fp32_ok(_np(dB), dB64, amax_t, cnt, "cfg1 dB (whole rows on A^T)")
+    # a hub row sends the plan back to the merge path: rows of >= 512 non-zeros need the task split
+    hub = graphs.rmat_csr(12, 16, seed=4).to(DEV)
+    assert not (ops.SpmmPlan(hub.crow, hub.col, hub.rows, hub.cols, 64).variant & _lib.VARIANT_ROWS)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("N", [24, 64, 128, 256])
+def test_whole_row_kernel_epilogue_skips_strides(dtype, N):
+    """The whole-row family on its own: ragged rows (empty ones included), masked lanes (N not a
+    power of two), skipped column indices with NaN bait, strided operands, accumulate + bias + relu,
+    and the fp32 running-sum passes of 16-bit products."""
+    g = torch.Generator().manual_seed(9)
+    M, K = 1500, 700
+    A = graphs.uniform_csr(M, K, 0.03, seed=21)
+    col = A.col.clone()
+    bad = torch.rand(col.numel(), generator=g) < 0.05
+    col[bad] = torch.tensor([-1, K, 2 ** 30], dtype=torch.int32)[torch.randint(0, 3, (int(bad.sum()),), generator=g)]
+    if dtype == torch.float32 and N > 128:
+        pytest.skip("fp32 rows wider than 512 bytes run the 64-item family (covered by test_forward_explicit_variants)")
+    V = X | _lib.VARIANT_ROWS
+    B = graphs.dense_operand(K, N, 5).to(dtype)
+    C_old = (graphs.dense_operand(M, N, 6) * 2).to(dtype)
+    bias = (torch.arange(N, dtype=torch.float32) * 0.02 - 0.4).to(dtype)
+    crow, coln, val = A.crow.numpy(), col.numpy(), A.val.numpy()
+    Bf = B.float().numpy()
+    ref = O.spmm_f64(crow, coln, val, Bf, K)
+    amax = O.spmm_absmax(crow, coln, val, Bf, K)
+    lens = np.diff(crow)
+
+    def ok(got, want, what, mag=0.0):
+        gg = got.float().cpu().numpy().astype(np.float64)
+        if dtype == torch.float32:
+            _fp32_ok(gg, want, amax, lens, what, extra=2.0 ** -22 * mag)
+        else:
+            assert (np.abs(gg - want) <= 1e-2 * np.abs(want) + 2.0 ** -8 * (amax + mag) + 1e-30).all(), what
+
+    d = dict(crow=A.crow.to(DEV), col=col.to(DEV), val=A.val.to(DEV))
+    n0 = _lib.lib().ofspmm_launch_count()
+    got = ops.spmm_csr_compute(d["crow"], d["col"], d["val"], B.to(DEV), M, K, variant=V)
+    assert _lib.lib().ofspmm_launch_count() - n0 == 1
+    ok(got, ref, "plain")
+    # NaN bait in B row 0: skipped entries must not touch it
+    Bn = B.clone()
+    Bn[0] = float("nan")
+    keep0 = np.ones(M, dtype=bool)
+    keep0[np.unique(np.repeat(np.arange(M), lens)[coln == 0])] = False
+    gn = ops.spmm_csr_compute(d["crow"], d["col"], d["val"], Bn.to(DEV), M, K, variant=V).float().cpu().numpy()
+    assert np.isfinite(gn[keep0]).all()
+    # accumulate + bias + relu
+    out = C_old.to(DEV).clone()
+    ops.spmm_csr_compute(d["crow"], d["col"], d["val"], B.to(DEV), M, K, out=out, accumulate=True, bias=bias.to(DEV),
+                         relu=True, variant=V)
+    want = np.maximum(ref + C_old.float().numpy().astype(np.float64) + bias.float().numpy().astype(np.float64)[None, :], 0)
+    ok(out, want, "acc+bias+relu", mag=np.abs(C_old.float().numpy()) + np.abs(bias.float().numpy())[None, :])
+    # strided B and C (row stride > n, a multiple of the 16-byte vector)
+    pad = 16 // B.element_size()
+    Bw = torch.zeros((K, N + pad), dtype=dtype, device=DEV)
+    Bw[:, :N] = B.to(DEV)
+    Cw = torch.full((M, N + 2 * pad), float("nan"), dtype=dtype, device=DEV)
+    ops.spmm_csr_compute(d["crow"], d["col"], d["val"], Bw[:, :N], M, K, out=Cw[:, :N], variant=V)
+    assert torch.equal(Cw[:, :N], got) and bool(torch.isnan(Cw[:, N:]).all())
+    # int64 indices: no whole-row kernel for them — the 64-item family answers, same tolerance
+    g64 = ops.spmm_csr_compute(d["crow"].long(), d["col"].long(), d["val"], B.to(DEV), M, K, variant=V)
+    ok(g64, ref, "int64 fallback")
+    if dtype != torch.float32:
+        # two passes with fp32 running sums == one pass, bit for bit (one rounding)
+        half = K // 2
+        rows_of = torch.repeat_interleave(torch.arange(M), torch.from_numpy(lens))
+        acc32 = torch.zeros((M, N), dtype=torch.float32, device=DEV)
+        outs = torch.empty((M, N), dtype=dtype, device=DEV)
+        masks = ((col < half) | bad, (col >= half) & ~bad)
+        for i, mask in enumerate(masks):
+            cnt = torch.bincount(rows_of[mask], minlength=M)
+            c = torch.zeros(M + 1, dtype=torch.int32)
+            c[1:] = cnt.cumsum(0)
+            ops.spmm_csr_compute(c.to(DEV), col[mask].to(DEV), A.val[mask].to(DEV), B.to(DEV), M, K, out=outs, variant=V,
+                                 acc32=acc32, acc32_in=i > 0, acc32_out=i == 0)
+        ok(outs, ref, "two passes, fp32 running sums")
 
 
 # ------------------------------------------------------------------ fused epilogue / accumulate

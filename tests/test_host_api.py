@@ -173,3 +173,51 @@ def test_partition_host_property_based():
         for k in range(parts + 1):
             assert (r[k], z[k]) == order[min(k * ipw, total)]
     check()
+
+
+# ------------------------------------------------------------------ histogram -> kernel variant (host function)
+
+def _hist_of(lengths):
+    """ofspmm_row_hist's bucketing on the host: bucket 0 = empty rows, bucket b = lengths in [2^(b-1), 2^b)."""
+    h = np.zeros(32, dtype=np.int64)
+    lengths = np.asarray(lengths, dtype=np.int64)
+    b = np.where(lengths <= 0, 0, np.floor(np.log2(np.maximum(lengths, 1))).astype(np.int64) + 1)
+    np.add.at(h, np.minimum(b, 31), 1)
+    return h
+
+
+@pytest.mark.parametrize("name,rows,lengths,n,dd,want", [
+    # BASELINE configs[0]: 4096 rows of ~41 non-zeros, n = 64 fp32 -> one launch, whole rows
+    ("cfg1", 4096, lambda r: r.binomial(4096, 0.01, 4096), 64, "f32", "ROWS"),
+    # same rows but one hub of 600 non-zeros: back to the merge path (64-item tasks: still a small problem)
+    ("cfg1+hub", 4096, lambda r: np.concatenate([r.binomial(4096, 0.01, 4095), [600]]), 64, "f32", "ITEMS64"),
+    # too few rows to fill the machine with one lane group per row
+    ("few rows", 300, lambda r: r.binomial(4096, 0.05, 300), 64, "f32", "ITEMS64"),
+    # fp32 rows wider than 512 bytes have no whole-row kernel
+    ("wide", 4096, lambda r: r.binomial(4096, 0.01, 4096), 256, "f32", "ITEMS64"),
+    # Reddit-shaped (median ~ 400), n = 128: base family
+    ("cfg2-like", 200_000, lambda r: r.integers(100, 900, 200_000), 128, "f32", "BASE"),
+    # R-MAT-like (most rows under 16 non-zeros), narrow operand: row-parallel groups
+    ("rmat n32", 1_000_000, lambda r: r.geometric(0.2, 1_000_000) - 1, 32, "f32", "ROWPAR"),
+    # same rows, warp-wide operand: the row-parallel family has no kernel -> base
+    ("rmat n128", 1_000_000, lambda r: r.geometric(0.2, 1_000_000) - 1, 128, "f32", "BASE"),
+    # products-shaped (median ~ 50), n = 64 bf16: base wins (profiles/r2_variant_sweeps.md)
+    ("products n64 bf16", 150_000, lambda r: r.integers(20, 90, 150_000), 64, "bf16", "BASE"),
+])
+def test_choose_variant_from_histogram(name, rows, lengths, n, dd, want):
+    from importlib import import_module
+    _lib = import_module("of-spmm_b200._lib")
+    L = _lib.lib()
+    lens = lengths(np.random.default_rng(5))
+    assert len(lens) == rows
+    hist = _hist_of(lens)
+    arr = (ctypes.c_int64 * 32)(*hist.tolist())
+    dense = _lib.DTYPE_FLOAT if dd == "f32" else _lib.DTYPE_BFLOAT16
+    code = L.ofspmm_choose_variant(arr, rows, int(lens.sum()), n, dense)
+    assert code & _lib.VARIANT_EXPLICIT
+    fam = ("ROWS" if code & _lib.VARIANT_ROWS else "ITEMS64" if code & _lib.VARIANT_ITEMS64
+           else "ROWPAR" if code & _lib.VARIANT_ROWPAR else "BASE")
+    assert fam == want, (name, hex(code), L.ofspmm_variant_name(code, rows, int(lens.sum()), n, dense).decode())
+    # without a histogram only the problem size decides
+    auto = L.ofspmm_choose_variant(None, rows, int(lens.sum()), n, dense)
+    assert not (auto & (_lib.VARIANT_ROWS | _lib.VARIANT_ROWPAR))

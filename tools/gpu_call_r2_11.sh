@@ -29,10 +29,14 @@ CUDA_VISIBLE_DEVICES=0,1,2,3 run cfg2_n4 4 29581 --steps 20 --warmup 5 --no-e2e 
 CUDA_VISIBLE_DEVICES=0,1 run cfg2_n2 2 29582 --steps 20 --warmup 5 --no-e2e --no-cpu-baseline
 CUDA_VISIBLE_DEVICES=0,1,2,3 run cfg4_n4 4 29583 --steps 10 --warmup 3 --no-e2e --no-cpu-baseline --workload cfg4_rmat24_n128_fp32
 wait $TESTS
+B="--no-e2e --no-cpu-baseline"
 run cfg2_n8 8 29584 --steps 20 --warmup 5 --no-cpu-baseline
-run cfg2_n8_comb 8 29585 --steps 20 --warmup 5 --no-e2e --no-cpu-baseline --combine-ctas 148
-run cfg4_n8 8 29586 --steps 10 --warmup 3 --no-e2e --no-cpu-baseline --workload cfg4_rmat24_n128_fp32
-run cfg4_n8_comb 8 29587 --steps 10 --warmup 3 --no-e2e --no-cpu-baseline --workload cfg4_rmat24_n128_fp32 --combine-ctas 148
-run cfg3_n8 8 29588 --steps 10 --warmup 3 --no-e2e --no-cpu-baseline --workload cfg3_products_n256_bf16
+run cfg4_n8 8 29586 --steps 10 --warmup 3 $B --workload cfg4_rmat24_n128_fp32
+run cfg2_n8_b2 8 29591 --steps 20 --warmup 5 $B --buckets 2
+run cfg3_n8 8 29588 --steps 10 --warmup 3 $B --workload cfg3_products_n256_bf16
 run cfg5_n8 8 29589 --steps 10 --warmup 3 --no-cpu-baseline --workload cfg5_gcn_reddit_h256
-run cfg3_n8_comb 8 29590 --steps 10 --warmup 3 --no-e2e --no-cpu-baseline --workload cfg3_products_n256_bf16 --combine-ctas 148
+run cfg2_n8_comb 8 29585 --steps 20 --warmup 5 $B --combine-ctas 148
+run cfg2_n8_ag 8 29592 --steps 20 --warmup 5 $B --scheme allgather
+run cfg4_n8_block 8 29593 --steps 10 --warmup 3 $B --workload cfg4_rmat24_n128_fp32 --layout block
+run cfg3_n8_comb 8 29590 --steps 10 --warmup 3 $B --workload cfg3_products_n256_bf16 --combine-ctas 148
+run cfg4_n8_comb 8 29587 --steps 10 --warmup 3 $B --workload cfg4_rmat24_n128_fp32 --combine-ctas 148
