@@ -444,10 +444,12 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-verify", action="store_true")
-    ap.add_argument("--scheme", default="pull", choices=["pull", "allgather"],
+    ap.add_argument("--ag-dynamic-order", action="store_true", help="N>1, allgather: dynamic task order in the overlapped products")
+    ap.add_argument("--scheme", default="auto", choices=["auto", "pull", "allgather"],
                     help="N>1: needed-rows pull over peer memory (default) or round 1's all-gather / reduce-scatter")
     ap.add_argument("--buckets", type=int, default=1, help="N>1, pull: remote column buckets (accumulate passes)")
-    ap.add_argument("--tasks-per-warp", type=int, default=4, help="N>1: CTAs of the overlapped products retire after k tasks")
+    ap.add_argument("--tasks-per-warp", type=int, default=0,
+                    help="N>1: CTAs of the overlapped products retire after k tasks (0: scheme default, 2 for allgather)")
     ap.add_argument("--pull-ctas", type=int, default=64, help="N>1, pull: grid cap of the peer-pull kernels")
     ap.add_argument("--no-interleave", action="store_true", help="N>1, pull: step = forward(); backward() back to back")
     ap.add_argument("--combine-ctas", type=int, default=0,
@@ -495,10 +497,18 @@ def main():
 
     if world > 1:
         dmod = __import__("importlib").import_module("of-spmm_b200.dist")
-        if args.scheme == "pull":
-            runner = dmod.ShardedSpmm(A, n, dtype, rank, world, dev, buckets=args.buckets,
-                                      tasks_per_warp=args.tasks_per_warp, pull_ctas=args.pull_ctas, shard_layout=args.layout,
-                                      interleave=not args.no_interleave, combine_ctas=args.combine_ctas)
+        runner, scheme, saving = dmod.make_sharded(
+            A, n, dtype, rank, world, dev, scheme=args.scheme,
+            allgather_kw=dict(tasks_per_warp=args.tasks_per_warp or 2, static_order=not args.ag_dynamic_order),
+            buckets=args.buckets, tasks_per_warp=args.tasks_per_warp or 4, pull_ctas=args.pull_ctas, shard_layout=args.layout,
+            interleave=not args.no_interleave, combine_ctas=args.combine_ctas)
+        detail["scheme"] = {"requested": args.scheme, "used": scheme,
+                            "needed_rows_saving_min_over_ranks": None if saving is None else round(saving, 4),
+                            "rule": "auto: fp32 and the needed-rows exchange saves < 25 % of an all-gather's bytes -> dense NCCL "
+                                    "collectives hidden behind the other product; otherwise (sparse exchange, or 16-bit products "
+                                    "whose partial sums are combined in fp32) the needed-rows exchange over peer memory "
+                                    "(profiles/r2_multigpu.md)"}
+        if scheme == "pull":
             xb = runner.exchange_bytes()
             detail["step_order"] = ("interleaved" + (f", combine beside the last forward pass ({args.combine_ctas} CTAs)"
                                                      if args.combine_ctas else "")) if runner.interleave else "forward(); backward()"
@@ -511,9 +521,9 @@ def main():
                            f"published, then combined in rank order by one kernel (ofspmm_combine_rows_multi); the two "
                            f"products are interleaved in ShardedSpmm.step")
         else:
-            runner = dmod.AllGatherSpmm(A, n, dtype, rank, world, dev, tasks_per_warp=args.tasks_per_warp or 2)
-            parallelism = (f"row-block x{world}, round-1 scheme: ncclAllGather(B) overlapped with A^T*dY, ncclReduceScatter(dB) "
-                           f"overlapped with A*B (comm={runner.comm})")
+            parallelism = (f"row-block x{world} (nnz-balanced whole rows), B/dB row-sharded; ncclAllGather(B) hidden behind "
+                           f"A^T*dY and ncclReduceScatter(dB) behind A*B, products launched as CTAs that retire after "
+                           f"{args.tasks_per_warp or 2} tasks per warp so the collectives get SMs (comm={runner.comm})")
         B_in, dY_in = runner.shard_rows(B), runner.shard_rows_out(dY)
         step = lambda: runner.step(B_in, dY_in)
         fwd_only = lambda: runner.forward(B_in)

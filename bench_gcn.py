@@ -49,7 +49,7 @@ def main(args):
     X = ofs.graphs.dense_operand(A.rows, in_dim, 31, dev)
     labels = torch.randint(0, out_dim, (A.rows,), generator=torch.Generator().manual_seed(32)).to(dev)
     model = gcn.ShardedGCN2(A, rank, world, dev, in_dim=in_dim, hidden=hidden, out_dim=out_dim, seed=5,
-                            tasks_per_warp=args.tasks_per_warp, buckets=args.buckets)
+                            tasks_per_warp=args.tasks_per_warp or 4, buckets=args.buckets)
     Xr, yr = model.local_rows(X), model.local_rows(labels)
     flops_step = 6 * 2.0 * A.nnz * hidden
 

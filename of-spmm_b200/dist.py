@@ -60,20 +60,21 @@ class CudaCompute:
         return ops.SpmmPlan(crow, col, rows, cols, n, dtype, transpose=True)
 
     def spmm(self, A: CsrMatrix, b, out, plan=None, accumulate=False, tasks_per_warp=0, bias=None, relu=False,
-             acc32=None, acc32_in=False, acc32_out=False, reserve_ctas=0):
+             acc32=None, acc32_in=False, acc32_out=False, reserve_ctas=0, static_order=False):
         if plan is not None:      # hot path of the sharded step: one ctypes call, everything else prepared
             L = ops._lib
             flags = (L.FWD_ACCUMULATE if accumulate else 0) | (L.FWD_BIAS if bias is not None else 0) | \
-                    (L.FWD_RELU if relu else 0) | (L.FWD_ACC32_IN if acc32_in else 0) | (L.FWD_ACC32_OUT if acc32_out else 0)
+                    (L.FWD_RELU if relu else 0) | (L.FWD_ACC32_IN if acc32_in else 0) | (L.FWD_ACC32_OUT if acc32_out else 0) | \
+                    (L.ORDER_STATIC if static_order else 0)
             return plan.prepared()(A.val, b, out, flags, bias, acc32 if (acc32_in or acc32_out) else None, reserve_ctas,
                                    tasks_per_warp)
         return ops.spmm_csr_compute(A.crow, A.col, A.val, b, A.rows, A.cols, out=out, plan=plan, accumulate=accumulate,
                                     tasks_per_warp=tasks_per_warp, bias=bias, relu=relu, acc32=acc32, acc32_in=acc32_in,
-                                    acc32_out=acc32_out, reserve_ctas=reserve_ctas)
+                                    acc32_out=acc32_out, reserve_ctas=reserve_ctas, order="static" if static_order else None)
 
-    def spmm_t(self, A: CsrMatrix, dy, out, plan=None, tasks_per_warp=0, acc32_out=None, reserve_ctas=0):
+    def spmm_t(self, A: CsrMatrix, dy, out, plan=None, tasks_per_warp=0, acc32_out=None, reserve_ctas=0, static_order=False):
         if plan is not None and plan.t_crow is not None:
-            flags = ops._lib.FWD_ACC32_OUT if acc32_out is not None else 0
+            flags = (ops._lib.FWD_ACC32_OUT if acc32_out is not None else 0) | (ops._lib.ORDER_STATIC if static_order else 0)
             return plan.prepared(True)(plan.transposed_values(A.val), dy, out, flags, None, acc32_out, reserve_ctas, tasks_per_warp)
         return ops.spmm_csr_grad_b_compute(A.crow, A.col, A.val, dy, A.rows, A.cols, out=out, plan=plan,
                                            tasks_per_warp=tasks_per_warp, acc32_out=acc32_out, reserve_ctas=reserve_ctas)
@@ -655,8 +656,13 @@ class AllGatherSpmm:
     short-lived CTAs (``tasks_per_warp``) so the NCCL kernels get SMs."""
 
     def __init__(self, A: CsrMatrix, n: int, dtype: torch.dtype, rank: int, world: int, device, *,
-                 tasks_per_warp: int = 2, group=None, compute=None):
+                 tasks_per_warp: int = 2, group=None, compute=None, static_order: bool = True):
+        """``tasks_per_warp`` / ``static_order``: launch policy of the products that run beside a
+        collective in ``step`` — CTAs retire after that many tasks per warp, tasks interleaved
+        statically over the warps (the configuration measured on 8 B200: profiles/r1_multigpu.md,
+        profiles/r2_multigpu.md)."""
         assert A.rows >= world, "fewer rows than ranks"
+        self._ov = dict(tasks_per_warp=tasks_per_warp, static_order=static_order) if (world > 1 and tasks_per_warp > 0) else {}
         self.rank, self.world, self.device, self.group = rank, world, device, group
         self.n, self.dtype, self.rows, self.cols = n, dtype, A.rows, A.cols
         self.cp = compute or CudaCompute()
@@ -703,10 +709,55 @@ class AllGatherSpmm:
 
     def step(self, B_shard: torch.Tensor, dY_blk: torch.Tensor):
         w_ag = dist.all_gather_into_tensor(self._b_full, B_shard.contiguous(), group=self.group, async_op=True)
-        self.cp.spmm_t(self.A_blk, dY_blk.contiguous(), self._db_part[: self.cols], plan=self.plan, tasks_per_warp=self.tpw)
+        self.cp.spmm_t(self.A_blk, dY_blk.contiguous(), self._db_part[: self.cols], plan=self.plan, **self._ov)
         w_rs = self._reduce_scatter(self._db, self._db_part)
         w_ag.wait()
-        self.cp.spmm(self.A_blk, self._b_full[: self.cols], self._c, plan=self.plan, tasks_per_warp=self.tpw)
+        self.cp.spmm(self.A_blk, self._b_full[: self.cols], self._c, plan=self.plan, **self._ov)
         if w_rs is not None:
             w_rs.wait()
         return self._c, self._db
+
+
+# ---------------------------------------------------------------------------------------------
+# which scheme for which graph
+
+def needed_rows_saving(A: CsrMatrix, rank: int, world: int, group=None) -> float:
+    """Fraction of an all-gather's bytes the needed-rows exchange would NOT move — the minimum
+    over ranks (the slowest rank sets the step time).  0: every rank touches every remote row of
+    B (Reddit-shaped: dense blocks, each rank's rows reach all 233 k columns); → 1: each rank
+    needs a sliver (R-MAT-24 on 8 GPUs: 0.80)."""
+    if world == 1:
+        return 1.0
+    bounds = ops.row_blocks(A.crow, A.nnz, world).cpu().tolist()
+    blk = A.row_slice(int(bounds[rank]), int(bounds[rank + 1]))
+    col = blk.col.long()
+    touched = torch.unique(col[(col >= 0) & (col < A.cols)])
+    eq = shard_rows_count(A.cols, world)
+    lo, hi = min(A.cols, rank * eq), min(A.cols, (rank + 1) * eq)
+    remote_needed = int(((touched < lo) | (touched >= hi)).sum())
+    remote_all = max(1, A.cols - (hi - lo))
+    t = torch.tensor([1.0 - remote_needed / remote_all], dtype=torch.float64, device=A.crow.device)
+    if dist.is_initialized():
+        dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
+    return float(t)
+
+
+def make_sharded(A: CsrMatrix, n: int, dtype: torch.dtype, rank: int, world: int, device, *, scheme: str = "auto",
+                 saving_threshold: float = 0.25, group=None, compute=None, allgather_kw=None, **pull_kw):
+    """The sharded product for this graph: ``ShardedSpmm`` (needed-rows exchange over peer memory)
+    or ``AllGatherSpmm`` (dense NCCL collectives hidden behind the other product).
+
+    ``scheme="auto"`` — measured on 8 B200 (profiles/r2_multigpu.md): when the needed-rows exchange
+    saves less than a quarter of the bytes, moving whole shards with NCCL's all-gather /
+    reduce-scatter is faster than gathering the same rows one by one (cfg2: 0.98-1.14 ms against
+    1.33 ms per step), so fp32 products on such graphs take the collective scheme.  Graphs where
+    the exchange is sparse (cfg4: 1.5 GB pulled instead of 7.5 GB gathered, 12.6 ms against
+    26.6 ms) and all 16-bit products (whose partial sums must travel in fp32 or be combined in
+    fp32 to round once — the collective scheme's bf16 reduce-scatter does not) take the
+    needed-rows exchange.  Returns (runner, scheme, saving)."""
+    saving = needed_rows_saving(A, rank, world, group) if (world > 1 and scheme == "auto") else None
+    if scheme == "auto":
+        scheme = "allgather" if (world > 1 and dtype == torch.float32 and saving < saving_threshold) else "pull"
+    if scheme == "allgather":
+        return AllGatherSpmm(A, n, dtype, rank, world, device, group=group, compute=compute, **(allgather_kw or {})), scheme, saving
+    return ShardedSpmm(A, n, dtype, rank, world, device, group=group, compute=compute, **pull_kw), scheme, saving

@@ -33,7 +33,7 @@ class OracleCompute:
     def plan(self, *a, **k):
         return None
 
-    def spmm(self, A, b, out, plan=None, accumulate=False, tasks_per_warp=0, bias=None, relu=False,
+    def spmm(self, A, b, out, plan=None, accumulate=False, tasks_per_warp=0, bias=None, relu=False, static_order=False,
              acc32=None, acc32_in=False, acc32_out=False, reserve_ctas=0):
         from oracle import oracle as O
         assert not (acc32_in or acc32_out), "fp32 running sums are a 16-bit feature; the CPU stand-in is fp32"
@@ -47,7 +47,7 @@ class OracleCompute:
         out.copy_(res)
         return out
 
-    def spmm_t(self, A, dy, out, plan=None, tasks_per_warp=0, acc32_out=None, reserve_ctas=0):
+    def spmm_t(self, A, dy, out, plan=None, tasks_per_warp=0, acc32_out=None, reserve_ctas=0, static_order=False):
         from oracle import oracle as O
         out.copy_(torch.from_numpy(O.spmm_t_f32(A.crow.numpy(), A.col.numpy(), A.val.numpy(), dy.contiguous().numpy(), A.cols)))
         return out
@@ -81,6 +81,17 @@ def _worker(rank, world, port, n, scheme, buckets, layout, q):
         if scheme == "pull":
             sh = dmod.ShardedSpmm(A, n, torch.float32, rank, world, "cpu", buckets=buckets, compute=OracleCompute(),
                                   shard_layout=layout, cyclic_block=16)
+        elif scheme.startswith("auto"):
+            # the factory's collective decision: threshold above / below any possible saving
+            thr = 2.0 if scheme == "auto_ag" else -1.0
+            sh, used, saving = dmod.make_sharded(A, n, torch.float32, rank, world, "cpu", scheme="auto", saving_threshold=thr,
+                                                 compute=OracleCompute(), buckets=buckets, shard_layout=layout, cyclic_block=16)
+            assert used == ("allgather" if scheme == "auto_ag" else "pull") and 0.0 <= saving <= 1.0
+            assert isinstance(sh, dmod.AllGatherSpmm if scheme == "auto_ag" else dmod.ShardedSpmm)
+            # 16-bit products never take the collective scheme (their partial sums are combined in fp32)
+            assert dmod.make_sharded(A, n, torch.bfloat16, rank, world, "cpu", scheme="auto", saving_threshold=2.0,
+                                     compute=OracleCompute())[1] == "pull"
+            scheme = "pull" if used == "pull" else "allgather"
         else:
             sh = dmod.AllGatherSpmm(A, n, torch.float32, rank, world, "cpu", compute=OracleCompute())
         out = {}
@@ -110,7 +121,8 @@ def _worker(rank, world, port, n, scheme, buckets, layout, q):
 
 @pytest.mark.parametrize("world,n,scheme,buckets,layout", [(2, 16, "pull", 1, "auto"), (3, 12, "pull", 1, "block"),
                                                            (3, 8, "pull", 2, "cyclic"), (4, 8, "pull", 1, "auto"),
-                                                           (2, 12, "allgather", 1, "block")])
+                                                           (2, 12, "allgather", 1, "block"), (2, 8, "auto_ag", 1, "block"),
+                                                           (3, 8, "auto_pull", 1, "auto")])
 def test_sharded_spmm_gloo(world, n, scheme, buckets, layout):
     sys.path.insert(0, ROOT)
     import ofspmm_b200 as ofs
@@ -165,7 +177,7 @@ def test_sharded_spmm_gloo(world, n, scheme, buckets, layout):
         assert results[0][5]["shard_ids"][:17].tolist() == list(range(16)) + [16 * world]   # blocks of 16 dealt round-robin
     assert all(r[5]["sep_equals_step"] for r in results)      # forward(); backward() == the interleaved step(), bit for bit
     assert len({r[5]["layout"] for r in results}) == 1        # "auto" is a collective decision: all ranks agree
-    if scheme != "pull":
+    if scheme not in ("pull", "auto_pull"):
         return
     dval = np.concatenate([r[5]["dval"] for r in results])
     dv_ref, _ = O.sddmm_f64(crow, col, dY, B)
