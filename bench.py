@@ -444,6 +444,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-verify", action="store_true")
+    ap.add_argument("--no-autotune", action="store_true", help="N>1, scheme auto: decide by the byte-saving rule alone")
     ap.add_argument("--ag-dynamic-order", action="store_true", help="N>1, allgather: dynamic task order in the overlapped products")
     ap.add_argument("--scheme", default="auto", choices=["auto", "pull", "allgather"],
                     help="N>1: needed-rows pull over peer memory (default) or round 1's all-gather / reduce-scatter")
@@ -497,17 +498,47 @@ def main():
 
     if world > 1:
         dmod = __import__("importlib").import_module("of-spmm_b200.dist")
-        runner, scheme, saving = dmod.make_sharded(
-            A, n, dtype, rank, world, dev, scheme=args.scheme,
-            allgather_kw=dict(tasks_per_warp=args.tasks_per_warp or 2, static_order=not args.ag_dynamic_order),
-            buckets=args.buckets, tasks_per_warp=args.tasks_per_warp or 4, pull_ctas=args.pull_ctas, shard_layout=args.layout,
-            interleave=not args.no_interleave, combine_ctas=args.combine_ctas)
+        import torch.distributed as dist
+        kw = dict(allgather_kw=dict(tasks_per_warp=args.tasks_per_warp or 2, static_order=not args.ag_dynamic_order),
+                  buckets=args.buckets, tasks_per_warp=args.tasks_per_warp or 4, pull_ctas=args.pull_ctas,
+                  shard_layout=args.layout, interleave=not args.no_interleave, combine_ctas=args.combine_ctas)
+        runner, scheme, saving = dmod.make_sharded(A, n, dtype, rank, world, dev, scheme=args.scheme, **kw)
+        tuned = None
+        if args.scheme == "auto" and scheme == "allgather" and not args.no_autotune:
+            # The rule says the exchange is dense (nothing saved by pulling only the needed rows), where
+            # the two schemes move the same bytes: settle it by measurement, at plan time, like any
+            # autotuner — a few untimed steps of each, max over ranks, same decision on every rank.
+            def probe(r):
+                b_in, dy_in = r.shard_rows(B), r.shard_rows_out(dY)
+                for _ in range(3):
+                    r.step(b_in, dy_in)
+                torch.cuda.synchronize()
+                dist.barrier()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(10):
+                    r.step(b_in, dy_in)
+                e1.record()
+                torch.cuda.synchronize()
+                t = torch.tensor([e0.elapsed_time(e1) / 10], dtype=torch.float64, device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                return float(t)
+            other, _, _ = dmod.make_sharded(A, n, dtype, rank, world, dev, scheme="pull", **kw)
+            tuned = {"allgather": probe(runner), "pull": probe(other)}
+            if tuned["pull"] < tuned["allgather"]:
+                runner, other, scheme = other, runner, "pull"
+            del other
+            import gc
+            gc.collect()
+            torch.cuda.empty_cache()
+            dist.barrier()
         detail["scheme"] = {"requested": args.scheme, "used": scheme,
                             "needed_rows_saving_min_over_ranks": None if saving is None else round(saving, 4),
-                            "rule": "auto: fp32 and the needed-rows exchange saves < 25 % of an all-gather's bytes -> dense NCCL "
-                                    "collectives hidden behind the other product; otherwise (sparse exchange, or 16-bit products "
-                                    "whose partial sums are combined in fp32) the needed-rows exchange over peer memory "
-                                    "(profiles/r2_multigpu.md)"}
+                            "autotune_ms_per_step": tuned,
+                            "rule": "auto: 16-bit products, and graphs where pulling only the needed rows of B saves >= 25 % of an "
+                                    "all-gather's bytes, take the needed-rows exchange over peer memory; fp32 products on graphs "
+                                    "where every rank needs (nearly) every row are timed on both schemes before the timed region "
+                                    "(10 steps each, max over ranks) and the faster one runs (profiles/r2_multigpu.md)"}
         if scheme == "pull":
             xb = runner.exchange_bytes()
             detail["step_order"] = ("interleaved" + (f", combine beside the last forward pass ({args.combine_ctas} CTAs)"
@@ -692,7 +723,10 @@ def main():
                             "traffic": rec["l2_bytes"], "kernel": rec["kernel"],
                             "peak_source": "ncu: 184 L2 slices x 2 sectors/clk x 32 B x 1.964 GHz (lts__lts2xbar peak_sustained)",
                             "dram_frac_of_measured_peak": rec["dram_bytes"] / (fwd_ms * 1e-3) / 1e9 / peak,
-                            "l2_hit_pct": rec.get("l2_hit_pct"), "ncu_capture": rec.get("tag")}
+                            "l2_hit_pct": rec.get("l2_hit_pct"), "ncu_capture": rec.get("tag"),
+                            "ncu_same_launch": {k: rec.get(k) for k in ("duration_ms_under_ncu", "l2_throughput_pct_ncu",
+                                                                        "l2_slice_output_busy_pct_avg", "l2_slice_output_busy_pct_max",
+                                                                        "dram_throughput_pct_ncu")}}
         except Exception:
             traffic = None
     out = {

@@ -83,6 +83,10 @@ def main():
             "l2_bytes": int(fnum(l2[0]) * TO_BYTES.get(l2[1], 1)),
             "duration_ms_under_ncu": fnum(dur[0]) * TO_MS.get(dur[1], 1),
             "l2_hit_pct": fnum(d["lts__t_sector_hit_rate.pct"][0]),
+            "l2_throughput_pct_ncu": fnum(d["lts__throughput.avg.pct_of_peak_sustained_elapsed"][0]),
+            "l2_slice_output_busy_pct_avg": fnum(d["lts__lts2xbar_cycles_active.avg.pct_of_peak_sustained_elapsed"][0]),
+            "l2_slice_output_busy_pct_max": fnum(d["lts__lts2xbar_cycles_active.max.pct_of_peak_sustained_elapsed"][0]),
+            "dram_throughput_pct_ncu": fnum(d["gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"][0]),
             "report": os.path.basename(path), "tag": args.tag,
         }
     with open(args.out, "w") as f:
