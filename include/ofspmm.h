@@ -174,7 +174,14 @@ OFSPMM_API int ofspmm_plan_build(const void* crow, int idx_dtype, int64_t rows, 
 
 /* ---- Variant choice from the row-length histogram (north_star (2)).  `hist32_host` = the 32
  * counters of ofspmm_row_hist copied to the HOST (once, when the op state is built — never inside a
- * captured call); NULL gives the AUTO decision.  Pure host function, no CUDA call. */
+ * captured call); NULL gives the AUTO decision.  Pure host function, no CUDA call.  Rules (measured,
+ * profiles/r2_variant_sweeps.md, profiles/r2_results_1gpu.md):
+ *   - small problem (fewer 256-item tasks than resident warps): ROWS when no row has >= 512
+ *     non-zeros, the dense rows are 16-byte vectors of <= 512 bytes and one lane group per row
+ *     gives >= 8 warps per SM; otherwise ITEMS64;
+ *   - else ROWPAR when the lane layout is sub-warp (dense row <= 256 bytes) and the median row,
+ *     empty rows included, has fewer than 16 non-zeros;
+ *   - else the base family (256-item tasks, nnz-parallel lane groups). */
 OFSPMM_API int ofspmm_choose_variant(const int64_t* hist32_host, int64_t rows, int64_t nnz, int64_t n,
                                      int dense_dtype);
 
