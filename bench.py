@@ -502,12 +502,19 @@ def main():
         kw = dict(allgather_kw=dict(tasks_per_warp=args.tasks_per_warp or 2, static_order=not args.ag_dynamic_order),
                   buckets=args.buckets, tasks_per_warp=args.tasks_per_warp or 4, pull_ctas=args.pull_ctas,
                   shard_layout=args.layout, interleave=not args.no_interleave, combine_ctas=args.combine_ctas)
-        runner, scheme, saving = dmod.make_sharded(A, n, dtype, rank, world, dev, scheme=args.scheme, **kw)
-        tuned = None
-        if args.scheme == "auto" and scheme == "allgather" and not args.no_autotune:
-            # The rule says the exchange is dense (nothing saved by pulling only the needed rows), where
-            # the two schemes move the same bytes: settle it by measurement, at plan time, like any
-            # autotuner — a few untimed steps of each, max over ranks, same decision on every rank.
+        tuned, saving = None, None
+        dense = False
+        if args.scheme == "auto":
+            saving = dmod.needed_rows_saving(A, rank, world)
+            dense = dtype == torch.float32 and saving < 0.25
+        if args.scheme != "auto" or not dense or args.no_autotune:
+            want = args.scheme if args.scheme != "auto" else ("allgather" if dense else "pull")
+            runner, scheme, _ = dmod.make_sharded(A, n, dtype, rank, world, dev, scheme=want, **kw)
+        else:
+            # The exchange is dense (pulling only the needed rows saves nothing), so the two schemes move the
+            # same bytes: settle it by measurement, at plan time, like any autotuner — untimed steps of
+            # each, max over ranks, the same decision on every rank.  The needed-rows runner is the
+            # fallback if the other one fails or disagrees with it.
             def probe(r):
                 b_in, dy_in = r.shard_rows(B), r.shard_rows_out(dY)
                 for _ in range(3):
@@ -517,17 +524,34 @@ def main():
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
                 for _ in range(10):
-                    r.step(b_in, dy_in)
+                    c, g = r.step(b_in, dy_in)
                 e1.record()
                 torch.cuda.synchronize()
                 t = torch.tensor([e0.elapsed_time(e1) / 10], dtype=torch.float64, device=dev)
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
-                return float(t)
-            other, _, _ = dmod.make_sharded(A, n, dtype, rank, world, dev, scheme="pull", **kw)
-            tuned = {"allgather": probe(runner), "pull": probe(other)}
-            if tuned["pull"] < tuned["allgather"]:
-                runner, other, scheme = other, runner, "pull"
-            del other
+                return float(t), c, g
+            runner, scheme, _ = dmod.make_sharded(A, n, dtype, rank, world, dev, scheme="pull", **kw)
+            t_pull, c_pull, g_pull = probe(runner)
+            tuned = {"pull": t_pull}
+            c_ag = g_ag = None
+            try:
+                other, _, _ = dmod.make_sharded(A, n, dtype, rank, world, dev, scheme="allgather", **kw)
+                t_ag, c_ag, g_ag = probe(other)
+                tuned["allgather"] = t_ag
+                # same inputs, two independent exchange paths: they must agree to fp32 summation-order noise
+                scale = float(c_pull.abs().max()) + 1e-30
+                ok = torch.tensor([float((c_ag - c_pull).abs().max()) <= 1e-4 * scale], dtype=torch.float64, device=dev)
+                if torch.equal(other.shard_ids, runner.shard_ids):
+                    gs = float(g_pull.abs().max()) + 1e-30
+                    ok *= float((g_ag - g_pull).abs().max()) <= 1e-4 * gs
+                dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+                tuned["schemes_agree"] = bool(ok.item())
+                if tuned["schemes_agree"] and t_ag < t_pull:
+                    runner, other, scheme = other, runner, "allgather"
+            except Exception as exc:  # pragma: no cover
+                tuned["allgather_error"] = repr(exc)[:200]
+                other = None
+            del other, c_pull, g_pull, c_ag, g_ag
             import gc
             gc.collect()
             torch.cuda.empty_cache()
