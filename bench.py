@@ -434,6 +434,84 @@ def _teardown(world):
     t.cancel()
 
 
+def pick_runner(args, dmod, A, B, dY, n, dtype, rank, world, dev, compute=None, steps=10):
+    """The sharded product for this workload at N > 1: by the byte-saving rule of
+    ``dist.make_sharded`` and, where the rule says the exchange is dense (both schemes move the same
+    bytes), by measurement at plan time.  ``compute`` / a CPU ``dev`` exist for the gloo test of
+    this control flow (tests/test_bench_contract.py); the bench passes neither."""
+    import torch
+    import torch.distributed as dist
+    cuda = torch.device(dev).type == "cuda"
+    kw = dict(allgather_kw=dict(tasks_per_warp=args.tasks_per_warp or 2, static_order=not args.ag_dynamic_order),
+              buckets=args.buckets, tasks_per_warp=args.tasks_per_warp or 4, pull_ctas=args.pull_ctas,
+              shard_layout=args.layout, interleave=not args.no_interleave, combine_ctas=args.combine_ctas, compute=compute)
+    tuned, saving = None, None
+    dense = False
+    if args.scheme == "auto":
+        saving = dmod.needed_rows_saving(A, rank, world)
+        dense = dtype == torch.float32 and saving < 0.25
+    if args.scheme != "auto" or not dense or args.no_autotune:
+        want = args.scheme if args.scheme != "auto" else ("allgather" if dense else "pull")
+        runner, scheme, _ = dmod.make_sharded(A, n, dtype, rank, world, dev, scheme=want, **kw)
+        return runner, scheme, saving, tuned
+
+    # The exchange is dense (pulling only the needed rows saves nothing), so the two schemes move the
+    # same bytes: settle it by measurement, at plan time, like any autotuner — untimed steps of each,
+    # max over ranks, the same decision on every rank.  The needed-rows runner is the fallback if the
+    # other one fails or disagrees with it.
+    def sync():
+        if cuda:
+            torch.cuda.synchronize()
+
+    def probe(r):
+        b_in, dy_in = r.shard_rows(B), r.shard_rows_out(dY)
+        for _ in range(3):
+            r.step(b_in, dy_in)
+        sync()
+        dist.barrier()
+        if cuda:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            c, g = r.step(b_in, dy_in)
+        if cuda:
+            e1.record()
+        sync()
+        ms = e0.elapsed_time(e1) / steps if cuda else (time.perf_counter() - t0) * 1e3 / steps
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t), c, g
+
+    runner, scheme, _ = dmod.make_sharded(A, n, dtype, rank, world, dev, scheme="pull", **kw)
+    t_pull, c_pull, g_pull = probe(runner)
+    tuned = {"pull": t_pull}
+    other = c_ag = g_ag = None
+    try:
+        other, _, _ = dmod.make_sharded(A, n, dtype, rank, world, dev, scheme="allgather", **kw)
+        t_ag, c_ag, g_ag = probe(other)
+        tuned["allgather"] = t_ag
+        # same inputs, two independent exchange paths: they must agree to fp32 summation-order noise
+        ok = torch.tensor([1.0], dtype=torch.float64, device=dev)
+        ok *= float((c_ag - c_pull).abs().max()) <= 1e-4 * (float(c_pull.abs().max()) + 1e-30)
+        if torch.equal(other.shard_ids.cpu(), runner.shard_ids.cpu()):
+            ok *= float((g_ag - g_pull).abs().max()) <= 1e-4 * (float(g_pull.abs().max()) + 1e-30)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        tuned["schemes_agree"] = bool(ok.item())
+        if tuned["schemes_agree"] and t_ag < t_pull:
+            runner, other, scheme = other, runner, "allgather"
+    except Exception as exc:  # pragma: no cover
+        tuned["allgather_error"] = repr(exc)[:200]
+    del other, c_pull, g_pull, c_ag, g_ag
+    import gc
+    gc.collect()
+    if cuda:
+        torch.cuda.empty_cache()
+    dist.barrier()
+    return runner, scheme, saving, tuned
+
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -498,64 +576,7 @@ def main():
 
     if world > 1:
         dmod = __import__("importlib").import_module("of-spmm_b200.dist")
-        import torch.distributed as dist
-        kw = dict(allgather_kw=dict(tasks_per_warp=args.tasks_per_warp or 2, static_order=not args.ag_dynamic_order),
-                  buckets=args.buckets, tasks_per_warp=args.tasks_per_warp or 4, pull_ctas=args.pull_ctas,
-                  shard_layout=args.layout, interleave=not args.no_interleave, combine_ctas=args.combine_ctas)
-        tuned, saving = None, None
-        dense = False
-        if args.scheme == "auto":
-            saving = dmod.needed_rows_saving(A, rank, world)
-            dense = dtype == torch.float32 and saving < 0.25
-        if args.scheme != "auto" or not dense or args.no_autotune:
-            want = args.scheme if args.scheme != "auto" else ("allgather" if dense else "pull")
-            runner, scheme, _ = dmod.make_sharded(A, n, dtype, rank, world, dev, scheme=want, **kw)
-        else:
-            # The exchange is dense (pulling only the needed rows saves nothing), so the two schemes move the
-            # same bytes: settle it by measurement, at plan time, like any autotuner — untimed steps of
-            # each, max over ranks, the same decision on every rank.  The needed-rows runner is the
-            # fallback if the other one fails or disagrees with it.
-            def probe(r):
-                b_in, dy_in = r.shard_rows(B), r.shard_rows_out(dY)
-                for _ in range(3):
-                    r.step(b_in, dy_in)
-                torch.cuda.synchronize()
-                dist.barrier()
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record()
-                for _ in range(10):
-                    c, g = r.step(b_in, dy_in)
-                e1.record()
-                torch.cuda.synchronize()
-                t = torch.tensor([e0.elapsed_time(e1) / 10], dtype=torch.float64, device=dev)
-                dist.all_reduce(t, op=dist.ReduceOp.MAX)
-                return float(t), c, g
-            runner, scheme, _ = dmod.make_sharded(A, n, dtype, rank, world, dev, scheme="pull", **kw)
-            t_pull, c_pull, g_pull = probe(runner)
-            tuned = {"pull": t_pull}
-            c_ag = g_ag = None
-            try:
-                other, _, _ = dmod.make_sharded(A, n, dtype, rank, world, dev, scheme="allgather", **kw)
-                t_ag, c_ag, g_ag = probe(other)
-                tuned["allgather"] = t_ag
-                # same inputs, two independent exchange paths: they must agree to fp32 summation-order noise
-                scale = float(c_pull.abs().max()) + 1e-30
-                ok = torch.tensor([float((c_ag - c_pull).abs().max()) <= 1e-4 * scale], dtype=torch.float64, device=dev)
-                if torch.equal(other.shard_ids, runner.shard_ids):
-                    gs = float(g_pull.abs().max()) + 1e-30
-                    ok *= float((g_ag - g_pull).abs().max()) <= 1e-4 * gs
-                dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-                tuned["schemes_agree"] = bool(ok.item())
-                if tuned["schemes_agree"] and t_ag < t_pull:
-                    runner, other, scheme = other, runner, "allgather"
-            except Exception as exc:  # pragma: no cover
-                tuned["allgather_error"] = repr(exc)[:200]
-                other = None
-            del other, c_pull, g_pull, c_ag, g_ag
-            import gc
-            gc.collect()
-            torch.cuda.empty_cache()
-            dist.barrier()
+        runner, scheme, saving, tuned = pick_runner(args, dmod, A, B, dY, n, dtype, rank, world, dev)
         detail["scheme"] = {"requested": args.scheme, "used": scheme,
                             "needed_rows_saving_min_over_ranks": None if saving is None else round(saving, 4),
                             "autotune_ms_per_step": tuned,
