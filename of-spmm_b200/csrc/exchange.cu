@@ -3,15 +3,28 @@
 //
 // In the needed-rows exchange every rank keeps its shard of the dense operand in symmetric (peer
 // mapped) memory; a rank PULLS exactly the B rows its row block touches straight out of the
-// owners' HBM over NVLink / NVSwitch with ordinary 16-byte loads on the peer pointer
-// (gather_rows_kernel, `src` = peer address), and the dual for A^T·dY: the owner of a dB shard
-// pulls the peers' partial rows and adds them in rank order (scatter_add_rows_kernel; the rows of
-// one list are distinct, so no atomics and a fixed summation order).  The reference instead
-// materialises the whole operand on every rank with a blocking all-gather before the op is even
-// issued (oneflow/core/boxing/ccl_boxing_function.cpp:105-124,183-197).
+// owners' HBM over NVLink / NVSwitch, and the dual for A^T·dY: the owner of a dB shard reads the
+// peers' published partial rows and adds them in rank order (the rows of one list are distinct,
+// so no atomics and a fixed summation order).  The reference instead materialises the whole
+// operand on every rank with a blocking all-gather before the op is even issued
+// (oneflow/core/boxing/ccl_boxing_function.cpp:105-124,183-197).
 //
-// Peer loads see ~2 us of latency: each thread keeps UNROLL independent 16-byte units in flight,
-// and the grid is capped (`max_ctas`) so the copy shares the GPU with the SpMM kernel it overlaps.
+// Two generations live here:
+//   * gather_rows / scatter_add_rows (+ the bf16 -> fp32 scatter, cast): one list, one peer per
+//     launch, ordered by the caller (device barriers).  Building blocks with bit-exact tests; the
+//     gloo emulation of the CPU tests has their semantics.
+//   * signal_peers / pull_rows_tma / pull_rows_multi / combine_rows_multi (second half of the
+//     file): the product path on NCCL groups.  ONE launch serves all peers; every segment spins
+//     (ld.acquire.sys) on its owner's epoch flag, written by signal_peers_kernel with a release at
+//     system scope after the owner's producing kernel — no host sync, no barrier kernel, no NCCL.
+//     pull_rows_tma_kernel moves each row with a TMA bulk copy from PEER memory into a 5-stage
+//     shared-memory ring and drains each stage with one bulk store: enough bytes in flight to cover
+//     the ~2-3 us NVLink round trip with 64 one-warp CTAs, which fit into the CTA slot the
+//     overlapped SpMM leaves free (ofspmm_opts.reserve_ctas_per_sm).
+//
+// Peer loads see ~2 us of latency: the register kernels keep UNROLL independent 16-byte units in
+// flight per thread, and every grid is capped (`max_ctas`) so the copy shares the GPU with the
+// SpMM kernel it overlaps.
 #include "common.cuh"
 #include "internal.h"
 

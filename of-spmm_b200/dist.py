@@ -21,15 +21,28 @@ Partitioning (both classes)
       backward  dBc_g  = A_remote_gᵀ·dY_blk  → published        (compact partial rows, remote owners)
                 dB_shard = A_localᵀ·dY_blk + Σ_r pull(dBc of rank r) in rank order   (deterministic)
       sddmm     per sub-CSR against the B rows the forward already holds
-  ``pull`` is ``ofspmm_gather_rows`` / ``ofspmm_scatter_add_rows`` reading the owners' shards
-  straight out of peer HBM over NVLink / NVSwitch (CUDA symmetric memory), ordered by device-side
-  barriers — no NCCL collective on the data path.  Only the rows a block touches cross the fabric
-  (R-MAT-24 on 8 GPUs: ~1/4 of an all-gather), and the local columns (70+ % of a community graph's
-  non-zeros) compute while they fly.
+  On NCCL process groups the exchange is two hand-written kernels over CUDA symmetric memory, with
+  no NCCL collective and no host synchronisation on the data path:
+    * ``ofspmm_pull_rows_multi`` — ONE launch pulls every needed row of a bucket straight out of
+      the owners' HBM over NVLink / NVSwitch (per row one TMA bulk copy into a shared-memory ring,
+      one bulk store per ring stage); each owner's segment waits on that owner's epoch flag;
+    * ``ofspmm_combine_rows_multi`` — ONE launch adds every peer's published partial rows into the
+      owner's dB shard in ascending rank order (fp32 accumulation for 16-bit operands);
+    * ``ofspmm_signal_peers`` publishes "my buffer of epoch e is complete" (release at system scope)
+      into every peer's signal pad.  Published buffers are double buffered by epoch parity, so no
+      "done reading" barrier exists (argument at ``B_pubs2`` below).
+  ``step`` interleaves the two products so both exchanges start first and land under compute.
+  Only the rows a block touches cross the fabric (R-MAT-24 on 8 GPUs: 1.5 GB instead of the 7.5 GB
+  of an all-gather), and the local columns (43-83 % of the non-zeros on the bench graphs) compute
+  while they fly.  B rows are owned in contiguous blocks, or in blocks of 256 rows dealt round-robin
+  when contiguous blocks would make one rank serve most pulls (``shard_layout``).
+  Under gloo (CPU tests) the same split / renumbering / ordering logic runs on
+  ``GatherTransport`` (barrier + all-gather emulation of the published buffers) with
+  ``ofspmm_gather_rows`` / ``ofspmm_scatter_add_rows`` semantics from a CPU stand-in.
 
 ``AllGatherSpmm`` — round 1's scheme (all-gather(B) → product, partial product → reduce-scatter,
-  the collectives of one product hidden behind the other product of a step).  Kept as the
-  reference-style baseline the exchange above is measured against.
+  the collectives of one product hidden behind the other product of a step).  The faster one when
+  every rank needs every row anyway (cfg2); ``make_sharded`` picks per graph and dtype.
 
 The compute back end defaults to the CUDA ops; tests inject a CPU stand-in built on the oracle to
 exercise the split / renumbering / exchange / accumulation-order logic under gloo.
