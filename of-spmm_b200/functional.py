@@ -98,3 +98,71 @@ def spmm_csr_grad_b(a_crow, a_col, a_val, dy, a_rows: int, a_cols: int, transpos
 def sddmm_csr(a_crow, a_col, dy, b, a_rows: int, a_cols: int, val_dtype=torch.float32) -> torch.Tensor:
     """dval[p] = <dy[row(p), :], b[a_col[p], :]> (the op the grad function dispatches for ``a_val``)."""
     return ops.sddmm_csr_compute(a_crow, a_col, dy, b, a_rows, a_cols, val_dtype)
+
+
+# ---------------------------------------------------------------------------------------------
+# aggregation with the epilogue fused into the SpMM store (SURVEY.md §8f rank 2)
+
+class OpsKernels:
+    """The three device entry points an aggregation layer needs, bound to the C ABI.  Tests of the
+    autograd wiring inject a CPU stand-in with the same three methods; the product path is this."""
+
+    def fwd(self, a_crow, a_col, a_val, b, a_rows, a_cols, bias, relu, plan):
+        return ops.spmm_csr_compute(a_crow, a_col, a_val, b, a_rows, a_cols, plan=plan, bias=bias, relu=relu)
+
+    def grad_b(self, a_crow, a_col, a_val, dy, a_rows, a_cols, plan):
+        return ops.spmm_csr_grad_b_compute(a_crow, a_col, a_val, dy, a_rows, a_cols, plan=plan)
+
+    def sddmm(self, a_crow, a_col, dy, b, a_rows, a_cols, val_dtype, plan):
+        return ops.sddmm_csr_compute(a_crow, a_col, dy, b, a_rows, a_cols, val_dtype, plan=plan)
+
+
+class _SpmmCsrEpilogueFn(torch.autograd.Function):
+    """out = act(A·b + bias) with bias and ReLU applied where the row sum is stored
+    (OFSPMM_FWD_BIAS | OFSPMM_FWD_RELU; precedent for a fused epilogue in the reference:
+    oneflow/user/kernels/cublas_fused_mlp_kernel.cu).  Backward: dz = dy ⊙ [out > 0] (the mask comes
+    from the saved OUTPUT, so the pre-activation is never materialised), dbias = Σ_rows dz,
+    db = Aᵀ·dz, dval = sddmm(dz, b)."""
+
+    @staticmethod
+    def forward(ctx, a_crow, a_col, a_val, b, bias, a_rows, a_cols, relu, state, kernels):
+        plan = state.plan(a_crow, a_col, a_rows, a_cols, b.shape[1], b.dtype) if state is not None else None
+        out = kernels.fwd(a_crow, a_col, a_val.detach(), b.detach(), a_rows, a_cols,
+                          None if bias is None else bias.detach(), relu, plan)
+        ctx.need = (a_val.requires_grad, b.requires_grad, bias is not None and bias.requires_grad)
+        ctx.a_rows, ctx.a_cols, ctx.state, ctx.relu, ctx.kernels = a_rows, a_cols, state, relu, kernels
+        ctx.save_for_backward(a_crow, a_col, a_val, b if a_val.requires_grad else None, out if relu else None)
+        ctx.mark_non_differentiable(a_crow, a_col)
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        a_crow, a_col, a_val, b, out = ctx.saved_tensors
+        need_val, need_b, need_bias = ctx.need
+        dz = dy * (out > 0).to(dy.dtype) if ctx.relu else dy
+        dz = dz.contiguous()
+        plan = None
+        if ctx.state is not None:
+            plan = ctx.state.plan(a_crow, a_col, ctx.a_rows, ctx.a_cols, dz.shape[1], dz.dtype)
+        d_val = d_b = d_bias = None
+        if need_bias:
+            d_bias = dz.float().sum(0).to(dz.dtype)
+        if need_val:
+            d_val = ctx.kernels.sddmm(a_crow, a_col, dz, b, ctx.a_rows, ctx.a_cols, a_val.dtype, plan)
+        if need_b:
+            d_b = ctx.kernels.grad_b(a_crow, a_col, a_val.detach(), dz, ctx.a_rows, ctx.a_cols, plan)
+        return None, None, d_val, d_b, d_bias, None, None, None, None, None
+
+
+def spmm_csr_bias_act(a_crow: torch.Tensor, a_col: torch.Tensor, a_val: torch.Tensor, b: torch.Tensor,
+                      a_rows: int, a_cols: int, bias: Optional[torch.Tensor] = None, relu: bool = False,
+                      state: Optional[SpmmOpKernelState] = None, kernels=None) -> torch.Tensor:
+    """out[a_rows, n] = act(CSR(a_crow, a_col, a_val) @ b + bias), epilogue fused into the product's
+    store; differentiable wrt ``a_val``, ``b`` and ``bias``."""
+    kernels = kernels or OpsKernels()
+    if isinstance(kernels, OpsKernels):
+        ops._check_device(a_crow, a_col, a_val, b)
+        ops.infer_spmm_csr(a_crow, a_col, a_val, b, a_rows, a_cols)
+    if bias is not None and (bias.dim() != 1 or bias.shape[0] != b.shape[1] or bias.dtype != b.dtype):
+        raise ops.OpInferError(f"bias must be a 1-D tensor of {b.shape[1]} elements of dtype {b.dtype}")
+    return _SpmmCsrEpilogueFn.apply(a_crow, a_col, a_val, b, bias, a_rows, a_cols, bool(relu), state, kernels)

@@ -30,6 +30,56 @@ def glorot(fan_in: int, fan_out: int, seed: int, device, dtype=torch.float32) ->
     return w.to(device=device, dtype=dtype)
 
 
+class GCNConv:
+    """One graph-convolution layer  out = act(Â · X · W + bias)  — the module-level caller of the op
+    (pattern: python/oneflow/nn/modules/linear.py).
+
+    * **Ordering by width**: the aggregation runs at the narrower of the two dense widths.
+      ``multiply first``  (out_dim ≤ in_dim):  Z = X·W (cuBLAS), out = act(Â·Z + bias) with bias and
+      ReLU **fused into the SpMM store** (one pass over the output, no pre-activation tensor);
+      ``aggregate first`` (out_dim > in_dim):  G = Â·X, out = act(G·W + bias) — the epilogue
+      follows the GEMM, so it is torch's.
+    * Dropout acts on the layer input (torch): a mask in the SpMM store would need a device RNG
+      stream per launch, which the C ABI does not carry.
+    * The normalised adjacency is shared between layers: pass the same ``CsrMatrix`` and the same
+      ``SpmmOpKernelState`` (plan, structure of Âᵀ) to every layer of a model.
+
+    ``kernels``: None = the C ABI (``functional.OpsKernels``); the CPU tests inject a stand-in."""
+
+    def __init__(self, in_dim: int, out_dim: int, bias: bool = True, activation: Optional[str] = "relu",
+                 order: str = "auto", dropout: float = 0.0, seed: int = 0, device="cuda", dtype=torch.float32,
+                 kernels=None):
+        assert activation in (None, "relu") and order in ("auto", "multiply_first", "aggregate_first")
+        self.in_dim, self.out_dim, self.activation, self.p = in_dim, out_dim, activation, float(dropout)
+        self.multiply_first = order == "multiply_first" or (order == "auto" and out_dim <= in_dim)
+        self.weight = glorot(in_dim, out_dim, seed, device, dtype).requires_grad_(True)
+        self.bias = torch.zeros(out_dim, device=device, dtype=dtype).requires_grad_(True) if bias else None
+        self.kernels = kernels
+        self.training = True
+
+    def parameters(self):
+        return [p for p in (self.weight, self.bias) if p is not None]
+
+    def aggregation_width(self) -> int:
+        return self.out_dim if self.multiply_first else self.in_dim
+
+    def __call__(self, A: CsrMatrix, X: torch.Tensor, val: Optional[torch.Tensor] = None,
+                 state: Optional[SpmmOpKernelState] = None) -> torch.Tensor:
+        from .functional import spmm_csr_bias_act
+        val = A.val if val is None else val
+        relu = self.activation == "relu"
+        if self.p > 0:
+            X = torch.nn.functional.dropout(X, self.p, self.training)
+        if self.multiply_first:
+            z = (X @ self.weight).contiguous()
+            return spmm_csr_bias_act(A.crow, A.col, val, z, A.rows, A.cols, self.bias, relu, state, self.kernels)
+        g = spmm_csr_bias_act(A.crow, A.col, val, X.contiguous(), A.rows, A.cols, None, False, state, self.kernels)
+        out = g @ self.weight
+        if self.bias is not None:
+            out = out + self.bias
+        return torch.relu(out) if relu else out
+
+
 class GCN2:
     """Two GCNConv layers sharing one normalised adjacency Â = (crow, col, val)."""
 
