@@ -58,6 +58,16 @@ from . import ops
 from .graphs import CsrMatrix
 
 
+def _row_bounds(A, world: int) -> List[int]:
+    """nnz-balanced whole-row block boundaries: from the device / host partitioner, or — for a graph
+    that was partitioned offline (formats.PartitionedGraph) — the boundaries stored with it."""
+    pre = getattr(A, "partition_bounds", None)
+    if pre is not None:
+        assert len(pre) == world + 1, f"partition cache was written for {len(pre) - 1} ranks, not {world}"
+        return [int(b) for b in pre]
+    return ops.row_blocks(A.crow, A.nnz, world).cpu().tolist()
+
+
 def shard_rows_count(k: int, world: int) -> int:
     return (k + world - 1) // world
 
@@ -256,7 +266,7 @@ class ShardedSpmm:
         # forward pass, on the communication stream, with that many CTAs
         self.interleave, self.combine_ctas = interleave, combine_ctas
         # nnz-balanced whole-row blocks (device partitioner when the graph is on the GPU)
-        self.bounds = ops.row_blocks(A.crow, A.nnz, world).cpu().tolist()
+        self.bounds = _row_bounds(A, world)
         self.r0, self.r1 = int(self.bounds[rank]), int(self.bounds[rank + 1])
         blk = A.row_slice(self.r0, self.r1)
         self.A_blk = blk
@@ -680,7 +690,7 @@ class AllGatherSpmm:
         self.n, self.dtype, self.rows, self.cols = n, dtype, A.rows, A.cols
         self.cp = compute or CudaCompute()
         self.tpw = tasks_per_warp if world > 1 else 0
-        self.bounds = ops.row_blocks(A.crow, A.nnz, world).cpu().tolist()
+        self.bounds = _row_bounds(A, world)
         self.r0, self.r1 = int(self.bounds[rank]), int(self.bounds[rank + 1])
         self.A_blk = A.row_slice(self.r0, self.r1)
         self.shard = shard_rows_count(A.cols, world)
@@ -741,7 +751,7 @@ def needed_rows_saving(A: CsrMatrix, rank: int, world: int, group=None) -> float
     needs a sliver (R-MAT-24 on 8 GPUs: 0.80)."""
     if world == 1:
         return 1.0
-    bounds = ops.row_blocks(A.crow, A.nnz, world).cpu().tolist()
+    bounds = _row_bounds(A, world)
     blk = A.row_slice(int(bounds[rank]), int(bounds[rank + 1]))
     col = blk.col.long()
     touched = torch.unique(col[(col >= 0) & (col < A.cols)])

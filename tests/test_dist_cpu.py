@@ -65,6 +65,71 @@ class OracleCompute:
         return dst
 
 
+def _cache_worker(rank, world, port, n, cache_dir, q):
+    """Every rank loads ONLY its row block from a partition cache; the result must equal the
+    whole-graph construction bit for bit."""
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import importlib
+        import ofspmm_b200 as ofs
+        dmod = importlib.import_module("of-spmm_b200.dist")
+        A = ofs.graphs.rmat_csr(10, 12, seed=4)
+        B = ofs.graphs.dense_operand(A.cols, n, 5)
+        dY = ofs.graphs.upstream_grad(A.rows, n, 6)
+        G = ofs.formats.load_partition(cache_dir, rank, world)
+        assert G.block.nnz < A.nnz and G.rows == A.rows and G.cols == A.cols
+        out = {}
+        for name, graph in (("cache", G), ("full", A)):
+            sh = dmod.ShardedSpmm(graph, n, torch.float32, rank, world, "cpu", compute=OracleCompute(), shard_layout="block")
+            C, dB = sh.step(sh.shard_rows(B), sh.shard_rows_out(dY))
+            out[name] = (C.clone(), dB.clone(), sh.bounds)
+            del sh
+        ag = dmod.make_sharded(G, n, torch.float32, rank, world, "cpu", scheme="allgather", compute=OracleCompute())[0]
+        C3, dB3 = ag.step(ag.shard_rows(B), ag.shard_rows_out(dY))
+        saving = dmod.needed_rows_saving(G, rank, world)
+        q.put((rank, bool(torch.equal(out["cache"][0], out["full"][0])), bool(torch.equal(out["cache"][1], out["full"][1])),
+               out["cache"][2] == out["full"][2], bool(torch.allclose(C3, out["full"][0], rtol=1e-5, atol=1e-5)), saving))
+        dist.barrier()
+        dist.destroy_process_group()
+    except Exception:
+        import traceback
+        q.put(("error", rank, traceback.format_exc()))
+
+
+def test_partition_cache_round_trip_gloo(tmp_path):
+    import ofspmm_b200 as ofs
+    world, n = 3, 8
+    A = ofs.graphs.rmat_csr(10, 12, seed=4)
+    m = ofs.formats.save_partition(str(tmp_path), A, world)
+    assert m["bounds"][0] == 0 and m["bounds"][-1] == A.rows and sum(m["block_nnz"]) == A.nnz
+    items = [m["bounds"][r + 1] - m["bounds"][r] + m["block_nnz"][r] for r in range(world)]     # merge items: rows + non-zeros
+    assert max(items) - min(items) <= int(A.row_lengths().max()) + 1                   # balanced up to one whole row
+    import scipy.sparse as sp                                                          # blocks are plain scipy files
+    blk1 = sp.load_npz(os.path.join(str(tmp_path), "block_1.npz"))
+    assert blk1.shape == (m["bounds"][2] - m["bounds"][1], A.cols) and blk1.nnz == m["block_nnz"][1]
+    with pytest.raises(ValueError):
+        ofs.formats.load_partition(str(tmp_path), 0, world + 1)                        # written for another world size
+    G0 = ofs.formats.load_partition(str(tmp_path), 0, world)
+    with pytest.raises(ValueError):
+        G0.row_slice(m["bounds"][1], m["bounds"][2])                                   # a rank holds only its own block
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_cache_worker, args=(r, world, port, n, str(tmp_path), q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=240) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    for r in res:
+        assert r[0] != "error", r[2]
+        assert r[1] and r[2] and r[3] and r[4], r
+        assert 0.0 <= r[5] <= 1.0
+
+
 def _worker(rank, world, port, n, scheme, buckets, layout, q):
     sys.path.insert(0, ROOT)
     os.environ["MASTER_ADDR"] = "127.0.0.1"
