@@ -479,18 +479,33 @@ def pick_runner(args, dmod, A, B, dY, n, dtype, rank, world, dev, compute=None, 
             e1.record()
         sync()
         ms = e0.elapsed_time(e1) / steps if cuda else (time.perf_counter() - t0) * 1e3 / steps
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        # the forward product alone (exchange included), for the record: an inference caller's number
+        sync()
+        dist.barrier()
+        if cuda:
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            f0.record()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            r.forward(b_in)
+        if cuda:
+            f1.record()
+        sync()
+        fms = f0.elapsed_time(f1) / steps if cuda else (time.perf_counter() - t0) * 1e3 / steps
+        c, g = r.step(b_in, dy_in)                    # leave the buffers holding a full step's results
+        sync()
+        t = torch.tensor([ms, fms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t), c, g
+        return float(t[0]), float(t[1]), c, g
 
     runner, scheme, _ = dmod.make_sharded(A, n, dtype, rank, world, dev, scheme="pull", **kw)
-    t_pull, c_pull, g_pull = probe(runner)
-    tuned = {"pull": t_pull}
+    t_pull, f_pull, c_pull, g_pull = probe(runner)
+    tuned = {"pull": t_pull, "pull_fwd_only": f_pull}
     other = c_ag = g_ag = None
     try:
         other, _, _ = dmod.make_sharded(A, n, dtype, rank, world, dev, scheme="allgather", **kw)
-        t_ag, c_ag, g_ag = probe(other)
-        tuned["allgather"] = t_ag
+        t_ag, f_ag, c_ag, g_ag = probe(other)
+        tuned["allgather"], tuned["allgather_fwd_only"] = t_ag, f_ag
         # same inputs, two independent exchange paths: they must agree to fp32 summation-order noise
         ok = torch.tensor([1.0], dtype=torch.float64, device=dev)
         ok *= float((c_ag - c_pull).abs().max()) <= 1e-4 * (float(c_pull.abs().max()) + 1e-30)
