@@ -631,8 +631,9 @@ def main():
                            f"products are interleaved in ShardedSpmm.step")
         else:
             parallelism = (f"row-block x{world} (nnz-balanced whole rows), B/dB row-sharded; ncclAllGather(B) hidden behind "
-                           f"A^T*dY and ncclReduceScatter(dB) behind A*B, products launched as CTAs that retire after "
-                           f"{args.tasks_per_warp or 2} tasks per warp so the collectives get SMs (comm={runner.comm})")
+                           f"A^T*dY and ncclReduceScatter(dB) behind A*B, products launched as short-lived CTAs so the "
+                           f"collectives get SMs ({(tuned or {}).get('allgather_policy') or f'{args.tasks_per_warp or 2} tasks/warp'}; "
+                           f"comm={runner.comm})")
         B_in, dY_in = runner.shard_rows(B), runner.shard_rows_out(dY)
         step = lambda: runner.step(B_in, dY_in)
         fwd_only = lambda: runner.forward(B_in)
