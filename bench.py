@@ -501,24 +501,29 @@ def pick_runner(args, dmod, A, B, dY, n, dtype, rank, world, dev, compute=None, 
     runner, scheme, _ = dmod.make_sharded(A, n, dtype, rank, world, dev, scheme="pull", **kw)
     t_pull, f_pull, c_pull, g_pull = probe(runner)
     tuned = {"pull": t_pull, "pull_fwd_only": f_pull}
-    # launch policies of the products that run beside the NCCL collectives: round 1's measured
-    # optimum (static task order, CTAs retire after 2 tasks per warp) and this round's kernels'
-    # default order with 2 and 4 tasks per warp
+    # Candidates besides the plain needed-rows step: the same with the dB combine moved beside the
+    # last forward pass (communication stream, 148 CTAs), and the collective scheme under three launch
+    # policies of the products that run beside NCCL — round 1's measured optimum (static task order,
+    # CTAs retire after 2 tasks per warp) and this round's default order with 2 and 4 tasks per warp.
+    cands = []
+    if not args.combine_ctas and not args.no_interleave:
+        cands.append(("pull[combine beside the last forward pass]", "pull", dict(kw, combine_ctas=148)))
     if args.tasks_per_warp or args.ag_dynamic_order:
         policies = [(args.tasks_per_warp or 2, not args.ag_dynamic_order)]
     else:
         policies = [(2, True), (2, False), (4, False)]
-    best_t, best_policy = t_pull, None
-    other = c_ag = g_ag = None
     for tpw, static in policies:
-        name = f"allgather[{'static' if static else 'dynamic'} order, {tpw} tasks/warp]"
+        cands.append((f"allgather[{'static' if static else 'dynamic'} order, {tpw} tasks/warp]", "allgather",
+                      dict(kw, allgather_kw=dict(tasks_per_warp=tpw, static_order=static))))
+    best_t, best_name, best_scheme = t_pull, None, "pull"
+    other = c_ag = g_ag = None
+    for name, sch, kw_c in cands:
         cand = None
         try:
-            kw_c = dict(kw, allgather_kw=dict(tasks_per_warp=tpw, static_order=static))
-            cand, _, _ = dmod.make_sharded(A, n, dtype, rank, world, dev, scheme="allgather", **kw_c)
+            cand, _, _ = dmod.make_sharded(A, n, dtype, rank, world, dev, scheme=sch, **kw_c)
             t_ag, f_ag, c_ag, g_ag = probe(cand)
             tuned[name], tuned[name + " fwd_only"] = t_ag, f_ag
-            # same inputs, two independent exchange paths: they must agree to fp32 summation-order noise
+            # same inputs, independent exchange paths: they must agree to fp32 summation-order noise
             ok = torch.tensor([1.0], dtype=torch.float64, device=dev)
             ok *= float((c_ag - c_pull).abs().max()) <= 1e-4 * (float(c_pull.abs().max()) + 1e-30)
             if torch.equal(cand.shard_ids.cpu(), runner.shard_ids.cpu()):
@@ -527,14 +532,18 @@ def pick_runner(args, dmod, A, B, dY, n, dtype, rank, world, dev, compute=None, 
             agree = bool(ok.item())
             tuned["schemes_agree"] = agree and tuned.get("schemes_agree", True)
             if agree and t_ag < best_t:
-                best_t, best_policy, other, cand = t_ag, name, cand, other     # keep the best, drop the previous best
+                best_t, best_name, best_scheme, other, cand = t_ag, name, sch, cand, other   # keep the best, drop the previous best
         except Exception as exc:  # pragma: no cover
             tuned[name + " error"] = repr(exc)[:200]
         del cand
         c_ag = g_ag = None
-    if best_policy is not None:
-        runner, other, scheme = other, runner, "allgather"
-        tuned["allgather_policy"] = best_policy
+    if best_name is not None:
+        runner, other, scheme = other, runner, best_scheme
+        tuned["chosen"] = best_name
+        if best_scheme == "allgather":
+            tuned["allgather_policy"] = best_name
+    else:
+        tuned["chosen"] = "pull"
     del other, c_pull, g_pull, c_ag, g_ag
     import gc
     gc.collect()
@@ -619,8 +628,8 @@ def main():
                                     "(10 steps each, max over ranks) and the faster one runs (profiles/r2_multigpu.md)"}
         if scheme == "pull":
             xb = runner.exchange_bytes()
-            detail["step_order"] = ("interleaved" + (f", combine beside the last forward pass ({args.combine_ctas} CTAs)"
-                                                     if args.combine_ctas else "")) if runner.interleave else "forward(); backward()"
+            detail["step_order"] = ("interleaved" + (f", combine beside the last forward pass ({runner.combine_ctas} CTAs)"
+                                                     if runner.combine_ctas else "")) if runner.interleave else "forward(); backward()"
             detail["shard_layout"] = runner.layout + (f" (blocks of {runner.cyc} rows dealt round-robin)" if runner.layout == "cyclic" else "")
             detail["exchange"] = {"pulled_bytes_per_product_rank0": xb["pulled"], "all_gather_bytes_per_product": xb["all_gather"],
                                   "local_nnz_fraction_rank0": round(xb["local_nnz_fraction"], 4)}

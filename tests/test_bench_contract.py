@@ -109,7 +109,8 @@ def test_pick_runner_dense_exchange_is_autotuned_and_sparse_is_not():
         assert r[2] < 0.25 and r[3]["schemes_agree"] is True
         assert set(r[3]) >= {"pull", "pull_fwd_only", "allgather[static order, 2 tasks/warp]",
                              "allgather[dynamic order, 2 tasks/warp]", "allgather[dynamic order, 4 tasks/warp]"}
-        assert (r[1] == "allgather") == ("allgather_policy" in r[3])
+        assert (r[1] == "allgather") == ("allgather_policy" in r[3]) and "chosen" in r[3]
+        assert "pull[combine beside the last forward pass]" in r[3]
         assert not any(k.endswith("error") for k in r[3])
         assert r[4] == ("AllGatherSpmm" if r[1] == "allgather" else "ShardedSpmm")
     A = ofs.graphs.uniform_csr(96, 96, 0.5, seed=3)
