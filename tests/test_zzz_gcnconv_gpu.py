@@ -15,18 +15,22 @@ DEV = "cuda:0"
 
 
 def test_gcnconv_gpu_matches_dense_fp64():
-    A, X, _ = _setup(DEV)
-    l1 = gcn.GCNConv(24, 16, bias=True, activation="relu", seed=3, device=DEV)
-    l2 = gcn.GCNConv(16, 40, bias=True, activation=None, seed=4, device=DEV)
+    A, _, _ = _setup(DEV)
+    X = ofs.graphs.dense_operand(A.rows, 128, 3).to(DEV)          # CPU generator: same numbers on every box
+    l1 = gcn.GCNConv(128, 64, bias=True, activation="relu", seed=3, device=DEV)      # multiply first: fused bias + ReLU at width 64
+    l2 = gcn.GCNConv(64, 128, bias=True, activation=None, seed=4, device=DEV)        # aggregate first at width 64
+    assert l1.multiply_first and not l2.multiply_first
     with torch.no_grad():
-        l1.bias.copy_(torch.linspace(-0.3, 0.3, 16))
-        l2.bias.copy_(torch.linspace(0.2, -0.2, 40))
+        l1.bias.copy_(torch.linspace(-0.3, 0.3, 64))
+        l2.bias.copy_(torch.linspace(0.2, -0.2, 128))
     val = A.val.clone().requires_grad_(True)
     state = F.SpmmOpKernelState()
     before = ofs.launch_count()
     _conv_vs_dense([l1, l2], A, X, val, DEV, state)
     assert ofs.launch_count() > before                       # the C ABI did the work
     # fused epilogue == unfused composition of the same op, to rounding
-    fused = F.spmm_csr_bias_act(A.crow, A.col, A.val, X, A.rows, A.cols, bias=torch.linspace(-1, 1, 24, device=DEV), relu=True)
-    plain = torch.relu(ofs.spmm_csr(A.crow, A.col, A.val, X, A.rows, A.cols) + torch.linspace(-1, 1, 24, device=DEV))
-    assert torch.allclose(fused, plain, rtol=1e-6, atol=1e-6)
+    Z = ofs.graphs.dense_operand(A.cols, 64, 8).to(DEV)
+    bias = torch.linspace(-1, 1, 64, device=DEV)
+    fused = F.spmm_csr_bias_act(A.crow, A.col, A.val, Z, A.rows, A.cols, bias=bias, relu=True)
+    plain = torch.relu(ofs.spmm_csr(A.crow, A.col, A.val, Z, A.rows, A.cols) + bias)
+    assert torch.allclose(fused, plain, rtol=1e-5, atol=1e-6)
