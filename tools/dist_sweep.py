@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Multi-GPU tuning sweep (development tool): one torchrun launch, one graph, several
-communication / grid configurations of dist.ShardedSpmm timed back to back.
+exchange-scheme / launch-policy configurations of the sharded products (dist.make_sharded) timed back to back.
 
     torchrun --nproc-per-node 8 tools/dist_sweep.py [--workload cfg2_reddit_n128_fp32]
 """
@@ -27,7 +27,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     args = ap.parse_args()
     # never hang the launcher
-    killer = threading.Timer(100.0, lambda: os._exit(3))
+    killer = threading.Timer(240.0, lambda: os._exit(3))
     killer.daemon = True
     killer.start()
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
@@ -42,19 +42,27 @@ def main():
     B = ofs.graphs.dense_operand(A.cols, n, 11, dev, dtype)
     dY = ofs.graphs.upstream_grad(A.rows, n, 12, dev, dtype)
     flops_step = 2.0 * 2.0 * A.nnz * n
-    # (comm, column panels, OFSPMM_TASKS_PER_WARP, cross-product overlap in step())
-    configs = [("nccl", 1, 0, False), ("nccl", 1, 0, True), ("nccl", 1, 2, True), ("peer", 1, 0, True), ("peer", 1, 0, False)]
+    # (name, scheme, constructor keywords): every launch policy is an argument of the C ABI now
+    # (round 1 switched them through an environment variable)
+    configs = [
+        ("needed rows", "pull", {}),
+        ("needed rows, forward(); backward()", "pull", dict(interleave=False)),
+        ("needed rows, combine beside the last forward pass", "pull", dict(combine_ctas=148)),
+        ("needed rows, 2 buckets", "pull", dict(buckets=2)),
+        ("needed rows, block ownership", "pull", dict(shard_layout="block")),
+        ("needed rows, cyclic ownership", "pull", dict(shard_layout="cyclic")),
+        ("all-gather, static order, 2 tasks/warp", "allgather", dict(allgather_kw=dict(tasks_per_warp=2, static_order=True))),
+        ("all-gather, dynamic order, 2 tasks/warp", "allgather", dict(allgather_kw=dict(tasks_per_warp=2, static_order=False))),
+        ("all-gather, dynamic order, 4 tasks/warp", "allgather", dict(allgather_kw=dict(tasks_per_warp=4, static_order=False))),
+        ("all-gather, persistent grids", "allgather", dict(allgather_kw=dict(tasks_per_warp=0))),
+    ]
     ref_c = None
-    for comm, panels, tpw, ov in configs:
+    for name, scheme, kw in configs:
         try:
-            if tpw:
-                os.environ["OFSPMM_TASKS_PER_WARP"] = str(tpw)
-            else:
-                os.environ.pop("OFSPMM_TASKS_PER_WARP", None)
-            r = dmod.ShardedSpmm(A, n, dtype, rank, world, dev, panels=panels, comm=comm)
+            r, _, _ = dmod.make_sharded(A, n, dtype, rank, world, dev, scheme=scheme, **kw)
             Bs, dYs = r.shard_rows(B), r.shard_rows_out(dY)
             for _ in range(3):
-                r.step(Bs, dYs, overlap=ov)
+                r.step(Bs, dYs)
             dist.barrier()
             torch.cuda.synchronize()
 
@@ -70,26 +78,30 @@ def main():
                 t = torch.tensor([a.elapsed_time(b) / args.steps], device=dev, dtype=torch.float64)
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
                 return float(t[0])
-            step_ms = timed(lambda: r.step(Bs, dYs, overlap=ov))
+            step_ms = timed(lambda: r.step(Bs, dYs))
             fwd_ms = timed(lambda: r.forward(Bs))
             bwd_ms = timed(lambda: r.backward(dYs))
-            c, db = r.step(Bs, dYs, overlap=ov)
+            c, db = r.step(Bs, dYs)
             torch.cuda.synchronize()
-            chk = torch.tensor([float(c.double().abs().sum()), float(db.double().abs().sum())], device=dev, dtype=torch.float64)
+            # layout-independent checksums: |C| over all row blocks, |dB| over all owned rows
+            chk = torch.tensor([float(c.double().abs().sum()), float(db[: r.own].double().abs().sum())], device=dev, dtype=torch.float64)
             dist.all_reduce(chk)
             if rank == 0:
                 same = None
                 if ref_c is None:
                     ref_c = chk.clone()
                 else:
-                    same = bool(torch.allclose(chk, ref_c, rtol=1e-6))
-                print(json.dumps({"comm": r.comm, "panels": r.panels, "tasks_per_warp": tpw, "overlap": ov, "step_ms": round(step_ms, 4),
-                                  "fwd_ms": round(fwd_ms, 4), "bwd_ms": round(bwd_ms, 4),
-                                  "tflops": round(flops_step / step_ms / 1e9, 2), "checksum_matches_first": same}), flush=True)
+                    same = bool(torch.allclose(chk, ref_c, rtol=1e-5))
+                print(json.dumps({"config": name, "comm": r.comm, "step_ms": round(step_ms, 4), "fwd_ms": round(fwd_ms, 4),
+                                  "bwd_ms": round(bwd_ms, 4), "tflops": round(flops_step / step_ms / 1e9, 2),
+                                  "checksum_matches_first": same}), flush=True)
             del r
+            import gc
+            gc.collect()
+            torch.cuda.empty_cache()
         except Exception as e:  # keep going: one failing configuration must not waste the box
             if rank == 0:
-                print(json.dumps({"comm": comm, "panels": panels, "tasks_per_warp": tpw, "error": repr(e)[:300]}), flush=True)
+                print(json.dumps({"config": name, "error": repr(e)[:300]}), flush=True)
     bench._teardown(world)
 
 
