@@ -506,7 +506,8 @@ def pick_runner(args, dmod, A, B, dY, n, dtype, rank, world, dev, compute=None, 
     # policies of the products that run beside NCCL — round 1's measured optimum (static task order,
     # CTAs retire after 2 tasks per warp) and this round's default order with 2 and 4 tasks per warp.
     cands = []
-    if not args.combine_ctas and not args.no_interleave:
+    if args.tune_combine and not args.combine_ctas and not args.no_interleave:
+        # opt-in: a second needed-rows runner (its own symmetric-memory buffers) alive beside the first
         cands.append(("pull[combine beside the last forward pass]", "pull", dict(kw, combine_ctas=148)))
     if args.tasks_per_warp or args.ag_dynamic_order:
         policies = [(args.tasks_per_warp or 2, not args.ag_dynamic_order)]
@@ -564,6 +565,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-verify", action="store_true")
+    ap.add_argument("--tune-combine", action="store_true",
+                    help="N>1, scheme auto: also time the needed-rows step with the combine beside the last forward pass")
     ap.add_argument("--no-autotune", action="store_true", help="N>1, scheme auto: decide by the byte-saving rule alone")
     ap.add_argument("--ag-dynamic-order", action="store_true", help="N>1, allgather: dynamic task order in the overlapped products")
     ap.add_argument("--scheme", default="auto", choices=["auto", "pull", "allgather"],

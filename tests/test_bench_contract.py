@@ -64,7 +64,7 @@ def _pick_worker(rank, world, port, scheme, no_autotune, graph, q):
         B = ofs.graphs.dense_operand(A.cols, n, 5)
         dY = ofs.graphs.upstream_grad(A.rows, n, 6)
         args = argparse.Namespace(scheme=scheme, no_autotune=no_autotune, tasks_per_warp=0, ag_dynamic_order=False, buckets=1,
-                                  pull_ctas=64, layout="auto", no_interleave=False, combine_ctas=0)
+                                  pull_ctas=64, layout="auto", no_interleave=False, combine_ctas=0, tune_combine=True)
         runner, used, saving, tuned = bench.pick_runner(args, dmod, A, B, dY, n, torch.float32, rank, world, "cpu",
                                                         compute=OracleCompute(), steps=2)
         C, dB = runner.step(runner.shard_rows(B), runner.shard_rows_out(dY))
