@@ -48,6 +48,34 @@ class SpmmCsrFunctor {
   std::shared_ptr<OpExpr> op_, op_with_at_;
 };
 
+// flow._C.fused_spmm_csr_bias_act(a_crow, a_col, a_val, b, bias, a_rows, a_cols, relu=False)
+class FusedSpmmCsrBiasActFunctor {
+ public:
+  FusedSpmmCsrBiasActFunctor() {
+    op_ = CHECK_JUST(one::OpBuilder("fused_spmm_csr_bias_act").Input("a_crow").Input("a_col").Input("a_val").Input("b")
+                         .Input("bias").Output("out").Build());
+  }
+  Maybe<Tensor> operator()(const std::shared_ptr<one::Tensor>& a_crow,
+                           const std::shared_ptr<one::Tensor>& a_col,
+                           const std::shared_ptr<one::Tensor>& a_val,
+                           const std::shared_ptr<one::Tensor>& b,
+                           const std::shared_ptr<one::Tensor>& bias, const int64_t& a_rows,
+                           const int64_t& a_cols, const bool& relu) const {
+    CHECK_EQ_OR_RETURN(b->ndim(), 2) << Error::RuntimeError() << "b must be 2-D, got " << b->ndim() << "-D";
+    CHECK_EQ_OR_RETURN(b->dim(0), a_cols) << Error::RuntimeError() << "b has " << b->dim(0)
+                                          << " rows but a_cols = " << a_cols;
+    CHECK_EQ_OR_RETURN(bias->ndim(), 1) << Error::RuntimeError() << "bias must be 1-D, got " << bias->ndim() << "-D";
+    CHECK_EQ_OR_RETURN(bias->dim(0), b->dim(1)) << Error::RuntimeError() << "bias has " << bias->dim(0)
+                                                << " entries but b has " << b->dim(1) << " columns";
+    auto& attrs = THREAD_CACHED_MUTABLE_ATTR_MAP("a_rows", "a_cols", "relu");
+    attrs.SetAllAttrs(a_rows, a_cols, relu);
+    return OpInterpUtil::Dispatch<Tensor>(*op_, {a_crow, a_col, a_val, b, bias}, attrs);
+  }
+
+ private:
+  std::shared_ptr<OpExpr> op_;
+};
+
 class SpmmCsrGradBFunctor {
  public:
   SpmmCsrGradBFunctor() {
@@ -121,6 +149,7 @@ class CsrTransposeStructureFunctor {
 
 ONEFLOW_FUNCTION_LIBRARY(m) {
   m.add_functor<impl::SpmmCsrFunctor>("SpmmCsr");
+  m.add_functor<impl::FusedSpmmCsrBiasActFunctor>("FusedSpmmCsrBiasAct");
   m.add_functor<impl::SpmmCsrGradBFunctor>("SpmmCsrGradB");
   m.add_functor<impl::SddmmCsrFunctor>("SddmmCsr");
   m.add_functor<impl::CsrTransposeStructureFunctor>("CsrTransposeStructure");

@@ -84,5 +84,80 @@ class SpmmCsr : public OpExprGradFunction<SpmmCsrCaptureState> {
 
 REGISTER_OP_EXPR_GRAD_FUNCTION("spmm_csr", SpmmCsr);
 
+// ---------------------------------------------------------------- fused_spmm_csr_bias_act
+// out = act(A·b + bias).  With dz = dy ⊙ [out > 0] (ReLU; the mask comes from the saved OUTPUT, as in
+// gradient_funcs/activation.cpp:205 — the pre-activation is never materialised) or dz = dy:
+//   dbias = Σ_rows dz      (gradient_funcs/bias_add.cpp:62: ReduceSum over the non-bias axes)
+//   dval  = sddmm_csr(dz, b)      db = A^T·dz
+// Python mirror: of-spmm_b200/functional.py:_SpmmCsrEpilogueFn.
+struct FusedSpmmCsrBiasActCaptureState : public AutoGradCaptureState {
+  bool val_requires_grad = false, b_requires_grad = false, bias_requires_grad = false;
+  bool relu = false;
+  int64_t a_rows = 0, a_cols = 0;
+  size_t crow_index = 0, col_index = 0, val_index = 0, b_index = 0, out_index = 0;
+  DataType val_dtype = DataType::kInvalidDataType;
+};
+
+class FusedSpmmCsrBiasAct : public OpExprGradFunction<FusedSpmmCsrBiasActCaptureState> {
+ public:
+  Maybe<void> Init(const OpExpr& op) override {
+    const UserOpExpr* fw_op_expr = dynamic_cast<const UserOpExpr*>(&op);
+    CHECK_NOTNULL_OR_RETURN(fw_op_expr);  // NOLINT(maybe-need-error-msg)
+    base_attrs_ = MakeAttrMapFromUserOpConf(fw_op_expr->proto());
+    return Maybe<void>::Ok();
+  }
+
+  // inputs: a_crow, a_col, a_val, b, bias
+  Maybe<void> Capture(FusedSpmmCsrBiasActCaptureState* ctx, const TensorTuple& inputs, const TensorTuple& outputs,
+                      const AttrMap& attrs) const override {
+    CHECK_EQ_OR_RETURN(inputs.size(), 5);  // NOLINT(maybe-need-error-msg)
+    ctx->val_requires_grad = inputs.at(2)->requires_grad();
+    ctx->b_requires_grad = inputs.at(3)->requires_grad();
+    ctx->bias_requires_grad = inputs.at(4)->requires_grad();
+    if (!ctx->val_requires_grad && !ctx->b_requires_grad && !ctx->bias_requires_grad) { return Maybe<void>::Ok(); }
+    ComposedAttrMap composed_attrs(attrs, base_attrs_);
+    ctx->a_rows = JUST(composed_attrs.GetAttr<int64_t>("a_rows"));
+    ctx->a_cols = JUST(composed_attrs.GetAttr<int64_t>("a_cols"));
+    ctx->relu = JUST(composed_attrs.GetAttr<bool>("relu"));
+    ctx->val_dtype = inputs.at(2)->dtype();
+    if (ctx->relu) { ctx->out_index = ctx->SaveTensorForBackward(outputs.at(0)); }
+    if (ctx->val_requires_grad || ctx->b_requires_grad) {
+      ctx->crow_index = ctx->SaveTensorForBackward(inputs.at(0));
+      ctx->col_index = ctx->SaveTensorForBackward(inputs.at(1));
+    }
+    if (ctx->b_requires_grad) { ctx->val_index = ctx->SaveTensorForBackward(inputs.at(2)); }
+    if (ctx->val_requires_grad) { ctx->b_index = ctx->SaveTensorForBackward(inputs.at(3)); }
+    return Maybe<void>::Ok();
+  }
+
+  Maybe<void> Apply(const FusedSpmmCsrBiasActCaptureState* ctx, const TensorTuple& out_grads,
+                    TensorTuple* in_grads) const override {
+    if (!ctx->val_requires_grad && !ctx->b_requires_grad && !ctx->bias_requires_grad) { return Maybe<void>::Ok(); }
+    CHECK_EQ_OR_RETURN(out_grads.size(), 1);  // NOLINT(maybe-need-error-msg)
+    in_grads->resize(5);
+    std::shared_ptr<Tensor> dz = out_grads.at(0);
+    if (ctx->relu) { dz = JUST(functional::ReluGrad(out_grads.at(0), ctx->SavedTensors().at(ctx->out_index))); }
+    if (ctx->bias_requires_grad) { in_grads->at(4) = JUST(functional::ReduceSum(dz, std::vector<int32_t>{0}, false)); }
+    if (ctx->val_requires_grad) {
+      in_grads->at(2) = JUST(functional::SddmmCsr(ctx->SavedTensors().at(ctx->crow_index), ctx->SavedTensors().at(ctx->col_index),
+                                                  dz, ctx->SavedTensors().at(ctx->b_index), ctx->a_rows, ctx->a_cols,
+                                                  ctx->val_dtype));
+    }
+    if (ctx->b_requires_grad) {
+      in_grads->at(3) = JUST(functional::SpmmCsrGradB(ctx->SavedTensors().at(ctx->crow_index),
+                                                      ctx->SavedTensors().at(ctx->col_index),
+                                                      ctx->SavedTensors().at(ctx->val_index), dz, ctx->a_rows, ctx->a_cols,
+                                                      Optional<Tensor>(), Optional<Tensor>(), Optional<Tensor>(),
+                                                      /*atomic=*/false));
+    }
+    return Maybe<void>::Ok();
+  }
+
+ private:
+  AttrMap base_attrs_;
+};
+
+REGISTER_OP_EXPR_GRAD_FUNCTION("fused_spmm_csr_bias_act", FusedSpmmCsrBiasAct);
+
 }  // namespace one
 }  // namespace oneflow

@@ -1,5 +1,5 @@
 // oneflow/user/kernels/spmm_kernels.cpp — REGISTER_USER_KERNEL glue for spmm_csr,
-// spmm_csr_grad_b and sddmm_csr.  Every Compute() body pulls raw pointers /
+// fused_spmm_csr_bias_act, spmm_csr_grad_b, sddmm_csr and csr_transpose_structure.  Every Compute() body pulls raw pointers /
 // shapes / attrs / the cudaStream_t out of the KernelComputeContext and calls the C ABI of
 // libofspmm_b200.so (include/ofspmm.h).  CUDA only: exactly one registered kernel may match a
 // context (oneflow/core/framework/user_op_registry_manager.cpp:93-117), and per the north star
@@ -72,6 +72,33 @@ size_t InferSpmmTmpSize(user_op::InferContext* ctx) {
                                     ctx->InputShape("b", 0).At(1),
                                     static_cast<int>(ctx->InputDType("b", 0)));
 }
+
+// ---------------------------------------------------------------- fused_spmm_csr_bias_act
+// out = act(A·b + bias): the same product with the epilogue bits of ofspmm_opts set — bias and ReLU
+// are applied where a row's complete fp32 sum is stored (merge kernel or fix-up kernel), once.
+class FusedSpmmCsrBiasActKernel final : public user_op::OpKernel, public user_op::CudaGraphSupport {
+ public:
+  FusedSpmmCsrBiasActKernel() = default;
+  ~FusedSpmmCsrBiasActKernel() override = default;
+
+ private:
+  void Compute(user_op::KernelComputeContext* ctx) const override {
+    const user_op::Tensor* val = ctx->Tensor4ArgNameAndIndex("a_val", 0);
+    const user_op::Tensor* b = ctx->Tensor4ArgNameAndIndex("b", 0);
+    const user_op::Tensor* bias = ctx->Tensor4ArgNameAndIndex("bias", 0);
+    user_op::Tensor* out = ctx->Tensor4ArgNameAndIndex("out", 0);
+    user_op::Tensor* tmp = ctx->Tensor4ArgNameAndIndex("tmp_buffer", 0);
+    const ofspmm_csr a = MakeCsr(ctx, val, val->data_type());
+    const int64_t n = b->shape_view().At(1);
+    ofspmm_opts opts{};
+    opts.flags = OFSPMM_FWD_BIAS | (ctx->Attr<bool>("relu") ? OFSPMM_FWD_RELU : 0u);
+    opts.variant = OFSPMM_VARIANT_AUTO;
+    opts.bias = bias->raw_dptr();
+    OFSPMM_CHECK(ofspmm_fwd_ex(&a, b->raw_dptr(), n, out->mut_raw_dptr(), n, n, static_cast<int>(b->data_type()), &opts,
+                               tmp->mut_raw_dptr(), tmp->shape_view().elem_cnt(), StreamOf(ctx)));
+  }
+  bool AlwaysComputeWhenAllOutputsEmpty() const override { return false; }
+};
 
 // ---------------------------------------------------------------- spmm_csr_grad_b
 // db = A^T · dy.  No OpKernelState, no allocation inside Compute, no pointer-keyed cache (round 1
@@ -186,6 +213,12 @@ size_t InferSddmmTmpSize(user_op::InferContext* ctx) {
 #define REGISTER_SPMM_KERNELS(dense_dtype, index_dtype)                                        \
   REGISTER_USER_KERNEL("spmm_csr")                                                             \
       .SetCreateFn<SpmmCsrKernel>()                                                            \
+      .SetIsMatchedHob((user_op::HobDeviceType() == DeviceType::kCUDA)                         \
+                       && (user_op::HobDataType("b", 0) == dense_dtype)                        \
+                       && (user_op::HobDataType("a_col", 0) == index_dtype))                   \
+      .SetInferTmpSizeFn(InferSpmmTmpSize);                                                    \
+  REGISTER_USER_KERNEL("fused_spmm_csr_bias_act")                                              \
+      .SetCreateFn<FusedSpmmCsrBiasActKernel>()                                                \
       .SetIsMatchedHob((user_op::HobDeviceType() == DeviceType::kCUDA)                         \
                        && (user_op::HobDataType("b", 0) == dense_dtype)                        \
                        && (user_op::HobDataType("a_col", 0) == index_dtype))                   \

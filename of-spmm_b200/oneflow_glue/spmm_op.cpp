@@ -1,5 +1,5 @@
-// oneflow/user/ops/spmm_op.cpp — shape / dtype / SBP inference of spmm_csr, spmm_csr_grad_b and
-// sddmm_csr.  Written against the reference's user-op framework; conventions
+// oneflow/user/ops/spmm_op.cpp — shape / dtype / SBP inference of spmm_csr, fused_spmm_csr_bias_act,
+// spmm_csr_grad_b, sddmm_csr and csr_transpose_structure.  Written against the reference's user-op framework; conventions
 // from oneflow/user/ops/matmul_op.cpp:23-138 and unsorted_segment_sum_op.cpp:66-78.
 // The Python mirror with the same checks is of-spmm_b200/ops.py:infer_spmm_csr.
 #include "oneflow/core/framework/framework.h"
@@ -100,6 +100,38 @@ Maybe<void> BilinearSbp(user_op::SbpContext* ctx, const char* dense_in, const ch
 }
 /*static*/ Maybe<void> SpmmCsrOp::ModifyInputArg(const GetInputArgModifier& fn,
                                                  const user_op::UserOpConfWrapper&) {
+  return NoGradForIndices(fn);
+}
+
+// ---------------------------------------------------------------- fused_spmm_csr_bias_act
+// out = act(A·b + bias); same operand checks as spmm_csr plus the bias row.
+/*static*/ Maybe<void> FusedSpmmCsrBiasActOp::InferLogicalTensorDesc(user_op::InferContext* ctx) {
+  JUST(SpmmCsrOp::InferLogicalTensorDesc(ctx));
+  const Shape& bias = ctx->InputShape("bias", 0);
+  CHECK_EQ_OR_RETURN(bias.NumAxes(), 1) << "bias must be 1-D";
+  CHECK_EQ_OR_RETURN(bias.At(0), ctx->InputShape("b", 0).At(1)) << "bias must have one entry per column of b";
+  return Maybe<void>::Ok();
+}
+/*static*/ Maybe<void> FusedSpmmCsrBiasActOp::InferPhysicalTensorDesc(user_op::InferContext* ctx) {
+  return InferLogicalTensorDesc(ctx);
+}
+/*static*/ Maybe<void> FusedSpmmCsrBiasActOp::InferDataType(user_op::InferContext* ctx) {
+  JUST(SpmmCsrOp::InferDataType(ctx));
+  CHECK_EQ_OR_RETURN(ctx->InputDType("bias", 0), ctx->InputDType("b", 0)) << "bias and b must share a dtype";
+  return Maybe<void>::Ok();
+}
+/*static*/ Maybe<void> FusedSpmmCsrBiasActOp::GetSbp(user_op::SbpContext* ctx) {
+  // bias add and ReLU are not linear, so no partial-sum signature survives: only the split of the
+  // dense width (bias split along its only axis) and all-broadcast
+  ctx->NewBuilder()
+      .Broadcast(user_op::OpArg("a_crow", 0)).Broadcast(user_op::OpArg("a_col", 0)).Broadcast(user_op::OpArg("a_val", 0))
+      .Split(user_op::OpArg("b", 0), 1).Split(user_op::OpArg("bias", 0), 0).Split(user_op::OpArg("out", 0), 1)
+      .Build();
+  ctx->NewBuilder().Broadcast(ctx->inputs()).Broadcast(ctx->outputs()).Build();
+  return Maybe<void>::Ok();
+}
+/*static*/ Maybe<void> FusedSpmmCsrBiasActOp::ModifyInputArg(const GetInputArgModifier& fn,
+                                                             const user_op::UserOpConfWrapper&) {
   return NoGradForIndices(fn);
 }
 

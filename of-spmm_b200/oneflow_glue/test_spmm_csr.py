@@ -38,6 +38,29 @@ def _test_spmm_csr_forward_backward(test_case, device, n, index_dtype):
     test_case.assertTrue(crow.grad is None and col.grad is None)
 
 
+def _test_fused_spmm_csr_bias_act(test_case, device, n, relu):
+    rng = np.random.RandomState(11)
+    a = _random_csr(300, 200, 0.05, rng)
+    b_np = rng.randn(200, n).astype(np.float32)
+    bias_np = np.linspace(-0.5, 0.5, n).astype(np.float32)
+    dy_np = rng.rand(300, n).astype(np.float32)
+    crow = flow.tensor(a.indptr.astype(np.int32), device=device)
+    col = flow.tensor(a.indices.astype(np.int32), device=device)
+    val = flow.tensor(a.data, device=device, requires_grad=True)
+    b = flow.tensor(b_np, device=device, requires_grad=True)
+    bias = flow.tensor(bias_np, device=device, requires_grad=True)
+    out = flow._C.fused_spmm_csr_bias_act(crow, col, val, b, bias, 300, 200, relu)
+    pre = a @ b_np + bias_np
+    want = np.maximum(pre, 0) if relu else pre
+    test_case.assertTrue(np.allclose(out.numpy(), want, rtol=1e-4, atol=1e-5))
+    out.backward(flow.tensor(dy_np, device=device))
+    dz = dy_np * (pre > 0) if relu else dy_np
+    rows = np.repeat(np.arange(300), np.diff(a.indptr))
+    test_case.assertTrue(np.allclose(bias.grad.numpy(), dz.sum(0), rtol=1e-4, atol=1e-4))
+    test_case.assertTrue(np.allclose(b.grad.numpy(), a.T @ dz, rtol=1e-4, atol=1e-5))
+    test_case.assertTrue(np.allclose(val.grad.numpy(), np.einsum("ij,ij->i", dz[rows], b_np[a.indices]), rtol=1e-4, atol=1e-5))
+
+
 @flow.unittest.skip_unless_1n1d()
 class TestSpmmCsr(flow.unittest.TestCase):
     def test_spmm_csr(test_case):
@@ -47,6 +70,14 @@ class TestSpmmCsr(flow.unittest.TestCase):
         arg_dict["index_dtype"] = [np.int32, np.int64]
         for arg in GenArgList(arg_dict):
             _test_spmm_csr_forward_backward(test_case, *arg)
+
+    def test_fused_spmm_csr_bias_act(test_case):
+        arg_dict = OrderedDict()
+        arg_dict["device"] = ["cuda"]
+        arg_dict["n"] = [16, 64, 136]
+        arg_dict["relu"] = [False, True]
+        for arg in GenArgList(arg_dict):
+            _test_fused_spmm_csr_bias_act(test_case, *arg)
 
     def test_spmm_csr_shape_error(test_case):
         with test_case.assertRaises(Exception) as ctx:

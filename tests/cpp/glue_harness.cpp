@@ -69,7 +69,7 @@ struct TensorDescs {
   std::map<std::string, Shape> shapes;
   std::map<std::string, DataType> dtypes;
   std::map<std::string, int64_t> attrs;
-  std::map<std::string, bool> battrs{{"atomic", false}};
+  std::map<std::string, bool> battrs{{"atomic", false}, {"relu", false}};
   std::map<std::string, DataType> dattrs{{"val_dtype", kInvalidDataType}};
   std::vector<std::string> present;   // optional inputs that are bound
 };
@@ -195,6 +195,25 @@ void HostChecks() {
   EXPECT(sd.signatures[0].find("dval:P") != std::string::npos);
   EXPECT(sd.signatures.size() == 4 && sd.signatures[1].find("dy:P") != std::string::npos &&
          sd.signatures[2].find("b:P") != std::string::npos);
+  // ---- fused_spmm_csr_bias_act: spmm_csr's checks plus the bias row; no partial-sum signature
+  TensorDescs df = SpmmDescs(300, 200, 1234, 64, kFloat, kInt32);
+  df.shapes["bias"] = Shape({64});
+  df.dtypes["bias"] = kFloat;
+  MockInferContext icf(&df);
+  EXPECT(FusedSpmmCsrBiasActOp::InferLogicalTensorDesc(&icf).IsOk() && df.shapes.at("out") == Shape({300, 64}));
+  EXPECT(FusedSpmmCsrBiasActOp::InferDataType(&icf).IsOk() && df.dtypes.at("out") == kFloat);
+  df.shapes["bias"] = Shape({63});
+  Maybe<void> mf = FusedSpmmCsrBiasActOp::InferLogicalTensorDesc(&icf);
+  EXPECT(!mf.IsOk() && mf.msg().find("one entry per column") != std::string::npos);
+  df.shapes["bias"] = Shape({64});
+  df.dtypes["bias"] = kBFloat16;
+  mf = FusedSpmmCsrBiasActOp::InferDataType(&icf);
+  EXPECT(!mf.IsOk() && mf.msg().find("share a dtype") != std::string::npos);
+  MockSbpContext sf({{"a_crow", 0}, {"a_col", 0}, {"a_val", 0}, {"b", 0}, {"bias", 0}}, {{"out", 0}});
+  EXPECT(FusedSpmmCsrBiasActOp::GetSbp(&sf).IsOk() && sf.signatures.size() == 2);
+  EXPECT(sf.signatures[0].find("b:S(1)") != std::string::npos && sf.signatures[0].find("bias:S(0)") != std::string::npos &&
+         sf.signatures[0].find("out:S(1)") != std::string::npos && sf.signatures[0].find("a_val:B") != std::string::npos);
+  for (const auto& sig : sf.signatures) EXPECT(sig.find(":P") == std::string::npos);   // bias / ReLU are not linear
   // ---- index inputs never require grad (ModifyInputArg)
   std::map<std::string, user_op::InputArgModifier> mods;
   auto getter = [&](const std::string& n, int32_t) { return &mods[n]; };
@@ -202,7 +221,7 @@ void HostChecks() {
   EXPECT(!mods["a_crow"].requires_grad() && !mods["a_col"].requires_grad());
   // ---- registry: exactly one kernel per (CUDA, dense dtype, index dtype); none for CPU
   int matches = 0;
-  for (const char* op : {"spmm_csr", "spmm_csr_grad_b", "sddmm_csr"}) {
+  for (const char* op : {"spmm_csr", "fused_spmm_csr_bias_act", "spmm_csr_grad_b", "sddmm_csr"}) {
     const char* dense_arg = std::string(op) == "spmm_csr_grad_b" ? "dy" : "b";
     for (DataType dense : {kFloat, kBFloat16})
       for (DataType idx : {kInt32, kInt64}) {
@@ -222,6 +241,8 @@ void HostChecks() {
   TensorDescs d2 = SpmmDescs(300, 200, 1234, 64, kFloat, kInt32);
   MockInferContext ic2(&d2);
   EXPECT(reg->infer_tmp_size(&ic2) == ofspmm_fwd_workspace_bytes(300, 200, 1234, 64, OFSPMM_DTYPE_FLOAT));
+  EXPECT(FindKernel("fused_spmm_csr_bias_act", q, &matches)->infer_tmp_size(&ic2) ==
+         ofspmm_fwd_ex_workspace_bytes(300, 200, 1234, 64, OFSPMM_DTYPE_FLOAT, OFSPMM_VARIANT_AUTO));
   // spmm_csr_grad_b: the route decides the tmp size — transient (default), atomic, cached structure
   user_op::KernelMatchQuery qg{DeviceType::kCUDA, {{"dy", kFloat}, {"a_col", kInt32}}};
   const auto* regg = FindKernel("spmm_csr_grad_b", qg, &matches);
@@ -309,6 +330,49 @@ void AutogradChecks() {
   EXPECT(saved == 3 && log.size() == 1 && log[0].op == "sddmm_csr" && ig[2] != nullptr && ig[3] == nullptr);
   // nothing requires grad: nothing saved, nothing dispatched
   saved = run_case(false, false, &ig);
+  EXPECT(saved == 0 && log.empty());
+  // ---- fused_spmm_csr_bias_act: functor and grad function
+  auto bias = T("bias", {64}, true);
+  log.clear();
+  out = one::functional::FusedSpmmCsrBiasAct(crow, col, T("val", {1234}, true), T("b", {200, 64}, true), bias, 300, 200, true);
+  EXPECT(out.IsOk() && log.size() == 1 && log[0].op == "fused_spmm_csr_bias_act");
+  EXPECT((log[0].inputs == std::vector<std::string>{"crow", "col", "val", "b", "bias"}) && log[0].attrs.at("relu") == 1);
+  bad = one::functional::FusedSpmmCsrBiasAct(crow, col, T("val", {1234}, true), T("b", {200, 64}, true), T("bias", {63}, true), 300, 200);
+  EXPECT(!bad.IsOk() && bad.msg().find("63 entries") != std::string::npos);
+  EXPECT(one::GradFunctionRegistry().count("fused_spmm_csr_bias_act") == 1);
+  auto run_fused = [&](bool val_rg, bool b_rg, bool bias_rg, bool relu, one::TensorTuple* in_grads) {
+    one::UserOpExpr ff;
+    ff.op_type_name = "fused_spmm_csr_bias_act";
+    ff.proto_.attrs.ints = {{"a_rows", 300}, {"a_cols", 200}, {"relu", relu ? 1 : 0}};
+    std::unique_ptr<one::OpExprGradFunctionIf> g(one::GradFunctionRegistry().at("fused_spmm_csr_bias_act")());
+    EXPECT(g->Init(ff).IsOk());
+    auto state = g->MakeCustomState();
+    one::TensorTuple inputs = {crow, col, T("val", {1234}, val_rg), T("b", {200, 64}, b_rg), T("bias", {64}, bias_rg)};
+    one::TensorTuple outputs = {T("out", {300, 64}, val_rg || b_rg || bias_rg)};
+    EXPECT(g->CaptureIf(state.get(), inputs, outputs, AttrMap()).IsOk());
+    log.clear();
+    in_grads->assign(5, nullptr);
+    EXPECT(g->ApplyIf(state.get(), {T("dy", {300, 64}, false)}, in_grads).IsOk());
+    return state->SavedTensors().size();
+  };
+  // everything needs grad, ReLU on: mask from the saved output, then bias / values / dense gradients of dz
+  saved = run_fused(true, true, true, true, &ig);
+  EXPECT(saved == 5 && log.size() == 4);
+  EXPECT(log[0].op == "relu_grad" && (log[0].inputs == std::vector<std::string>{"dy", "out"}));
+  EXPECT(log[1].op == "reduce_sum" && (log[1].inputs == std::vector<std::string>{"relu_grad:dx"}) && log[1].attrs.at("axis0") == 0 &&
+         log[1].attrs.at("keepdims") == 0);
+  EXPECT(log[2].op == "sddmm_csr" && (log[2].inputs == std::vector<std::string>{"crow", "col", "relu_grad:dx", "b"}));
+  EXPECT(log[3].op == "spmm_csr_grad_b" && (log[3].inputs == std::vector<std::string>{"crow", "col", "val", "relu_grad:dx"}));
+  EXPECT(ig[0] == nullptr && ig[1] == nullptr && ig[2] != nullptr && ig[3] != nullptr && ig[4] != nullptr);
+  // no activation: dy goes straight through, the output is not saved
+  saved = run_fused(true, true, true, false, &ig);
+  EXPECT(saved == 4 && log.size() == 3 && log[0].op == "reduce_sum" && (log[0].inputs == std::vector<std::string>{"dy"}));
+  EXPECT((log[2].inputs == std::vector<std::string>{"crow", "col", "val", "dy"}));
+  // only the bias: one reduction, no sparse kernel, no CSR saved
+  saved = run_fused(false, false, true, true, &ig);
+  EXPECT(saved == 1 && log.size() == 2 && log[1].op == "reduce_sum" && ig[2] == nullptr && ig[3] == nullptr && ig[4] != nullptr);
+  // nothing requires grad
+  saved = run_fused(false, false, false, true, &ig);
   EXPECT(saved == 0 && log.empty());
   std::printf("glue autograd checks ok: functors + OpExprGradFunction dispatch as specified\n");
 }

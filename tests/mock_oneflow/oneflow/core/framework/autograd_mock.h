@@ -208,6 +208,23 @@ inline Maybe<Tensor> SddmmCsr(const TensorPtr& crow, const TensorPtr& col, const
   return CallFunctor<Maybe<Tensor>, const TensorPtr&, const TensorPtr&, const TensorPtr&, const TensorPtr&, const int64_t&,
                      const int64_t&, const DataType&>("SddmmCsr", crow, col, dy, b, rows, cols, val_dtype);
 }
+inline Maybe<Tensor> FusedSpmmCsrBiasAct(const TensorPtr& crow, const TensorPtr& col, const TensorPtr& val, const TensorPtr& b,
+                                         const TensorPtr& bias, const int64_t& rows, const int64_t& cols, const bool& relu = false) {
+  return CallFunctor<Maybe<Tensor>, const TensorPtr&, const TensorPtr&, const TensorPtr&, const TensorPtr&, const TensorPtr&,
+                     const int64_t&, const int64_t&, const bool&>("FusedSpmmCsrBiasAct", crow, col, val, b, bias, rows, cols, relu);
+}
+// two functions of the reference's own library the fused op's grad function calls
+// (functional_api.yaml:295-298 "reduce_sum", :547-549 "relu_grad"); here they only log the dispatch
+inline Maybe<Tensor> ReluGrad(const TensorPtr& dy, const TensorPtr& y) {
+  DispatchLog().push_back(DispatchRecord{"relu_grad", {dy->name(), y->name()}, {}});
+  return std::make_shared<Tensor>("relu_grad:dx", std::vector<int64_t>{}, false);
+}
+inline Maybe<Tensor> ReduceSum(const TensorPtr& x, const std::vector<int32_t>& axis, const bool& keepdims) {
+  std::map<std::string, int64_t> attrs{{"keepdims", keepdims ? 1 : 0}};
+  for (size_t i = 0; i < axis.size(); ++i) attrs["axis" + std::to_string(i)] = axis[i];
+  DispatchLog().push_back(DispatchRecord{"reduce_sum", {x->name()}, attrs});
+  return std::make_shared<Tensor>("reduce_sum:y", std::vector<int64_t>{}, false);
+}
 inline Maybe<TensorTuple> CsrTransposeStructure(const TensorPtr& crow, const TensorPtr& col, const int64_t& rows,
                                                 const int64_t& cols) {
   return CallFunctor<Maybe<TensorTuple>, const TensorPtr&, const TensorPtr&, const int64_t&, const int64_t&>(

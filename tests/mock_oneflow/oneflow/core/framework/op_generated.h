@@ -16,5 +16,6 @@ OF_MOCK_DECLARE_OP(SpmmCsrOp)
 OF_MOCK_DECLARE_OP(SpmmCsrGradBOp)
 OF_MOCK_DECLARE_OP(SddmmCsrOp)
 OF_MOCK_DECLARE_OP(CsrTransposeStructureOp)
+OF_MOCK_DECLARE_OP(FusedSpmmCsrBiasActOp)
 #undef OF_MOCK_DECLARE_OP
 }  // namespace oneflow

@@ -31,7 +31,7 @@ def _build(tmp_path):
 def test_glue_compiles_and_host_side_behaves(tmp_path):
     out = subprocess.run([_build(tmp_path), "host"], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout + out.stderr
-    assert "glue host checks ok: 14 kernel registrations" in out.stdout
+    assert "glue host checks ok: 18 kernel registrations" in out.stdout
     assert "glue autograd checks ok" in out.stdout          # functors + OpExprGradFunction
 
 
