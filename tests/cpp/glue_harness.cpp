@@ -516,6 +516,20 @@ void GpuChecks() {
   t_out.ToHost(got.data());
   EXPECT(max_err(got, C) < 2e-5);
 
+  // fused_spmm_csr_bias_act: out = relu(A·b + bias) in one pass (the mock context answers every bool
+  // attr with its `atomic` member, so atomic = true here means relu = true)
+  std::vector<float> bias(N);
+  for (int64_t j = 0; j < N; ++j) bias[j] = 0.03f * static_cast<float>(j) - 1.f;
+  DevTensor t_bias(Shape({N}), kFloat, bias.data(), bias.size() * 4);
+  DevTensor t_fused(Shape({M, N}), kFloat, nullptr, C.size() * 4);
+  run("fused_spmm_csr_bias_act", "b", {{"a_crow", &t_crow}, {"a_col", &t_col}, {"a_val", &t_val}, {"b", &t_b}, {"bias", &t_bias},
+                                      {"out", &t_fused}}, 1, /*relu=*/true);
+  std::vector<double> Cf(C.size());
+  for (int64_t i = 0; i < M; ++i)
+    for (int64_t j = 0; j < N; ++j) Cf[i * N + j] = std::max(0.0, C[i * N + j] + static_cast<double>(bias[j]));
+  t_fused.ToHost(got.data());
+  EXPECT(max_err(got, Cf) < 2e-5);
+
   run("spmm_csr_grad_b", "dy", {{"a_crow", &t_crow}, {"a_col", &t_col}, {"a_val", &t_val}, {"dy", &t_dy}, {"db", &t_db}}, 2);
   got.resize(dB.size());
   t_db.ToHost(got.data());
@@ -551,7 +565,7 @@ void GpuChecks() {
   t_dval.ToHost(got.data());
   EXPECT(max_err(got, dval) < 2e-5);
   CUDA_OK(cudaStreamDestroy(cs));
-  std::printf("glue gpu checks ok: spmm_csr / spmm_csr_grad_b / sddmm_csr through OpKernel::Compute, "
+  std::printf("glue gpu checks ok: spmm_csr / fused_spmm_csr_bias_act / spmm_csr_grad_b / sddmm_csr through OpKernel::Compute, "
               "%llu library launches\n", static_cast<unsigned long long>(ofspmm_launch_count()));
 }
 
